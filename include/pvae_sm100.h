@@ -1,0 +1,160 @@
+/* pvae_sm100.h -- C ABI of libpvae_sm100.so, the B200 (sm_100a) implementation of the PhysicsVAE training hot path.
+ *
+ * The reference (facebookresearch/PhysicsVAE) has no FFI: the path sits behind two Python plugin APIs
+ * (RLlib custom model `PhysicsVAE`, rllib_model_torch.py:461-950; Ray Tune `Trainable`, torch_models.py:109-216 and
+ * train_physics_vae.py:313-467).  Each entry point below names the reference code it replaces; the Python package
+ * `physicsvae_b200` binds them with ctypes (physicsvae_b200/_abi.py) and mirrors the reference's classes on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative pvae_status otherwise; the message is in pvae_last_error();
+ *     nothing throws across the ABI.
+ *   - all pointers named *_dev are device pointers owned by the caller (PyTorch's caching allocator); the library
+ *     allocates only its handle, bf16 shadow weights, TMA descriptors and a few scalars, and frees them in pvae_destroy.
+ *   - all work is enqueued on the given stream, never synchronises, never allocates after pvae_plan(): every step
+ *     entry point is CUDA-graph capturable.
+ *   - a handle is not thread-safe; distinct handles are independent (one per process / GPU).
+ *   - fp32 parameters / gradients use the reference's nn.Linear layout: W[out][in] row-major, b[out].
+ */
+#ifndef PVAE_SM100_H
+#define PVAE_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVAE_ABI_VERSION 1
+#define PVAE_MAX_LAYERS 8
+
+typedef struct pvae_engine* pvae_handle;
+typedef void* pvae_stream;                 /* cudaStream_t */
+
+enum pvae_status {
+  PVAE_OK = 0,
+  PVAE_ERR_INVALID = -1,                   /* bad argument / unsupported configuration */
+  PVAE_ERR_CUDA = -2,                      /* a CUDA runtime / driver call failed */
+  PVAE_ERR_STATE = -3                      /* call order violated (not planned / not bound) */
+};
+
+/* activation registry of the reference: get_activation_fn, rllib_model_torch.py:30-46 */
+enum pvae_act { PVAE_ACT_LINEAR = 0, PVAE_ACT_RELU = 1, PVAE_ACT_TANH = 2, PVAE_ACT_SIGMOID = 3, PVAE_ACT_ELU = 4, PVAE_ACT_SWISH = 5 };
+
+/* arithmetic of the tensor-core contractions */
+enum pvae_precision {
+  PVAE_PREC_BF16 = 1,                      /* bf16 operands, fp32 accumulate (performance mode) */
+  PVAE_PREC_BF16X3 = 3                     /* hi/lo split bf16, 3 products, fp32 accumulate: matches fp32 to ~1e-6 (parity mode) */
+};
+
+/* the four MLPs of PhysicsVAE (rllib_model_torch.py:638-699) */
+enum pvae_net { PVAE_NET_TASK_ENCODER = 0, PVAE_NET_MOTOR_DECODER = 1, PVAE_NET_WORLD_MODEL = 2, PVAE_NET_VALUE_BRANCH = 3, PVAE_NUM_NETS = 4 };
+
+/* one FC stack: rllib_model_torch.FC (rllib_model_torch.py:234-282); the input width is implied by the net's role */
+typedef struct {
+  int32_t n_layers;                        /* number of Linear layers (hidden + output); 0 = net absent */
+  int32_t out_dims[PVAE_MAX_LAYERS];       /* nn.Linear out_features per layer */
+  int32_t acts[PVAE_MAX_LAYERS];           /* pvae_act per layer */
+} pvae_net_desc;
+
+/* PhysicsVAE.__init__ (rllib_model_torch.py:511-727), default wiring: encoder sees (body, task), decoder sees (body, z) */
+typedef struct {
+  int32_t dim_state_body;                  /* dsb; dim_state_task == dsb on this path (train_physics_vae.py:198-214) */
+  int32_t dim_action;                      /* da */
+  int32_t latent_dim;                      /* z  (task_encoder_output_dim) */
+  int32_t latent_prior;                    /* 1 = "normal_zero_mean_one_std" (encoder emits 2z), 0 = False (encoder emits z) */
+  int32_t precision;                       /* pvae_precision */
+  int32_t max_batch;                       /* capacity of the workspace in rows */
+  pvae_net_desc nets[PVAE_NUM_NETS];
+} pvae_model_desc;
+
+/* loss bookkeeping written by the step functions (device, fp32):
+ *   [0] total  [1] MSE(a, a_hat)  [2] KL  [3] MSE(s2, world(s1, a_gt))  [4] MSE(s2, world(s1, a_hat))
+ * weights as in train_physics_vae.py:430-434 */
+#define PVAE_LOSS_SLOTS 8
+
+const char* pvae_last_error(void);
+int pvae_abi_version(void);
+
+/* --- lifetime ------------------------------------------------------------------------------------------------ */
+/* replaces: PhysicsVAE.__init__ network construction (rllib_model_torch.py:638-699) */
+int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device);
+int pvae_destroy(pvae_handle h);
+
+/* fp32 master parameters of one net and its flat gradient buffer.
+ * W_dev[l] / b_dev[l]: nn.Linear weight/bias of layer l.  grad_flat_dev: [dW0 | db0 | dW1 | db1 | ...] (may be NULL for
+ * nets that are never trained).  replaces: model.parameters() / .grad consumed by torch.optim.Adam (torch_models.py:119-122) */
+int pvae_bind_net(pvae_handle h, int net, const float* const* W_dev, const float* const* b_dev, float* grad_flat_dev);
+int64_t pvae_net_grad_elems(pvae_handle h, int net);
+
+/* refresh the bf16 (hi/lo) shadow copies of the fp32 masters of every net whose bit is set in net_mask
+ * (after load_state_dict or optimizer.step()).  */
+int pvae_sync_weights(pvae_handle h, uint32_t net_mask, pvae_stream s);
+
+/* --- workspace ----------------------------------------------------------------------------------------------- */
+int pvae_workspace_bytes(pvae_handle h, size_t* bytes);
+int pvae_bind_workspace(pvae_handle h, void* ws_dev, size_t bytes);
+
+/* --- transition buffers -------------------------------------------------------------------------------------- */
+/* Resident transition buffer = the reference's DatasetBase.X / .Y (torch_models.py:39-58; built by
+ * load_dataset_for_PhysicsVAE, train_physics_vae.py:117-164) converted once to bf16 hi(/lo) planes:
+ *   x: [n_rows][2*dsb]  (s_t | s_{t+1}),  y: [n_rows][da].
+ * pvae_ingest converts rows [0, n_rows) of the raw arrays (x_raw_dev: float64 if x_is_f64 else float32, row stride
+ * 2*dsb; y_raw_dev: float32, row stride da) into rows [dst_row, dst_row + n_rows) of buf_dev.
+ * replaces: DatasetBase.__getitem__ + default collate (torch.Tensor(x) per item, torch_models.py:52-68). */
+int pvae_transitions_bytes(pvae_handle h, int64_t n_rows, size_t* bytes);
+int pvae_ingest(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t dst_row, const void* x_raw_dev, int x_is_f64,
+                const float* y_raw_dev, int64_t n_rows, pvae_stream s);
+/* select the buffer the step functions read from; mini-batch b = rows [cursor, cursor + batch) */
+int pvae_bind_transitions(pvae_handle h, const void* buf_dev, int64_t buf_rows);
+int pvae_set_cursor(pvae_handle h, int64_t row, pvae_stream s);
+/* cursor += delta; if cursor + batch > limit then cursor = 0  (device-side, graph-replayable) */
+int pvae_advance_cursor(pvae_handle h, int64_t delta, int64_t batch, int64_t limit, pvae_stream s);
+
+/* --- the training steps (forward + loss + backward; gradients land in the bound grad buffers) ------------------ */
+/* World-model phase: loss = s_coeff * MSE(s2, WM(cat[s1, a_gt])); gradients for the world model only.
+ * replaces: TrainModel.compute_loss world branch + loss.backward() (train_physics_vae.py:412-414; torch_models.py:141-142).
+ * The reference's discarded full-model forward (train_physics_vae.py:377-378) is not executed. */
+int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pvae_stream s);
+
+/* VAE phase: loss = a_coeff*MSE(a_gt, a_hat) + kl_coeff*KL + cyc_coeff*MSE(s2, WM(cat[s1, a_hat])), gradients for task
+ * encoder + motor decoder, world model differentiated through but frozen.
+ * eps_dev: [batch][z] fp32 standard-normal noise (the reference draws it with torch.randn_like, rllib_model_torch.py:737);
+ * if NULL, a Philox4x32-10 stream keyed by (seed, offset) is generated in-kernel.  noise == 0: z = mu
+ * (PhysicsVAE.latent_prior_noise False, rllib_model_torch.py:734-740).
+ * replaces: TrainModel.compute_loss VAE branch + backward (train_physics_vae.py:377-434). */
+int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
+                  float kl_coeff, float cyc_coeff, float* loss_dev, pvae_stream s);
+
+/* --- inference API ------------------------------------------------------------------------------------------- */
+/* PhysicsVAE.forward and its parts (rllib_model_torch.py:742-853).  obs_dev: fp32 [batch][2*dsb] (row stride obs_ld).
+ * parts: bit 0 encoder (+reparameterise), bit 1 decoder, bit 2 world, bit 3 value branch.
+ * Inputs consumed only when the producing part is not run: z_in_dev ([batch][z], decoder without encoder),
+ * act_in_dev ([batch][da], world without decoder).  eps_dev NULL + noise=0 -> z = mu (latent_prior_noise False).
+ * Outputs (each may be NULL): act_out [batch][da] (the first half of `logits`; AppendLogStd's constant half is
+ * bookkeeping done by the caller), mu/logvar/z [batch][z], future [batch][dsb], value [batch]. */
+#define PVAE_PART_ENCODER 1u
+#define PVAE_PART_DECODER 2u
+#define PVAE_PART_WORLD 4u
+#define PVAE_PART_VALUE 8u
+int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev, int64_t obs_ld, const float* z_in_dev,
+                 const float* act_in_dev, int64_t act_in_ld, const float* eps_dev, int noise, uint64_t seed,
+                 uint64_t offset, float* act_out_dev, int64_t act_out_ld, float* mu_dev, float* logvar_dev, float* z_dev,
+                 float* future_dev, float* value_dev, pvae_stream s);
+
+/* --- kernel-level entry (unit tests, bench roofline) ----------------------------------------------------------- */
+/* D[M][N] (fp32, row-major) = A . B^T on the tcgen05 path.
+ *   a_major 0: A is [M][K] row-major (ld K);  1: A is [K][M] row-major (ld M)
+ *   b_major 0: B is [N][K] row-major;         1: B is [K][N] row-major
+ * planes 1: bf16 operands; 2: operands are hi plane followed by lo plane, bf16x3 products.
+ * splits > 1 splits K over CTAs and accumulates with red.global.add (D must be zeroed by the caller). */
+int pvae_gemm_bf16(const void* A_dev, int a_major, const void* B_dev, int b_major, int M, int N, int K, int planes,
+                   int splits, float* D_dev, pvae_stream s);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t pvae_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVAE_SM100_H */

@@ -1,0 +1,188 @@
+// pvae_aux.cuh -- the small HBM-bound kernels around the tensor-core GEMM:
+//   ingest          raw transition arrays (f64/f32) -> resident bf16 hi(/lo) planes, vectorised + coalesced
+//   sync_weights    fp32 nn.Linear masters -> K-padded bf16 hi(/lo) shadow operands
+//   reparam_fwd     z = mu + eps * exp(0.5 logvar), KL partial sums          (rllib_model_torch.py:734-740,
+//                                                                              train_physics_vae.py:384-389)
+//   reparam_bwd     d(mu|logvar) from dz and the KL term, bias-grad column sums
+//   finalize_loss   the weighted sum of train_physics_vae.py:430-434
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace pvae {
+
+__device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+// ---- ingest: one thread per (row, 2 columns) pair; rows are contiguous so warps read/write whole lines ------
+template <typename SrcT>
+__global__ void ingest_kernel(const SrcT* __restrict__ src, int64_t src_ld, int width, __nv_bfloat16* __restrict__ dst,
+                              int64_t dst_ld, int64_t dst_ps, int planes, int64_t n_rows) {
+  const int64_t pairs_per_row = dst_ld >> 1;   // dst_ld is a multiple of 8
+  const int64_t total = n_rows * pairs_per_row;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / pairs_per_row;
+    const int c = (int)(i - r * pairs_per_row) * 2;
+    const float v0 = (c < width) ? (float)src[r * src_ld + c] : 0.f;
+    const float v1 = (c + 1 < width) ? (float)src[r * src_ld + c + 1] : 0.f;
+    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    *reinterpret_cast<__nv_bfloat162*>(dst + r * dst_ld + c) = h;
+    if (planes > 1) {
+      __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __low2float(h), v1 - __high2float(h));
+      *reinterpret_cast<__nv_bfloat162*>(dst + dst_ps + r * dst_ld + c) = l;
+    }
+  }
+}
+
+// ---- shadow weights: Wsh[plane][out][Kpad]; columns [0,K0pad) <- W[:, 0:k0], [K0pad, K0pad+K1pad) <- W[:, k0:k0+k1]
+__global__ void sync_weights_kernel(const float* __restrict__ W, int out, int in, int k0, int k1, int K0pad, int Kpad,
+                                    __nv_bfloat16* __restrict__ Wsh, int64_t ps, int planes) {
+  const int64_t total = (int64_t)out * Kpad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i / Kpad);
+    const int c = (int)(i - (int64_t)o * Kpad);
+    int src_c = -1;
+    if (c < K0pad) { if (c < k0) src_c = c; }
+    else { const int j = c - K0pad; if (j < k1) src_c = k0 + j; }
+    const float v = (src_c >= 0) ? W[(int64_t)o * in + src_c] : 0.f;
+    const __nv_bfloat16 h = f2bf(v);
+    Wsh[i] = h;
+    if (planes > 1) Wsh[ps + i] = f2bf(v - __bfloat162float(h));
+  }
+}
+
+// ---- Philox4x32-10 + Box-Muller: counter-based N(0,1) stream for the (seed, offset) noise mode ----------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t offset, uint64_t idx) {
+  uint32_t c[4] = {(uint32_t)(idx >> 1), (uint32_t)(idx >> 33), (uint32_t)offset, (uint32_t)(offset >> 32)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u1 = ((float)c[0] + 0.5f) * 2.3283064365386963e-10f;   // (0,1)
+  const float u2 = ((float)c[1] + 0.5f) * 2.3283064365386963e-10f;
+  const float rad = sqrtf(-2.f * __logf(u1));
+  float s, co;
+  __sincosf(6.283185307179586f * u2, &s, &co);
+  return (idx & 1) ? rad * s : rad * co;
+}
+
+// ---- reparameterise + KL.  ml: [B][w] fp32, w = 2z (mu | logvar) with a prior, z without.  One thread per (row, latent)
+__global__ void reparam_fwd_kernel(const float* __restrict__ ml, const float* __restrict__ eps_in, float* __restrict__ eps_out,
+                                   int has_lv, int noise, uint64_t seed, uint64_t offset, int B, int z,
+                                   __nv_bfloat16* __restrict__ zb, int64_t z_ld, int64_t z_ps, int planes,
+                                   float* __restrict__ z_f32, float* __restrict__ mu_out, float* __restrict__ lv_out,
+                                   double* __restrict__ kl_acc) {
+  const int64_t total = (int64_t)B * z;
+  const int w = has_lv ? 2 * z : z;
+  float kl = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / z), d = (int)(i - (int64_t)r * z);
+    const float mu = ml[(int64_t)r * w + d];
+    const float lv = has_lv ? ml[(int64_t)r * w + z + d] : 0.f;
+    float zt = mu;
+    if (noise) {
+      const float e = eps_in ? eps_in[i] : philox_normal(seed, offset, (uint64_t)i);
+      if (eps_out) eps_out[i] = e;
+      zt = mu + e * expf(0.5f * lv);
+    }
+    const __nv_bfloat16 h = f2bf(zt);
+    zb[(int64_t)r * z_ld + d] = h;
+    if (planes > 1) zb[z_ps + (int64_t)r * z_ld + d] = f2bf(zt - __bfloat162float(h));
+    if (z_f32) z_f32[i] = zt;
+    if (mu_out) mu_out[i] = mu;
+    if (lv_out) lv_out[i] = lv;
+    kl += -0.5f * (1.f + lv - mu * mu - expf(lv));
+  }
+  if (kl_acc) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, off);
+    __shared__ float part[32];
+    const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) part[wi] = kl;
+    __syncthreads();
+    if (wi == 0) {
+      float t = (l < (int)(blockDim.x >> 5)) ? part[l] : 0.f;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      if (l == 0) atomicAdd(kl_acc, (double)t);
+    }
+  }
+}
+
+// ---- backward of reparameterise + KL.  dml[B][w] = (dmu | dlogvar);  colsum -> bias grad of the encoder's last layer
+//   dmu = dz + kl_scale*mu ; dlogvar = dz*eps*0.5*exp(0.5 lv) + kl_scale*0.5*(exp(lv)-1),  kl_scale = kl_coeff / B
+// without a prior (has_lv == 0) the encoder output IS z: dml = dz.
+// blockDim.x == w * rows_per_block, thread t -> column t % w
+__global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ ml, const float* __restrict__ eps,
+                                   int has_lv, int noise, float kl_scale, int B, int z, __nv_bfloat16* __restrict__ dml,
+                                   int64_t ld, int64_t ps, int planes, float* __restrict__ colsum) {
+  const int w2 = has_lv ? 2 * z : z;
+  const int col = threadIdx.x % w2;
+  const int rsub = threadIdx.x / w2;
+  const int rows_per_block = blockDim.x / w2;
+  float acc = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_block + rsub; r < B; r += (int64_t)gridDim.x * rows_per_block) {
+    const int d = (col < z) ? col : col - z;
+    const float g = dz[r * z + d];
+    float v;
+    if (!has_lv) {
+      v = g;
+    } else {
+      const float mu = ml[r * w2 + d];
+      const float lv = ml[r * w2 + z + d];
+      if (col < z) v = g + kl_scale * mu;
+      else v = (noise ? g * eps[r * z + d] * 0.5f * expf(0.5f * lv) : 0.f) + kl_scale * 0.5f * (expf(lv) - 1.f);
+    }
+    const __nv_bfloat16 h = f2bf(v);
+    dml[r * ld + col] = h;
+    if (planes > 1) dml[ps + r * ld + col] = f2bf(v - __bfloat162float(h));
+    acc += v;
+  }
+  if (colsum) atomicAdd(colsum + col, acc);
+}
+
+// ---- fp32 [B][w] -> bf16 planes (decoder / world inputs handed in by the inference API) -------------------------
+__global__ void f32_to_planes_kernel(const float* __restrict__ src, int64_t src_ld, int width, __nv_bfloat16* __restrict__ dst,
+                                     int64_t dst_ld, int64_t dst_ps, int planes, int64_t n_rows) {
+  const int64_t total = n_rows * dst_ld;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dst_ld;
+    const int c = (int)(i - r * dst_ld);
+    const float v = (c < width) ? src[r * src_ld + c] : 0.f;
+    const __nv_bfloat16 h = f2bf(v);
+    dst[i] = h;
+    if (planes > 1) dst[dst_ps + i] = f2bf(v - __bfloat162float(h));
+  }
+}
+
+// ---- loss bookkeeping ---------------------------------------------------------------------------------------------
+// acc: [0] sum sq a, [1] sum kl, [2] sum sq s (world), [3] sum sq cyc
+__global__ void finalize_loss_kernel(const double* __restrict__ acc, float* __restrict__ loss, int B, int da, int dsb,
+                                     float a_c, float kl_c, float s_c, float cyc_c) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float la = (float)(acc[0] / ((double)B * da));
+    const float lk = (float)(acc[1] / (double)B);
+    const float ls = (float)(acc[2] / ((double)B * dsb));
+    const float lc = (float)(acc[3] / ((double)B * dsb));
+    loss[1] = la; loss[2] = lk; loss[3] = ls; loss[4] = lc;
+    loss[0] = a_c * la + kl_c * lk + s_c * ls + cyc_c * lc;
+  }
+}
+
+__global__ void set_cursor_kernel(int32_t* cur, int32_t v) { if (threadIdx.x == 0) *cur = v; }
+__global__ void advance_cursor_kernel(int32_t* cur, int32_t delta, int32_t batch, int32_t limit) {
+  if (threadIdx.x == 0) {
+    int32_t c = *cur + delta;
+    if (c + batch > limit) c = 0;
+    *cur = c;
+  }
+}
+
+}  // namespace pvae

@@ -1,0 +1,866 @@
+// pvae_engine.cu -- host side of libpvae_sm100.so: the C ABI declared in include/pvae_sm100.h.
+//
+// The engine owns no tensors besides bf16 shadow weights and a few scalars.  Every step entry point turns the
+// reference's Python control flow (TrainModel.compute_loss, train_physics_vae.py:361-435; PhysicsVAE.forward*,
+// rllib_model_torch.py:742-853; autograd of both, torch_models.py:142) into a fixed sequence of launches of the single
+// tcgen05 GEMM kernel in pvae_gemm.cuh with different operand views / epilogues, plus the few elementwise kernels of
+// pvae_aux.cuh.  Nothing here synchronises or allocates, so a step can be captured into a CUDA graph.
+#include "../../include/pvae_sm100.h"
+#include "pvae_gemm.cuh"
+#include "pvae_aux.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace pvae {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(PVAE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKR(call)                  \
+  do {                             \
+    int r_ = (call);               \
+    if (r_ != PVAE_OK) return r_;  \
+  } while (0)
+
+static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- driver entry point for tensor-map encoding (resolved at run time: the library must load on a box without libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int resolve_driver() {
+  if (g_encode) return PVAE_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
+    return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver (%s)", cudaGetErrorString(e));
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return PVAE_OK;
+}
+
+// A 2-D bf16 matrix (one or two precision planes) somewhere in device memory.
+struct View {
+  const __nv_bfloat16* base = nullptr;
+  int64_t ld = 0;       // row stride, elements (multiple of 8)
+  int64_t ps = 0;       // plane stride, elements
+  int planes = 1;
+  int width = 0;        // valid columns
+  int64_t rows = 0;     // valid rows
+  int dyn = 0;          // add the device-side row cursor to row coordinates
+};
+
+static int encode_map(CUtensorMap* m, const View& v, int box_cols, int box_rows) {
+  if ((reinterpret_cast<uintptr_t>(v.base) & 15) != 0) return fail(PVAE_ERR_INVALID, "operand base %p is not 16-byte aligned", (const void*)v.base);
+  if ((v.ld & 7) != 0) return fail(PVAE_ERR_INVALID, "operand row stride %lld is not a multiple of 8 elements", (long long)v.ld);
+  if (v.planes > 1 && (v.ps & 7) != 0) return fail(PVAE_ERR_INVALID, "operand plane stride %lld is not a multiple of 8 elements", (long long)v.ps);
+  if (v.width <= 0 || v.rows <= 0) return fail(PVAE_ERR_INVALID, "empty operand (%d x %lld)", v.width, (long long)v.rows);
+  cuuint64_t dims[3] = {(cuuint64_t)v.width, (cuuint64_t)v.rows, (cuuint64_t)v.planes};
+  cuuint64_t strides[2] = {(cuuint64_t)v.ld * 2, (cuuint64_t)(v.planes > 1 ? v.ps : v.ld * v.rows) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(v.base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d x %lld x %d, ld %lld, box %d x %d", (int)r, v.width,
+                (long long)v.rows, v.planes, (long long)v.ld, box_cols, box_rows);
+  return PVAE_OK;
+}
+
+// One GEMM launch, described on the host.
+struct GemmDesc {
+  View A[2];
+  int nseg = 1;
+  int a_major = MAJOR_K;
+  View B;
+  int b_major = MAJOR_K;
+  int b_k0[2] = {0, 0};   // where each A segment's k range starts inside B (B k coordinate)
+  int b_n0 = 0;           // first n coordinate inside B
+  int M = 0, N = 0;       // valid extents of D
+  int K[2] = {0, 0};      // valid k extent per segment
+  int passes = 1;
+  bool split = false;     // split K over CTAs (wgrad)
+  EpiParams epi;
+  GemmDesc() { memset(&epi, 0, sizeof(epi)); }
+};
+
+struct Device {
+  int id = 0;
+  int sms = 148;
+  int mn_bn_align = 64;   // UMMA N granularity used when B is MN-major (PVAE_MN_BN_ALIGN)
+  int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
+  bool attr_set = false;
+};
+
+static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
+  CKR(resolve_driver());
+  if (d.M <= 0 || d.N <= 0) return fail(PVAE_ERR_INVALID, "empty GEMM %d x %d", d.M, d.N);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_major = d.a_major;
+  p.b_major = d.b_major;
+  p.passes = d.passes;
+  p.m_tiles = cdiv(d.M, BM);
+  int n_tiles = cdiv(d.N, MAX_BN);
+  int bn = rup(cdiv(d.N, n_tiles), d.b_major == MAJOR_MN ? dev.mn_bn_align : 16);
+  if (bn > MAX_BN) bn = MAX_BN;
+  n_tiles = cdiv(d.N, bn);
+  p.n_tiles = n_tiles;
+  p.bn = bn;
+  for (int s = 0; s < 2; ++s) {
+    if (s < d.nseg) {
+      p.kb[s] = cdiv(d.K[s], BK);
+      p.klen[s] = d.K[s];
+      p.a_dyn[s] = d.A[s].dyn;
+      p.b_k0[s] = d.b_k0[s];
+      CKR(encode_map(&p.tmA[s], d.A[s], 64, d.a_major == MAJOR_K ? BM : BK));
+    }
+  }
+  if (d.nseg == 1) p.tmA[1] = p.tmA[0];
+  p.b_n0 = d.b_n0;
+  p.b_dyn = d.B.dyn;
+  CKR(encode_map(&p.tmB, d.B, 64, d.b_major == MAJOR_K ? bn : BK));
+  const int kb_total = p.kb[0] + p.kb[1];
+  const int iters = kb_total * d.passes;
+  int splits = 1;
+  if (d.split) {
+    const int tiles = p.m_tiles * n_tiles;
+    splits = cdiv(2 * dev.sms, tiles);
+    if (splits > iters) splits = iters;
+    if (splits < 1) splits = 1;
+  }
+  p.splits = splits;
+  p.row_cursor = dev.cursor;
+  p.epi = d.epi;
+  p.epi.m_valid = d.M;
+  p.epi.n_valid = d.N;
+  const int units = p.m_tiles * n_tiles * splits;
+  const int grid = units < dev.sms ? units : dev.sms;
+  pvae_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct Net {
+  int n_layers = 0;
+  int in_dim = 0;
+  int k0 = 0, k1 = 0;          // layer-0 input segments (k1 == 0: single segment)
+  int K0pad = 0;               // shadow column where segment 1 starts
+  int in_dims[PVAE_MAX_LAYERS], out_dims[PVAE_MAX_LAYERS], acts[PVAE_MAX_LAYERS], kpad[PVAE_MAX_LAYERS];
+  const float* W[PVAE_MAX_LAYERS];
+  const float* b[PVAE_MAX_LAYERS];
+  float* grad = nullptr;
+  int64_t gW[PVAE_MAX_LAYERS], gb[PVAE_MAX_LAYERS];
+  int64_t grad_elems = 0;
+  __nv_bfloat16* Wsh[PVAE_MAX_LAYERS];
+  int64_t wsh_ps[PVAE_MAX_LAYERS];
+  __nv_bfloat16* act[PVAE_MAX_LAYERS];
+  __nv_bfloat16* g[PVAE_MAX_LAYERS];
+  int act_ld[PVAE_MAX_LAYERS];
+  bool bound = false;
+};
+
+struct NetIO {     // what feeds layer 0: one or two column segments (the reference's torch.cat inputs)
+  View seg[2];
+  int nseg = 1;
+};
+
+}  // namespace pvae
+
+using namespace pvae;
+
+struct pvae_engine {
+  pvae_model_desc desc;
+  Device dev;
+  Net nets[PVAE_NUM_NETS];
+  int planes = 1, passes = 1;
+  int max_batch = 0;
+  int dsb = 0, da = 0, z = 0, te_out = 0;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  float* ml = nullptr;      // [B][te_out] fp32 encoder output (mu | logvar)
+  float* eps = nullptr;     // [B][z]
+  float* dz = nullptr;      // [B][z]
+  __nv_bfloat16* zb = nullptr;    int zb_ld = 0;
+  __nv_bfloat16* ahat = nullptr;  int a_ld = 0;
+  __nv_bfloat16* ga = nullptr;
+  __nv_bfloat16* xin = nullptr;   int x_ld = 0;
+  __nv_bfloat16* ain = nullptr;
+  // transitions
+  const __nv_bfloat16* tbuf = nullptr;
+  int64_t tbuf_rows = 0;
+  int tx_ld = 0, ty_ld = 0;
+  // scalars
+  double* acc = nullptr;    // [4] loss accumulators
+};
+
+namespace pvae {
+
+static int64_t plane_elems(const pvae_engine* h, int ld) { return (int64_t)h->max_batch * ld; }
+
+// carve the workspace; with base == nullptr only the size is computed
+static size_t carve(pvae_engine* h, uint8_t* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    uint8_t* p = base ? base + off : nullptr;
+    off += (bytes + 1023) & ~size_t(1023);
+    return p;
+  };
+  const int64_t B = h->max_batch;
+  for (int n = 0; n < PVAE_NUM_NETS; ++n) {
+    Net& net = h->nets[n];
+    for (int l = 0; l < net.n_layers; ++l) {
+      net.act_ld[l] = rup(net.out_dims[l], 64);
+      const size_t bytes = (size_t)h->planes * B * net.act_ld[l] * 2;
+      net.act[l] = (l < net.n_layers - 1) ? reinterpret_cast<__nv_bfloat16*>(take(bytes)) : nullptr;
+      net.g[l] = (n != PVAE_NET_VALUE_BRANCH) ? reinterpret_cast<__nv_bfloat16*>(take(bytes)) : nullptr;
+    }
+  }
+  h->ml = reinterpret_cast<float*>(take((size_t)B * h->te_out * 4));
+  h->eps = reinterpret_cast<float*>(take((size_t)B * h->z * 4));
+  h->dz = reinterpret_cast<float*>(take((size_t)B * h->z * 4));
+  h->zb_ld = rup(h->z, 64);
+  h->a_ld = rup(h->da, 64);
+  h->x_ld = rup(2 * h->dsb, 64);
+  h->zb = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->zb_ld * 2));
+  h->ahat = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
+  h->ga = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
+  h->xin = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->x_ld * 2));
+  h->ain = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
+  return off;
+}
+
+static View ws_view(const pvae_engine* h, const __nv_bfloat16* p, int ld, int width, int batch) {
+  View v;
+  v.base = p; v.ld = ld; v.ps = plane_elems(h, ld); v.planes = h->planes; v.width = width; v.rows = batch; v.dyn = 0;
+  return v;
+}
+static View shadow_view(const pvae_engine* h, const Net& net, int l) {
+  View v;
+  v.base = net.Wsh[l]; v.ld = net.kpad[l]; v.ps = net.wsh_ps[l]; v.planes = h->planes; v.width = net.kpad[l];
+  v.rows = net.out_dims[l]; v.dyn = 0;
+  return v;
+}
+static void set_out(EpiParams& e, const pvae_engine* h, __nv_bfloat16* p, int ld) {
+  e.out = p; e.out_ld = ld; e.out_ps = plane_elems(h, ld); e.out_planes = h->planes;
+}
+static void set_out2(EpiParams& e, const pvae_engine* h, __nv_bfloat16* p, int ld) {
+  e.out2 = p; e.out2_ld = ld; e.out2_ps = plane_elems(h, ld); e.out2_planes = h->planes;
+}
+static void set_aux(EpiParams& e, const View& v, int col0) {
+  e.aux = v.base + col0; e.aux_ld = v.ld; e.aux_ps = v.ps; e.aux_planes = v.planes; e.aux_dyn = v.dyn;
+}
+
+// views of the resident transition buffer: x planes then y planes
+static View tx_view(const pvae_engine* h, int col0, int width) {
+  View v;
+  v.base = h->tbuf + col0; v.ld = h->tx_ld; v.ps = h->tbuf_rows * h->tx_ld; v.planes = h->planes; v.width = width;
+  v.rows = h->tbuf_rows; v.dyn = 1;
+  return v;
+}
+static View ty_view(const pvae_engine* h, int width) {
+  View v;
+  v.base = h->tbuf + (int64_t)h->planes * h->tbuf_rows * h->tx_ld; v.ld = h->ty_ld; v.ps = h->tbuf_rows * h->ty_ld;
+  v.planes = h->planes; v.width = width; v.rows = h->tbuf_rows; v.dyn = 1;
+  return v;
+}
+
+// ---- forward through one FC stack (rllib_model_torch.FC.forward, rllib_model_torch.py:274-275) -----------------------
+// `last` is the epilogue of the output layer (type/outputs/loss wiring chosen by the caller).
+static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, const EpiParams& last, cudaStream_t st) {
+  if (!net.bound) return fail(PVAE_ERR_STATE, "net not bound (pvae_bind_net)");
+  for (int l = 0; l < net.n_layers; ++l) {
+    GemmDesc d;
+    d.a_major = MAJOR_K;
+    if (l == 0) {
+      d.nseg = in.nseg;
+      for (int s = 0; s < in.nseg; ++s) { d.A[s] = in.seg[s]; d.K[s] = in.seg[s].width; }
+      d.b_k0[0] = 0; d.b_k0[1] = net.K0pad;
+    } else {
+      d.nseg = 1;
+      d.A[0] = ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
+      d.K[0] = net.out_dims[l - 1];
+    }
+    d.B = shadow_view(h, net, l);
+    d.b_major = MAJOR_K;
+    d.M = batch; d.N = net.out_dims[l];
+    d.passes = h->passes;
+    if (l < net.n_layers - 1) {
+      d.epi.type = EPI_STORE; d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
+      set_out(d.epi, h, net.act[l], net.act_ld[l]);
+    } else {
+      d.epi = last;
+      d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
+    }
+    CKR(launch_gemm(h->dev, d, st));
+  }
+  return PVAE_OK;
+}
+
+// ---- backward through one FC stack: g[L-1] (gradient w.r.t. the output layer's pre-activation) is already in place ---
+// train: accumulate dW / db into the bound gradient buffer.  in_epi: if non-null, also produce the gradient w.r.t. the
+// SECOND input segment of layer 0 (z for the decoder, the action for the world model) with this epilogue.
+static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bool train, const EpiParams* in_epi, cudaStream_t st) {
+  const int L = net.n_layers;
+  if (train && !net.grad) return fail(PVAE_ERR_STATE, "net has no gradient buffer bound");
+  for (int l = L - 1; l >= 0; --l) {
+    const View gl = ws_view(h, net.g[l], net.act_ld[l], net.out_dims[l], batch);
+    if (train) {
+      // dW[l]^T [in][out] = input^T . g[l]; one launch per input segment
+      const int nseg = (l == 0) ? in.nseg : 1;
+      int col0 = 0;
+      for (int s = 0; s < nseg; ++s) {
+        GemmDesc d;
+        d.a_major = MAJOR_MN; d.b_major = MAJOR_MN;
+        d.nseg = 1;
+        d.A[0] = (l == 0) ? in.seg[s] : ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
+        d.B = gl;
+        d.K[0] = batch;
+        d.M = d.A[0].width; d.N = net.out_dims[l];
+        d.passes = h->passes;
+        d.split = true;
+        d.epi.type = EPI_WGRAD;
+        d.epi.out_f32 = net.grad + net.gW[l] + col0;
+        d.epi.f32_sm = 1; d.epi.f32_sn = net.in_dims[l];
+        d.epi.f32_atomic = 1;
+        // the A operand of a wgrad walks the batch along k: the dynamic cursor applies to its row coordinate
+        CKR(launch_gemm(h->dev, d, st));
+        col0 += d.M;
+      }
+    }
+    if (l > 0) {
+      GemmDesc d;
+      d.a_major = MAJOR_K; d.b_major = MAJOR_MN;
+      d.A[0] = gl; d.K[0] = net.out_dims[l];
+      d.B = shadow_view(h, net, l);
+      d.M = batch; d.N = net.out_dims[l - 1];
+      d.passes = h->passes;
+      d.epi.type = EPI_DGRAD; d.epi.act = net.acts[l - 1];
+      const View al = ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
+      if (net.acts[l - 1] != ACT_LINEAR) set_aux(d.epi, al, 0);
+      set_out(d.epi, h, net.g[l - 1], net.act_ld[l - 1]);
+      d.epi.colsum = train ? net.grad + net.gb[l - 1] : nullptr;
+      CKR(launch_gemm(h->dev, d, st));
+    } else if (in_epi) {
+      GemmDesc d;
+      d.a_major = MAJOR_K; d.b_major = MAJOR_MN;
+      d.A[0] = gl; d.K[0] = net.out_dims[0];
+      d.B = shadow_view(h, net, 0);
+      d.b_n0 = net.K0pad;
+      d.M = batch; d.N = net.k1;
+      d.passes = h->passes;
+      d.epi = *in_epi;
+      CKR(launch_gemm(h->dev, d, st));
+    }
+  }
+  return PVAE_OK;
+}
+
+static int check_trainable_acts(const Net& net) {
+  for (int l = 0; l < net.n_layers - 1; ++l)
+    if (net.acts[l] == ACT_SWISH) return fail(PVAE_ERR_INVALID, "swish hidden layers are forward-only in this build");
+  if (net.n_layers > 0 && net.acts[net.n_layers - 1] != ACT_LINEAR)
+    return fail(PVAE_ERR_INVALID, "the training steps need a linear output layer (train_physics_vae.py:188-190)");
+  return PVAE_OK;
+}
+
+static int grid_for(int64_t total, int threads, int sms) {
+  int64_t g = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)sms * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace pvae
+
+// ====================================================================================================================
+// C ABI
+// ====================================================================================================================
+extern "C" {
+
+const char* pvae_last_error(void) { return g_err; }
+int pvae_abi_version(void) { return PVAE_ABI_VERSION; }
+uint64_t pvae_launch_count(void) { return g_launches.load(); }
+
+static int ensure_kernel_attr(Device& dev) {
+  if (dev.attr_set) return PVAE_OK;
+  CK(cudaFuncSetAttribute(pvae_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  dev.attr_set = true;
+  return PVAE_OK;
+}
+
+static int init_device(Device& dev, int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(PVAE_ERR_CUDA, "no CUDA device: libpvae_sm100 has no CPU fallback (%s)", cudaGetErrorString(e));
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(PVAE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  dev.id = device;
+  dev.sms = prop.multiProcessorCount;
+  const char* env = getenv("PVAE_MN_BN_ALIGN");
+  if (env) { int v = atoi(env); if (v == 16 || v == 32 || v == 64) dev.mn_bn_align = v; }
+  CKR(resolve_driver());
+  CKR(ensure_kernel_attr(dev));
+  return PVAE_OK;
+}
+
+int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
+  if (!out || !desc) return fail(PVAE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (desc->dim_state_body <= 0 || desc->dim_action <= 0 || desc->latent_dim <= 0 || desc->max_batch <= 0)
+    return fail(PVAE_ERR_INVALID, "dims and max_batch must be positive");
+  if (desc->precision != PVAE_PREC_BF16 && desc->precision != PVAE_PREC_BF16X3)
+    return fail(PVAE_ERR_INVALID, "unknown precision %d", desc->precision);
+  pvae_engine* h = new pvae_engine();
+  h->desc = *desc;
+  int r = init_device(h->dev, device);
+  if (r != PVAE_OK) { delete h; return r; }
+  h->planes = desc->precision == PVAE_PREC_BF16X3 ? 2 : 1;
+  h->passes = desc->precision == PVAE_PREC_BF16X3 ? 3 : 1;
+  h->max_batch = desc->max_batch;
+  h->dsb = desc->dim_state_body; h->da = desc->dim_action; h->z = desc->latent_dim;
+  h->te_out = desc->latent_prior ? 2 * h->z : h->z;
+  h->tx_ld = rup(2 * h->dsb, 8);
+  h->ty_ld = rup(h->da, 8);
+  for (int n = 0; n < PVAE_NUM_NETS; ++n) {
+    Net& net = h->nets[n];
+    const pvae_net_desc& nd = desc->nets[n];
+    if (nd.n_layers < 0 || nd.n_layers > PVAE_MAX_LAYERS) { delete h; return fail(PVAE_ERR_INVALID, "net %d: bad layer count %d", n, nd.n_layers); }
+    net.n_layers = nd.n_layers;
+    if (nd.n_layers == 0) continue;
+    switch (n) {
+      case PVAE_NET_TASK_ENCODER: net.k0 = 2 * h->dsb; net.k1 = 0; break;
+      case PVAE_NET_MOTOR_DECODER: net.k0 = h->dsb; net.k1 = h->z; break;
+      case PVAE_NET_WORLD_MODEL: net.k0 = h->dsb; net.k1 = h->da; break;
+      default: net.k0 = 2 * h->dsb; net.k1 = 0; break;
+    }
+    net.in_dim = net.k0 + net.k1;
+    net.K0pad = rup(net.k0, 64);
+    int64_t goff = 0;
+    for (int l = 0; l < nd.n_layers; ++l) {
+      if (nd.out_dims[l] <= 0 || nd.acts[l] < 0 || nd.acts[l] > PVAE_ACT_SWISH) { delete h; return fail(PVAE_ERR_INVALID, "net %d layer %d: bad size/activation", n, l); }
+      net.in_dims[l] = l == 0 ? net.in_dim : nd.out_dims[l - 1];
+      net.out_dims[l] = nd.out_dims[l];
+      net.acts[l] = nd.acts[l];
+      net.kpad[l] = l == 0 ? net.K0pad + (net.k1 ? rup(net.k1, 64) : 0) : rup(net.in_dims[l], 64);
+      net.gW[l] = goff; goff += (int64_t)net.in_dims[l] * net.out_dims[l];
+      net.gb[l] = goff; goff += net.out_dims[l];
+      net.wsh_ps[l] = (int64_t)net.out_dims[l] * net.kpad[l];
+      net.Wsh[l] = nullptr;
+    }
+    net.grad_elems = goff;
+  }
+  const int want[PVAE_NUM_NETS] = {h->te_out, h->da, h->dsb, 1};
+  for (int n = 0; n < PVAE_NUM_NETS; ++n) {
+    Net& net = h->nets[n];
+    if (net.n_layers && net.out_dims[net.n_layers - 1] != want[n]) {
+      int got = net.out_dims[net.n_layers - 1];
+      delete h;
+      return fail(PVAE_ERR_INVALID, "net %d: output width %d, expected %d", n, got, want[n]);
+    }
+  }
+  // shadow weights + scalars
+  for (int n = 0; n < PVAE_NUM_NETS; ++n) {
+    Net& net = h->nets[n];
+    for (int l = 0; l < net.n_layers; ++l) {
+      cudaError_t e = cudaMalloc(&net.Wsh[l], (size_t)h->planes * net.wsh_ps[l] * 2);
+      if (e != cudaSuccess) { pvae_destroy(h); return fail(PVAE_ERR_CUDA, "cudaMalloc(shadow weights) failed: %s", cudaGetErrorString(e)); }
+    }
+  }
+  if (cudaMalloc(&h->acc, 4 * sizeof(double)) != cudaSuccess || cudaMalloc(&h->dev.cursor, sizeof(int32_t)) != cudaSuccess) {
+    pvae_destroy(h);
+    return fail(PVAE_ERR_CUDA, "cudaMalloc(scalars) failed");
+  }
+  cudaMemset(h->dev.cursor, 0, sizeof(int32_t));
+  cudaMemset(h->acc, 0, 4 * sizeof(double));
+  h->ws_bytes = carve(h, nullptr);
+  *out = h;
+  return PVAE_OK;
+}
+
+int pvae_destroy(pvae_handle h) {
+  if (!h) return PVAE_OK;
+  for (int n = 0; n < PVAE_NUM_NETS; ++n)
+    for (int l = 0; l < h->nets[n].n_layers; ++l)
+      if (h->nets[n].Wsh[l]) cudaFree(h->nets[n].Wsh[l]);
+  if (h->acc) cudaFree(h->acc);
+  if (h->dev.cursor) cudaFree(h->dev.cursor);
+  delete h;
+  return PVAE_OK;
+}
+
+int pvae_bind_net(pvae_handle h, int net_id, const float* const* W_dev, const float* const* b_dev, float* grad_flat_dev) {
+  if (!h || net_id < 0 || net_id >= PVAE_NUM_NETS) return fail(PVAE_ERR_INVALID, "bad handle / net id");
+  Net& net = h->nets[net_id];
+  if (net.n_layers == 0) return fail(PVAE_ERR_INVALID, "net %d is absent from the model description", net_id);
+  for (int l = 0; l < net.n_layers; ++l) {
+    if (!W_dev[l] || !b_dev[l]) return fail(PVAE_ERR_INVALID, "net %d layer %d: null parameter pointer", net_id, l);
+    net.W[l] = W_dev[l]; net.b[l] = b_dev[l];
+  }
+  net.grad = grad_flat_dev;
+  net.bound = true;
+  return PVAE_OK;
+}
+
+int64_t pvae_net_grad_elems(pvae_handle h, int net_id) {
+  if (!h || net_id < 0 || net_id >= PVAE_NUM_NETS) return -1;
+  return h->nets[net_id].grad_elems;
+}
+
+int pvae_sync_weights(pvae_handle h, uint32_t net_mask, pvae_stream s) {
+  if (!h) return fail(PVAE_ERR_INVALID, "null handle");
+  cudaStream_t st = (cudaStream_t)s;
+  for (int n = 0; n < PVAE_NUM_NETS; ++n) {
+    if (!(net_mask & (1u << n))) continue;
+    Net& net = h->nets[n];
+    if (net.n_layers == 0) continue;
+    if (!net.bound) return fail(PVAE_ERR_STATE, "net %d not bound", n);
+    for (int l = 0; l < net.n_layers; ++l) {
+      const int k0 = l == 0 ? net.k0 : net.in_dims[l];
+      const int k1 = l == 0 ? net.k1 : 0;
+      const int K0pad = l == 0 && net.k1 ? net.K0pad : net.kpad[l];
+      const int64_t total = (int64_t)net.out_dims[l] * net.kpad[l];
+      sync_weights_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(net.W[l], net.out_dims[l], net.in_dims[l], k0, k1, K0pad,
+                                                                            net.kpad[l], net.Wsh[l], net.wsh_ps[l], h->planes);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+  }
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+int pvae_workspace_bytes(pvae_handle h, size_t* bytes) {
+  if (!h || !bytes) return fail(PVAE_ERR_INVALID, "null argument");
+  *bytes = h->ws_bytes;
+  return PVAE_OK;
+}
+
+int pvae_bind_workspace(pvae_handle h, void* ws_dev, size_t bytes) {
+  if (!h || !ws_dev) return fail(PVAE_ERR_INVALID, "null argument");
+  if (bytes < h->ws_bytes) return fail(PVAE_ERR_INVALID, "workspace too small: %zu < %zu", bytes, h->ws_bytes);
+  if ((reinterpret_cast<uintptr_t>(ws_dev) & 1023) != 0) return fail(PVAE_ERR_INVALID, "workspace must be 1024-byte aligned");
+  h->ws = ws_dev;
+  carve(h, reinterpret_cast<uint8_t*>(ws_dev));
+  return PVAE_OK;
+}
+
+int pvae_transitions_bytes(pvae_handle h, int64_t n_rows, size_t* bytes) {
+  if (!h || !bytes || n_rows <= 0) return fail(PVAE_ERR_INVALID, "bad argument");
+  *bytes = (size_t)h->planes * n_rows * (h->tx_ld + h->ty_ld) * 2;
+  return PVAE_OK;
+}
+
+int pvae_ingest(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t dst_row, const void* x_raw_dev, int x_is_f64,
+                const float* y_raw_dev, int64_t n_rows, pvae_stream s) {
+  if (!h || !buf_dev || !x_raw_dev || !y_raw_dev) return fail(PVAE_ERR_INVALID, "null argument");
+  if (n_rows <= 0 || dst_row < 0 || dst_row + n_rows > buf_rows) return fail(PVAE_ERR_INVALID, "row range [%lld, %lld) outside the buffer of %lld rows", (long long)dst_row, (long long)(dst_row + n_rows), (long long)buf_rows);
+  if ((reinterpret_cast<uintptr_t>(buf_dev) & 15) != 0) return fail(PVAE_ERR_INVALID, "transition buffer must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)s;
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(buf_dev);
+  __nv_bfloat16* yb = xb + (int64_t)h->planes * buf_rows * h->tx_ld;
+  const int64_t xt = n_rows * (h->tx_ld / 2), yt = n_rows * (h->ty_ld / 2);
+  if (x_is_f64)
+    ingest_kernel<double><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const double*>(x_raw_dev), 2 * h->dsb, 2 * h->dsb,
+                                                                         xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
+  else
+    ingest_kernel<float><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const float*>(x_raw_dev), 2 * h->dsb, 2 * h->dsb,
+                                                                        xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
+  ingest_kernel<float><<<grid_for(yt, 256, h->dev.sms), 256, 0, st>>>(y_raw_dev, h->da, h->da, yb + dst_row * h->ty_ld, h->ty_ld,
+                                                                      buf_rows * h->ty_ld, h->planes, n_rows);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+int pvae_bind_transitions(pvae_handle h, const void* buf_dev, int64_t buf_rows) {
+  if (!h || !buf_dev || buf_rows <= 0) return fail(PVAE_ERR_INVALID, "bad argument");
+  if (buf_rows > 0x7fffffffLL) return fail(PVAE_ERR_INVALID, "at most 2^31-1 rows per transition buffer");
+  h->tbuf = reinterpret_cast<const __nv_bfloat16*>(buf_dev);
+  h->tbuf_rows = buf_rows;
+  return PVAE_OK;
+}
+
+int pvae_set_cursor(pvae_handle h, int64_t row, pvae_stream s) {
+  if (!h || row < 0 || row >= (h->tbuf_rows ? h->tbuf_rows : 1)) return fail(PVAE_ERR_INVALID, "cursor row out of range");
+  set_cursor_kernel<<<1, 32, 0, (cudaStream_t)s>>>(h->dev.cursor, (int32_t)row);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+int pvae_advance_cursor(pvae_handle h, int64_t delta, int64_t batch, int64_t limit, pvae_stream s) {
+  if (!h) return fail(PVAE_ERR_INVALID, "null handle");
+  advance_cursor_kernel<<<1, 32, 0, (cudaStream_t)s>>>(h->dev.cursor, (int32_t)delta, (int32_t)batch, (int32_t)limit);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+static int step_prologue(pvae_handle h, int batch) {
+  if (!h) return fail(PVAE_ERR_INVALID, "null handle");
+  if (!h->ws) return fail(PVAE_ERR_STATE, "no workspace bound (pvae_bind_workspace)");
+  if (batch <= 0 || batch > h->max_batch) return fail(PVAE_ERR_INVALID, "batch %d outside [1, %d]", batch, h->max_batch);
+  return PVAE_OK;
+}
+
+int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pvae_stream s) {
+  CKR(step_prologue(h, batch));
+  if (!h->tbuf) return fail(PVAE_ERR_STATE, "no transition buffer bound (pvae_bind_transitions)");
+  if (!loss_dev) return fail(PVAE_ERR_INVALID, "null loss pointer");
+  cudaStream_t st = (cudaStream_t)s;
+  Net& wm = h->nets[PVAE_NET_WORLD_MODEL];
+  if (wm.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no world model");
+  CKR(check_trainable_acts(wm));
+  if (!wm.grad) return fail(PVAE_ERR_STATE, "world model has no gradient buffer bound");
+  CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
+  CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));
+  NetIO in;
+  in.nseg = 2;
+  in.seg[0] = tx_view(h, 0, h->dsb);
+  in.seg[1] = ty_view(h, h->da);
+  const int L = wm.n_layers;
+  EpiParams last;
+  memset(&last, 0, sizeof(last));
+  last.type = EPI_MSE;
+  set_aux(last, tx_view(h, 0, 2 * h->dsb), h->dsb);
+  last.scale = 2.f * s_coeff / ((float)batch * (float)h->dsb);
+  set_out(last, h, wm.g[L - 1], wm.act_ld[L - 1]);
+  last.colsum = wm.grad + wm.gb[L - 1];
+  last.loss = h->acc + 2;
+  CKR(net_forward(h, wm, in, batch, last, st));
+  CKR(net_backward(h, wm, in, batch, true, nullptr, st));
+  finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, 0.f, 0.f, s_coeff, 0.f);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
+                  float kl_coeff, float cyc_coeff, float* loss_dev, pvae_stream s) {
+  CKR(step_prologue(h, batch));
+  if (!h->tbuf) return fail(PVAE_ERR_STATE, "no transition buffer bound (pvae_bind_transitions)");
+  if (!loss_dev) return fail(PVAE_ERR_INVALID, "null loss pointer");
+  cudaStream_t st = (cudaStream_t)s;
+  Net& te = h->nets[PVAE_NET_TASK_ENCODER];
+  Net& md = h->nets[PVAE_NET_MOTOR_DECODER];
+  Net& wm = h->nets[PVAE_NET_WORLD_MODEL];
+  if (te.n_layers == 0 || md.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no encoder / decoder");
+  const bool cyc = cyc_coeff != 0.f && wm.n_layers > 0;
+  CKR(check_trainable_acts(te));
+  CKR(check_trainable_acts(md));
+  if (cyc) CKR(check_trainable_acts(wm));
+  if (!te.grad || !md.grad) return fail(PVAE_ERR_STATE, "encoder / decoder have no gradient buffers bound");
+  const int prior = h->desc.latent_prior;
+  CK(cudaMemsetAsync(te.grad, 0, te.grad_elems * sizeof(float), st));
+  CK(cudaMemsetAsync(md.grad, 0, md.grad_elems * sizeof(float), st));
+  CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));
+  const int z = h->z, Lte = te.n_layers, Lmd = md.n_layers, Lwm = wm.n_layers;
+
+  // encoder: h = TE(cat[s1, s2]) -> (mu | logvar)                      rllib_model_torch.py:773-800
+  NetIO te_in; te_in.nseg = 1; te_in.seg[0] = tx_view(h, 0, 2 * h->dsb);
+  EpiParams e;
+  memset(&e, 0, sizeof(e));
+  e.type = EPI_STORE; e.out_f32 = h->ml; e.f32_sm = h->te_out; e.f32_sn = 1;
+  CKR(net_forward(h, te, te_in, batch, e, st));
+  // z = mu + eps * exp(0.5 logvar), KL partial sums                     rllib_model_torch.py:734-740, train_physics_vae.py:384-389
+  {
+    const int64_t total = (int64_t)batch * z;
+    reparam_fwd_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(h->ml, eps_dev, h->eps, prior, prior && noise, seed, offset, batch, z,
+                                                                         h->zb, h->zb_ld, plane_elems(h, h->zb_ld), h->planes, nullptr,
+                                                                         nullptr, nullptr, (prior && kl_coeff != 0.f) ? h->acc + 1 : nullptr);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  // decoder: a_hat = MD(cat[s1, z]); action reconstruction loss          rllib_model_torch.py:822-837, train_physics_vae.py:381-382
+  NetIO md_in; md_in.nseg = 2; md_in.seg[0] = tx_view(h, 0, h->dsb); md_in.seg[1] = ws_view(h, h->zb, h->zb_ld, z, batch);
+  memset(&e, 0, sizeof(e));
+  e.type = EPI_MSE;
+  set_aux(e, ty_view(h, h->da), 0);
+  e.scale = 2.f * a_coeff / ((float)batch * (float)h->da);
+  e.loss = h->acc + 0;
+  set_out2(e, h, h->ahat, h->a_ld);
+  if (cyc) {
+    set_out(e, h, h->ga, h->a_ld);
+  } else {
+    set_out(e, h, md.g[Lmd - 1], md.act_ld[Lmd - 1]);
+    e.colsum = md.grad + md.gb[Lmd - 1];
+  }
+  CKR(net_forward(h, md, md_in, batch, e, st));
+  NetIO wm_in;
+  if (cyc) {
+    // frozen world model on the decoded action: cycle loss                rllib_model_torch.py:839-844, train_physics_vae.py:417-419
+    if (!wm.bound) return fail(PVAE_ERR_STATE, "world model not bound");
+    wm_in.nseg = 2; wm_in.seg[0] = tx_view(h, 0, h->dsb); wm_in.seg[1] = ws_view(h, h->ahat, h->a_ld, h->da, batch);
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_MSE;
+    set_aux(e, tx_view(h, 0, 2 * h->dsb), h->dsb);
+    e.scale = 2.f * cyc_coeff / ((float)batch * (float)h->dsb);
+    e.loss = h->acc + 3;
+    set_out(e, h, wm.g[Lwm - 1], wm.act_ld[Lwm - 1]);
+    CKR(net_forward(h, wm, wm_in, batch, e, st));
+    // d/d a_hat through the frozen world model, plus the action-loss gradient -> decoder output gradient
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_DGRAD; e.act = ACT_LINEAR;
+    e.add = h->ga; e.add_ld = h->a_ld; e.add_ps = plane_elems(h, h->a_ld); e.add_planes = h->planes;
+    set_out(e, h, md.g[Lmd - 1], md.act_ld[Lmd - 1]);
+    e.colsum = md.grad + md.gb[Lmd - 1];
+    CKR(net_backward(h, wm, wm_in, batch, false, &e, st));
+  }
+  // decoder backward; gradient w.r.t. z lands in dz (fp32)
+  memset(&e, 0, sizeof(e));
+  e.type = EPI_DGRAD; e.act = ACT_LINEAR;
+  e.out_f32 = h->dz; e.f32_sm = z; e.f32_sn = 1;
+  CKR(net_backward(h, md, md_in, batch, true, &e, st));
+  // reparameterisation + KL backward -> gradient of the encoder's output layer
+  {
+    const int w = h->te_out;
+    int rows_per_block = 256 / w; if (rows_per_block < 1) rows_per_block = 1;
+    const int threads = w * rows_per_block;
+    if (threads > 1024) return fail(PVAE_ERR_INVALID, "latent_dim %d too large for the reparameterisation kernel", z);
+    int grid = cdiv(batch, rows_per_block); if (grid > h->dev.sms * 8) grid = h->dev.sms * 8;
+    reparam_bwd_kernel<<<grid, threads, 0, st>>>(h->dz, h->ml, h->eps, prior, prior && noise, prior ? kl_coeff / (float)batch : 0.f, batch, z,
+                                                 te.g[Lte - 1], te.act_ld[Lte - 1], plane_elems(h, te.act_ld[Lte - 1]), h->planes,
+                                                 te.grad + te.gb[Lte - 1]);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  CKR(net_backward(h, te, te_in, batch, true, nullptr, st));
+  finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, a_coeff, prior ? kl_coeff : 0.f, 0.f, cyc ? cyc_coeff : 0.f);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev, int64_t obs_ld, const float* z_in_dev,
+                 const float* act_in_dev, int64_t act_in_ld, const float* eps_dev, int noise, uint64_t seed,
+                 uint64_t offset, float* act_out_dev, int64_t act_out_ld, float* mu_dev, float* logvar_dev, float* z_dev,
+                 float* future_dev, float* value_dev, pvae_stream s) {
+  CKR(step_prologue(h, batch));
+  if (!obs_dev) return fail(PVAE_ERR_INVALID, "obs_dev is required (the body state feeds the decoder and the world model)");
+  cudaStream_t st = (cudaStream_t)s;
+  const int z = h->z;
+  const bool enc = parts & PVAE_PART_ENCODER, dec = parts & PVAE_PART_DECODER, wld = parts & PVAE_PART_WORLD, val = parts & PVAE_PART_VALUE;
+  const int obs_w = (enc || val) ? 2 * h->dsb : h->dsb;
+  if (obs_ld < obs_w) return fail(PVAE_ERR_INVALID, "obs row stride %lld < %d", (long long)obs_ld, obs_w);
+  {
+    const int64_t total = (int64_t)batch * h->x_ld;
+    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(obs_dev, obs_ld, obs_w, h->xin, h->x_ld, plane_elems(h, h->x_ld), h->planes, batch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  EpiParams e;
+  if (enc) {
+    Net& te = h->nets[PVAE_NET_TASK_ENCODER];
+    if (te.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no task encoder");
+    NetIO in; in.nseg = 1; in.seg[0] = ws_view(h, h->xin, h->x_ld, 2 * h->dsb, batch);
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_STORE; e.out_f32 = h->ml; e.f32_sm = h->te_out; e.f32_sn = 1;
+    CKR(net_forward(h, te, in, batch, e, st));
+    const int prior = h->desc.latent_prior;
+    const int64_t total = (int64_t)batch * z;
+    reparam_fwd_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(h->ml, eps_dev, h->eps, prior, prior && noise, seed, offset, batch, z,
+                                                                         h->zb, h->zb_ld, plane_elems(h, h->zb_ld), h->planes, z_dev, mu_dev,
+                                                                         prior ? logvar_dev : nullptr, nullptr);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else if (dec) {
+    if (!z_in_dev) return fail(PVAE_ERR_INVALID, "decoder without encoder needs z_in_dev");
+    const int64_t total = (int64_t)batch * h->zb_ld;
+    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(z_in_dev, z, z, h->zb, h->zb_ld, plane_elems(h, h->zb_ld), h->planes, batch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  const __nv_bfloat16* act_planes = h->ahat;
+  if (dec) {
+    Net& md = h->nets[PVAE_NET_MOTOR_DECODER];
+    if (md.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no motor decoder");
+    NetIO in; in.nseg = 2; in.seg[0] = ws_view(h, h->xin, h->x_ld, h->dsb, batch); in.seg[1] = ws_view(h, h->zb, h->zb_ld, z, batch);
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_STORE;
+    set_out(e, h, h->ahat, h->a_ld);
+    if (act_out_dev) { e.out_f32 = act_out_dev; e.f32_sm = act_out_ld; e.f32_sn = 1; }
+    CKR(net_forward(h, md, in, batch, e, st));
+  } else if (wld) {
+    if (!act_in_dev) return fail(PVAE_ERR_INVALID, "world model without decoder needs act_in_dev");
+    const int64_t total = (int64_t)batch * h->a_ld;
+    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(act_in_dev, act_in_ld, h->da, h->ain, h->a_ld, plane_elems(h, h->a_ld), h->planes, batch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    act_planes = h->ain;
+  }
+  if (wld) {
+    Net& wm = h->nets[PVAE_NET_WORLD_MODEL];
+    if (wm.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no world model");
+    if (!future_dev) return fail(PVAE_ERR_INVALID, "world part needs future_dev");
+    NetIO in; in.nseg = 2; in.seg[0] = ws_view(h, h->xin, h->x_ld, h->dsb, batch); in.seg[1] = ws_view(h, act_planes, h->a_ld, h->da, batch);
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_STORE; e.out_f32 = future_dev; e.f32_sm = h->dsb; e.f32_sn = 1;
+    CKR(net_forward(h, wm, in, batch, e, st));
+  }
+  if (val) {
+    Net& vb = h->nets[PVAE_NET_VALUE_BRANCH];
+    if (vb.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no value branch");
+    if (!value_dev) return fail(PVAE_ERR_INVALID, "value part needs value_dev");
+    NetIO in; in.nseg = 1; in.seg[0] = ws_view(h, h->xin, h->x_ld, 2 * h->dsb, batch);
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_STORE; e.out_f32 = value_dev; e.f32_sm = 1; e.f32_sn = 1;
+    CKR(net_forward(h, vb, in, batch, e, st));
+  }
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+// D = A . B^T on the tensor-core path, operands given as bf16 planes (unit tests / bench roofline).
+int pvae_gemm_bf16(const void* A_dev, int a_major, const void* B_dev, int b_major, int M, int N, int K, int planes,
+                   int splits, float* D_dev, pvae_stream s) {
+  static Device dev;
+  static bool dev_ok = false;
+  if (!A_dev || !B_dev || !D_dev) return fail(PVAE_ERR_INVALID, "null argument");
+  if (M <= 0 || N <= 0 || K <= 0 || (planes != 1 && planes != 2)) return fail(PVAE_ERR_INVALID, "bad shape / planes");
+  if (!dev_ok) {
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    CKR(init_device(dev, cur));
+    dev_ok = true;
+  }
+  GemmDesc d;
+  d.a_major = a_major ? MAJOR_MN : MAJOR_K;
+  d.b_major = b_major ? MAJOR_MN : MAJOR_K;
+  View& a = d.A[0];
+  a.base = reinterpret_cast<const __nv_bfloat16*>(A_dev); a.planes = planes;
+  if (a_major) { a.ld = M; a.width = M; a.rows = K; } else { a.ld = K; a.width = K; a.rows = M; }
+  a.ps = a.ld * a.rows;
+  View& b = d.B;
+  b.base = reinterpret_cast<const __nv_bfloat16*>(B_dev); b.planes = planes;
+  if (b_major) { b.ld = N; b.width = N; b.rows = K; } else { b.ld = K; b.width = K; b.rows = N; }
+  b.ps = b.ld * b.rows;
+  d.M = M; d.N = N; d.K[0] = K;
+  d.passes = planes == 2 ? 3 : 1;
+  d.split = splits > 1;
+  d.epi.type = EPI_WGRAD;
+  d.epi.out_f32 = D_dev; d.epi.f32_sm = N; d.epi.f32_sn = 1; d.epi.f32_atomic = splits > 1;
+  return launch_gemm(dev, d, (cudaStream_t)s);
+}
+
+}  // extern "C"

@@ -1,0 +1,522 @@
+// pvae_gemm.cuh -- the one tensor-core kernel of the PhysicsVAE hot path.
+//
+// A persistent, warp-specialised sm_100a GEMM:  D[M,N] = epilogue( A[M,K] . B[N,K]^T )
+//   * operands arrive in shared memory by TMA (cp.async.bulk.tensor, 128B swizzle),
+//   * products are issued by one thread as tcgen05.mma (cta_group::1, 128 x bn x 16, bf16 -> fp32),
+//   * accumulators live in TMEM (2 stages x 256 columns) and are drained by four epilogue warps
+//     with tcgen05.ld while the next tile's main loop runs.
+// Everything a Linear layer of the reference needs is expressed by parameters of this kernel:
+//   forward   y = act(x W^T + b)            A = x  (K-major)   B = W shadow (K-major)
+//   dgrad     dx = (dy W) * act'(y)         A = dy (K-major)   B = W shadow (MN-major view)
+//   wgrad     dW^T = x^T dy                 A = x  (MN-major)  B = dy (MN-major), split over the batch
+// (reference: rllib SlimFC = nn.Linear + activation, rllib_model_torch.py:248-253; autograd of it,
+//  torch_models.py:142).  "Virtual concat" (torch.cat in rllib_model_torch.py:829,842 and
+//  train_physics_vae.py:377) is done by giving operand A two K-segments with their own tensor maps.
+// Precision modes: passes=1 -> plain bf16 operands; passes=3 -> bf16x3 split (hi*hi + hi*lo + lo*hi,
+// operands stored as hi/lo planes) which reproduces fp32 results to ~1e-6 relative.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace pvae {
+
+constexpr int BM = 128;                       // tile rows  (UMMA M)
+constexpr int BK = 64;                        // k elements per pipeline stage (= one 128B swizzle span)
+constexpr int MAX_BN = 256;                   // tile cols  (UMMA N), runtime value bn <= 256, multiple of 16
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KiB
+constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;    // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 256;              // warps 0..3: TMA / MMA / TMEM-alloc / idle, warps 4..7: epilogue
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+enum : int { EPI_STORE = 0, EPI_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD = 3 };
+enum : int { ACT_LINEAR = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3, ACT_ELU = 4, ACT_SWISH = 5 };
+enum : int { MAJOR_K = 0, MAJOR_MN = 1 };
+
+struct EpiParams {
+  int32_t type, act;
+  int32_t m_valid, n_valid;        // rows / cols of D that exist
+  const float* bias;               // [n_valid] fp32 or null
+  // primary bf16 output (activation / gradient), hi plane at out, lo plane at out + out_ps
+  __nv_bfloat16* out;  int64_t out_ld,  out_ps;  int32_t out_planes;  int32_t pad0;
+  // secondary bf16 output (EPI_MSE: the prediction itself, e.g. the decoded action fed to the world model)
+  __nv_bfloat16* out2; int64_t out2_ld, out2_ps; int32_t out2_planes; int32_t pad1;
+  // fp32 output with arbitrary strides (EPI_WGRAD target, or fp32 copy of the EPI_STORE/EPI_MSE result)
+  float* out_f32; int64_t f32_sm, f32_sn;
+  // aux bf16 input: EPI_MSE target / EPI_DGRAD forward activation (for act')
+  const __nv_bfloat16* aux; int64_t aux_ld, aux_ps; int32_t aux_planes; int32_t aux_dyn;
+  // addend bf16 input (EPI_DGRAD: g = acc + add)
+  const __nv_bfloat16* add; int64_t add_ld, add_ps; int32_t add_planes; int32_t pad2;
+  float scale;                     // EPI_MSE: d = scale * (pred - target)
+  int32_t f32_atomic;              // EPI_WGRAD: 1 = red.global.add, 0 = plain store
+  float* colsum;                   // [n_valid] fp32, atomically accumulated column sums of the primary output (bias grad)
+  double* loss;                    // EPI_MSE: sum of squared errors accumulated here
+};
+
+struct GemmParams {
+  CUtensorMap tmA[2];              // operand A, one map per K-segment
+  CUtensorMap tmB;                 // operand B
+  int32_t a_major, b_major;        // MAJOR_K / MAJOR_MN
+  int32_t kb[2];                   // 64-wide k-blocks per segment
+  int32_t klen[2];                 // valid k elements per segment (to skip all-zero k16 slices)
+  int32_t a_c0[2];                 // A: K-major -> first k element; MN-major -> first m element (inner coordinate)
+  int32_t a_r0[2];                 // A: row coordinate offset (K-major: m rows, MN-major: k rows)
+  int32_t a_dyn[2];                // A: add *row_cursor to the row coordinate
+  int32_t b_k0[2];                 // B: k offset at the start of the segment (K-major: inner coord, MN-major: row coord)
+  int32_t b_n0;                    // B: n offset
+  int32_t b_dyn;                   // B: add *row_cursor to the k row coordinate (MN-major)
+  int32_t passes;                  // 1 = bf16, 3 = bf16x3
+  int32_t m_tiles, n_tiles, bn, splits;
+  const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
+  EpiParams epi;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0) {
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) {   // 4 s
+        printf("pvae_gemm: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+               (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1, 128B swizzle).
+//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1).
+//   MN-major: 64-element (128 B) MN atoms x 8 k-rows; next 8 k-rows 1024 B on (SBO);
+//             next MN atom one whole TMA box on = 64 k-rows * 128 B = 8192 B (LBO).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int major) {
+  const uint64_t lbo = (major == MAJOR_K) ? 1ull : (8192ull >> 4);
+  const uint64_t sbo = 1024ull >> 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+// tcgen05 instruction descriptor, kind::f16, A/B = bf16, D = fp32, M = 128.
+__device__ __forceinline__ uint32_t umma_idesc(int n, int a_major, int b_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  switch (act) {
+    case ACT_RELU:    return fmaxf(v, 0.f);
+    case ACT_TANH:    return tanhf(v);
+    case ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case ACT_ELU:     return v > 0.f ? v : expm1f(v);
+    case ACT_SWISH:   return v / (1.f + __expf(-v));
+    default:          return v;
+  }
+}
+// derivative of the activation expressed through its OUTPUT y (what the forward pass stored)
+__device__ __forceinline__ float act_bwd_from_out(float y, int act) {
+  switch (act) {
+    case ACT_RELU:    return y > 0.f ? 1.f : 0.f;
+    case ACT_TANH:    return 1.f - y * y;
+    case ACT_SIGMOID: return y * (1.f - y);
+    case ACT_ELU:     return y > 0.f ? 1.f : y + 1.f;
+    default:          return 1.f;
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo_part(float v) {  // v - bf16(v)
+  return v - __bfloat162float(__float2bfloat16_rn(v));
+}
+
+// Load 32 consecutive bf16 (hi plane + optional lo plane) of one row as floats; columns >= nvalid read as 0.
+__device__ __forceinline__ void load_row32(const __nv_bfloat16* base, int64_t ps, int planes, int nvalid, float (&v)[32]) {
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ps & 7) == 0);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  for (int pl = 0; pl < planes; ++pl) {
+    const __nv_bfloat16* p = base + pl * ps;
+    if (vec_ok && nvalid >= 32) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(p) + g);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[g * 8 + 2 * j]     += __uint_as_float(w[j] << 16);
+          v[g * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) v[i] += __bfloat162float(p[i]);
+    }
+  }
+}
+// Store 32 consecutive values of one row as bf16 hi (+lo) planes; 8-column groups that start at or past
+// nvalid are skipped, columns past nvalid inside a written group are zero. Row base must be 16B aligned.
+__device__ __forceinline__ void store_row32(__nv_bfloat16* base, int64_t ps, int planes, int nvalid, const float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g * 8 < nvalid) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = (g * 8 + j < nvalid) ? v[g * 8 + j] : 0.f;
+      uint4 q;
+      q.x = pack_bf16x2(t[0], t[1]); q.y = pack_bf16x2(t[2], t[3]);
+      q.z = pack_bf16x2(t[4], t[5]); q.w = pack_bf16x2(t[6], t[7]);
+      *(reinterpret_cast<uint4*>(base) + g) = q;
+      if (planes > 1) {
+        uint4 l;
+        l.x = pack_bf16x2(bf16_lo_part(t[0]), bf16_lo_part(t[1]));
+        l.y = pack_bf16x2(bf16_lo_part(t[2]), bf16_lo_part(t[3]));
+        l.z = pack_bf16x2(bf16_lo_part(t[4]), bf16_lo_part(t[5]));
+        l.w = pack_bf16x2(bf16_lo_part(t[6]), bf16_lo_part(t[7]));
+        *(reinterpret_cast<uint4*>(base + ps) + g) = l;
+      }
+    }
+  }
+}
+// Transposing butterfly: on return lane j holds sum over the 32 lanes of v[j].
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle atoms need 1024 B alignment
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    if (p.kb[1] > 0) tma_prefetch_desc(&p.tmA[1]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int row0 = p.row_cursor ? *p.row_cursor : 0;
+  const int kb_total = p.kb[0] + p.kb[1];
+  const int iters_total = p.passes * kb_total;
+  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+  const int bn = p.bn;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const int b_boxes = (bn + 63) >> 6;
+      const uint32_t stage_tx = A_STAGE_BYTES + (p.b_major == MAJOR_K ? (uint32_t)bn * (BK * 2) : (uint32_t)b_boxes * 8192u);
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int split = u % p.splits;
+        const int tile = u / p.splits;
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
+        const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
+        for (int it = it_begin; it < it_end; ++it) {
+          const int pass = it / kb_total;
+          int r = it - pass * kb_total;
+          const int seg = (r >= p.kb[0]) ? 1 : 0;
+          if (seg) r -= p.kb[0];
+          const int a_plane = (pass == 2) ? 1 : 0;
+          const int b_plane = (pass == 1) ? 1 : 0;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), stage_tx);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const int a_row = p.a_r0[seg] + (p.a_dyn[seg] ? row0 : 0);
+          if (p.a_major == MAJOR_K) {
+            tma_load_3d(sa, &p.tmA[seg], full_bar(stage), p.a_c0[seg] + r * BK, a_row + m_tile * BM, a_plane);
+          } else {
+            tma_load_3d(sa,         &p.tmA[seg], full_bar(stage), p.a_c0[seg] + m_tile * BM,      a_row + r * BK, a_plane);
+            tma_load_3d(sa + 8192u, &p.tmA[seg], full_bar(stage), p.a_c0[seg] + m_tile * BM + 64, a_row + r * BK, a_plane);
+          }
+          if (p.b_major == MAJOR_K) {
+            tma_load_3d(sb, &p.tmB, full_bar(stage), p.b_k0[seg] + r * BK, p.b_n0 + n_tile * bn, b_plane);
+          } else {
+            const int b_row = p.b_k0[seg] + r * BK + (p.b_dyn ? row0 : 0);
+            for (int j = 0; j < b_boxes; ++j)
+              tma_load_3d(sb + 8192u * j, &p.tmB, full_bar(stage), p.b_n0 + n_tile * bn + 64 * j, b_row, b_plane);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(bn, p.a_major, p.b_major);
+      const uint32_t a_kstep = (p.a_major == MAJOR_K) ? 2u : 128u;   // 16 k elements, in 16 B units: 32 B or 16 rows * 128 B
+      const uint32_t b_kstep = (p.b_major == MAJOR_K) ? 2u : 128u;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int split = u % p.splits;
+        const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
+        const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
+        for (int it = it_begin; it < it_end; ++it) {
+          const int pass = it / kb_total;
+          int r = it - pass * kb_total;
+          const int seg = (r >= p.kb[0]) ? 1 : 0;
+          if (seg) r -= p.kb[0];
+          int k16 = (p.klen[seg] - r * BK + 15) >> 4;
+          k16 = k16 > 4 ? 4 : (k16 < 1 ? 1 : k16);
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = umma_desc(sa, p.a_major);
+          const uint64_t bdesc = umma_desc(sa + A_STAGE_BYTES, p.b_major);
+          for (int k = 0; k < k16; ++k)
+            umma_bf16(tmem_d, adesc + (uint64_t)(a_kstep * k), bdesc + (uint64_t)(b_kstep * k), idesc,
+                      (it > it_begin || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const EpiParams& e = p.epi;
+    const int q = warp - 4;                       // TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    double loss_local = 0.0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int tile = u / p.splits;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int row = m_tile * BM + q * 32 + lane;
+      const bool row_ok = row < e.m_valid;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int nchunks = (bn + 31) >> 5;
+      for (int c = 0; c < nchunks; ++c) {
+        const int col0 = n_tile * bn + c * 32;
+        if (col0 >= e.n_valid) break;             // warp-uniform
+        int nv = e.n_valid - col0; nv = nv > 32 ? 32 : nv;
+        const int tile_nv = bn - c * 32;          // columns of this chunk that belong to this tile
+        if (tile_nv < nv) nv = tile_nv;
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + c * 32), raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+
+        if (e.type == EPI_WGRAD) {
+          if (row_ok) {
+            float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nv) {
+                if (e.f32_atomic) atomicAdd(dst + (int64_t)i * e.f32_sn, v[i]);
+                else dst[(int64_t)i * e.f32_sn] = v[i];
+              }
+            }
+          }
+          continue;
+        }
+
+        if (e.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += (i < nv) ? __ldg(e.bias + col0 + i) : 0.f;
+        }
+
+        if (e.type == EPI_STORE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_fwd(v[i], e.act);
+          if (row_ok) {
+            if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
+            if (e.out_f32) {
+              float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
+            }
+          }
+        } else if (e.type == EPI_MSE) {
+          float t[32];
+          const int64_t arow = (int64_t)row + (e.aux_dyn ? row0 : 0);
+          if (row_ok) load_row32(e.aux + arow * e.aux_ld + col0, e.aux_ps, e.aux_planes, nv, t);
+          if (row_ok) {
+            if (e.out2) store_row32(e.out2 + (int64_t)row * e.out2_ld + col0, e.out2_ps, e.out2_planes, nv, v);
+            if (e.out_f32) {
+              float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
+            }
+          }
+          float sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = (row_ok && i < nv) ? (v[i] - t[i]) : 0.f;
+            sq += d * d;
+            v[i] = e.scale * d;
+          }
+          loss_local += (double)sq;
+          if (row_ok && e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
+          if (e.colsum) {
+            const float s = warp_colsum32(v, lane);
+            if (lane < nv) atomicAdd(e.colsum + col0 + lane, s);
+          }
+        } else {  // EPI_DGRAD
+          if (row_ok) {
+            if (e.add) {
+              float a[32];
+              load_row32(e.add + (int64_t)row * e.add_ld + col0, e.add_ps, e.add_planes, nv, a);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += a[i];
+            }
+            if (e.aux) {
+              float y[32];
+              load_row32(e.aux + (int64_t)row * e.aux_ld + col0, e.aux_ps, e.aux_planes, nv, y);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= act_bwd_from_out(y[i], e.act);
+            }
+            if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
+            if (e.out_f32) {
+              float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
+            }
+          }
+          if (e.colsum) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (row_ok && i < nv) ? v[i] : 0.f;
+            const float s = warp_colsum32(v, lane);
+            if (lane < nv) atomicAdd(e.colsum + col0 + lane, s);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (e.type == EPI_MSE && e.loss) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, off);
+      if (lane == 0 && loss_local != 0.0) atomicAdd(e.loss, loss_local);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+}  // namespace pvae

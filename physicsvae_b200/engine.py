@@ -1,0 +1,197 @@
+"""Host-side handle on the sm_100a engine: owns the torch tensors (workspace, transition buffer, flat gradients) whose raw
+device pointers are handed to libpvae_sm100.so, and nothing else.  PyTorch is plumbing here -- device memory, streams --
+all arithmetic of the hot path happens inside the library.
+"""
+import ctypes as C
+
+import torch
+
+from . import _abi
+
+NET_NAMES = ("task_encoder", "motor_decoder", "world_model", "value_branch")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One engine per process / GPU (the handle is not thread-safe; include/pvae_sm100.h).
+
+    nets: dict net name -> list of (out_features, activation name) per Linear layer, in the reference's FC order
+    (rllib_model_torch.py:243-264).  precision: "bf16" (performance) or "bf16x3" (fp32-accurate parity mode).
+    """
+
+    def __init__(self, dim_state_body, dim_action, latent_dim, nets, latent_prior=True, precision="bf16x3", max_batch=4096,
+                 device=None):
+        if not torch.cuda.is_available():
+            raise _abi.PvaeError("physicsvae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _abi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.dsb, self.da, self.z = int(dim_state_body), int(dim_action), int(latent_dim)
+        self.latent_prior = bool(latent_prior)
+        self.precision = precision
+        self.planes = 2 if precision == "bf16x3" else 1
+        self.max_batch = int(max_batch)
+        desc = _abi.ModelDesc()
+        desc.dim_state_body, desc.dim_action, desc.latent_dim = self.dsb, self.da, self.z
+        desc.latent_prior = 1 if latent_prior else 0
+        desc.precision = {"bf16": _abi.PREC_BF16, "bf16x3": _abi.PREC_BF16X3}[precision]
+        desc.max_batch = self.max_batch
+        self.layers = {}
+        for i, name in enumerate(NET_NAMES):
+            spec = nets.get(name) or []
+            if len(spec) > _abi.PVAE_MAX_LAYERS:
+                raise ValueError("%s: at most %d layers" % (name, _abi.PVAE_MAX_LAYERS))
+            desc.nets[i].n_layers = len(spec)
+            for l, (out, act) in enumerate(spec):
+                if act not in _abi.ACT_IDS:
+                    raise ValueError("Unknown activation ({})!".format(act))
+                desc.nets[i].out_dims[l] = int(out)
+                desc.nets[i].acts[l] = _abi.ACT_IDS[act]
+            self.layers[name] = list(spec)
+        self._h = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_create(C.byref(self._h), C.byref(desc), self.device.index))
+            nbytes = C.c_size_t(0)
+            _abi.check(self.lib.pvae_workspace_bytes(self._h, C.byref(nbytes)))
+            # zero-initialised: padding columns are never written and must stay finite
+            self.workspace = torch.zeros(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
+            off = (-self.workspace.data_ptr()) % 1024
+            _abi.check(self.lib.pvae_bind_workspace(self._h, C.c_void_p(self.workspace.data_ptr() + off), nbytes.value))
+        self.loss = torch.zeros(_abi.PVAE_LOSS_SLOTS, dtype=torch.float32, device=self.device)
+        self._keep = {}          # tensors whose pointers the library holds
+        self.transitions = None
+        self.n_rows = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.pvae_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters ---------------------------------------------------------------------------------------------
+    def grad_elems(self, name):
+        return int(self.lib.pvae_net_grad_elems(self._h, NET_NAMES.index(name)))
+
+    def bind_net(self, name, weights, biases, grad_flat=None):
+        """weights[l]: fp32 [out, in] contiguous CUDA tensors (nn.Linear layout); grad_flat: fp32 [grad_elems] or None."""
+        n = len(weights)
+        if n != len(self.layers[name]) or n != len(biases):
+            raise ValueError("%s: expected %d layers" % (name, len(self.layers[name])))
+        for t in list(weights) + list(biases) + ([grad_flat] if grad_flat is not None else []):
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("%s: parameters must be contiguous fp32 tensors on %s" % (name, self.device))
+        if grad_flat is not None and grad_flat.numel() != self.grad_elems(name):
+            raise ValueError("%s: gradient buffer has %d elements, expected %d" % (name, grad_flat.numel(), self.grad_elems(name)))
+        W = (C.c_void_p * n)(*[t.data_ptr() for t in weights])
+        b = (C.c_void_p * n)(*[t.data_ptr() for t in biases])
+        _abi.check(self.lib.pvae_bind_net(self._h, NET_NAMES.index(name), W, b, _ptr(grad_flat)))
+        self._keep[name] = (list(weights), list(biases), grad_flat)
+
+    def sync_weights(self, names=None):
+        mask = 0
+        for name in (names or [n for n in NET_NAMES if n in self._keep]):
+            mask |= 1 << NET_NAMES.index(name)
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_sync_weights(self._h, mask, _stream()))
+
+    # ---- resident transition buffer -------------------------------------------------------------------------------
+    def alloc_transitions(self, n_rows):
+        nbytes = C.c_size_t(0)
+        _abi.check(self.lib.pvae_transitions_bytes(self._h, int(n_rows), C.byref(nbytes)))
+        self.transitions = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        self.n_rows = int(n_rows)
+        _abi.check(self.lib.pvae_bind_transitions(self._h, _ptr(self.transitions), self.n_rows))
+        return self.transitions
+
+    def ingest(self, x_raw, y_raw, dst_row=0):
+        """x_raw: CUDA [n, 2*dsb] float64 or float32; y_raw: CUDA [n, da] float32 (DatasetBase.X / .Y, torch_models.py:39-58)."""
+        if self.transitions is None:
+            raise _abi.PvaeError("alloc_transitions() first")
+        x_raw = x_raw.reshape(x_raw.shape[0], -1)
+        y_raw = y_raw.reshape(y_raw.shape[0], -1)
+        if x_raw.shape[1] != 2 * self.dsb or y_raw.shape[1] != self.da or x_raw.shape[0] != y_raw.shape[0]:
+            raise ValueError("transition arrays must be [n, %d] and [n, %d]" % (2 * self.dsb, self.da))
+        if x_raw.dtype not in (torch.float64, torch.float32):
+            raise ValueError("x must be float64 or float32")
+        x_raw = x_raw.to(self.device).contiguous()
+        y_raw = y_raw.to(self.device, torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_ingest(self._h, _ptr(self.transitions), self.n_rows, int(dst_row), _ptr(x_raw),
+                                            1 if x_raw.dtype == torch.float64 else 0, _ptr(y_raw), x_raw.shape[0], _stream()))
+
+    def set_cursor(self, row):
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_set_cursor(self._h, int(row), _stream()))
+
+    def advance_cursor(self, delta, batch, limit):
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_advance_cursor(self._h, int(delta), int(batch), int(limit), _stream()))
+
+    # ---- training steps ---------------------------------------------------------------------------------------------
+    def world_step(self, batch, s_coeff=1.0):
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_world_step(self._h, int(batch), float(s_coeff), _ptr(self.loss), _stream()))
+        return self.loss
+
+    def vae_step(self, batch, eps=None, seed=0, offset=0, noise=True, a_coeff=1.0, kl_coeff=1.0, cyc_coeff=1e-3):
+        if eps is not None:
+            if eps.shape != (batch, self.z) or eps.dtype != torch.float32 or eps.device != self.device or not eps.is_contiguous():
+                raise ValueError("eps must be a contiguous fp32 [%d, %d] tensor on %s" % (batch, self.z, self.device))
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_vae_step(self._h, int(batch), _ptr(eps), int(seed), int(offset), 1 if noise else 0,
+                                              float(a_coeff), float(kl_coeff), float(cyc_coeff), _ptr(self.loss), _stream()))
+        return self.loss
+
+    # ---- inference ------------------------------------------------------------------------------------------------
+    def forward(self, obs, parts, z_in=None, act_in=None, eps=None, noise=False, seed=0, offset=0):
+        """Runs the selected parts of PhysicsVAE.forward (rllib_model_torch.py:742-853); returns a dict of fp32 outputs."""
+        B = obs.shape[0]
+        dev, f32 = self.device, torch.float32
+        obs = obs.to(dev, f32).contiguous()
+        out = {}
+        enc, dec = parts & _abi.PART_ENCODER, parts & _abi.PART_DECODER
+        wld, val = parts & _abi.PART_WORLD, parts & _abi.PART_VALUE
+        if enc:
+            out["z"] = torch.empty(B, self.z, dtype=f32, device=dev)
+            out["mu"] = torch.empty(B, self.z, dtype=f32, device=dev)
+            if self.latent_prior:
+                out["logvar"] = torch.empty(B, self.z, dtype=f32, device=dev)
+        if dec:
+            out["action"] = torch.empty(B, self.da, dtype=f32, device=dev)
+        if wld:
+            out["future"] = torch.empty(B, self.dsb, dtype=f32, device=dev)
+        if val:
+            out["value"] = torch.empty(B, dtype=f32, device=dev)
+        if z_in is not None:
+            z_in = z_in.to(dev, f32).contiguous()
+        if act_in is not None:
+            act_in = act_in.to(dev, f32).contiguous()
+        if eps is not None:
+            eps = eps.to(dev, f32).contiguous()
+        with torch.cuda.device(dev):
+            _abi.check(self.lib.pvae_forward(
+                self._h, int(parts), int(B), _ptr(obs), obs.shape[1], _ptr(z_in), _ptr(act_in),
+                act_in.shape[1] if act_in is not None else 0, _ptr(eps), 1 if noise else 0, int(seed), int(offset),
+                _ptr(out.get("action")), self.da, _ptr(out.get("mu")), _ptr(out.get("logvar")), _ptr(out.get("z")),
+                _ptr(out.get("future")), _ptr(out.get("value")), _stream()))
+        return out
+
+
+def gemm_bf16(A, B, M, N, K, a_major=0, b_major=0, planes=1, splits=1):
+    """Kernel-level entry: D[M,N] = A . B^T on the tcgen05 path (include/pvae_sm100.h, pvae_gemm_bf16)."""
+    lib = _abi.load()
+    D = torch.zeros(M, N, dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        _abi.check(lib.pvae_gemm_bf16(_ptr(A), a_major, _ptr(B), b_major, M, N, K, planes, splits, _ptr(D), _stream()))
+    return D
