@@ -1,0 +1,352 @@
+"""bench.py -- transitions/sec of the PhysicsVAE training step on B200 (BASELINE.json metric), with the CPU reference arm.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--phase world|vae] [--batch B] [--config default|wide|loco]
+  python bench.py --impl reference ...            the reference algorithm (oracle port) on the box's host cores
+
+A "step" is one mini-batch SGD step of the hot path: forward + loss + backward (libpvae_sm100 tcgen05 kernels) +
+gradient all-reduce (N > 1) + fused Adam + refresh of the bf16 shadow weights, on a batch of synthetic transitions.
+Default workload = BASELINE.json configs[1]: world-model-only pretrain, dim_state_body 197 / dim_action 45, batch 65536
+per GPU, bf16 operands with fp32 accumulation.  Weak scaling: every rank holds its own resident shard of 4*B transitions.
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for how each field is computed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+CONFIGS = {
+    "default": dict(dsb=197, da=45, z=32, te=(256, 2), md=(512, 3), wm=(1024, 2)),
+    "wide": dict(dsb=512, da=128, z=32, te=(1024, 3), md=(1024, 3), wm=(1024, 3)),
+    "loco": dict(dsb=361, da=54, z=32, te=(256, 2), md=(512, 3), wm=(1024, 2)),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--phase", default="world", choices=["world", "vae"])
+    ap.add_argument("--config", default="default", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=65536, help="mini-batch rows PER GPU")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="rows per step of the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def synthetic_arrays(cfg, n, seed):
+    """s_0 ~ N(0,1), s_{t+1} = s_t + 0.05 N(0,1) inside episodes of 129 steps, a ~ U(-1,1);
+    X float64 [n, 1, 2*dsb], Y float32 [n, 1, da] exactly like load_dataset_for_PhysicsVAE produces."""
+    rng = np.random.default_rng(seed)
+    T = 129
+    E = (n + T - 2) // (T - 1)
+    s = rng.standard_normal((E, 1, cfg["dsb"])) + np.cumsum(
+        np.concatenate([np.zeros((E, 1, cfg["dsb"])), 0.05 * rng.standard_normal((E, T - 1, cfg["dsb"]))], axis=1), axis=1)
+    X = np.concatenate([s[:, :-1], s[:, 1:]], axis=-1).reshape(-1, 1, 2 * cfg["dsb"])[:n]
+    Y = rng.uniform(-1, 1, size=(n, 1, cfg["da"])).astype(np.float32)
+    return np.ascontiguousarray(X), Y
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+        except Exception:
+            pass
+
+    def stop(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for t, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        f = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
+        sm = [f(r[0]) for r in rows if f(r[0]) is not None]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": f(rows[0][1]), "samples": len(rows),
+                "power_w_max": max([f(r[2]) or 0 for r in rows]), "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port of train_physics_vae.TrainModel.compute_loss + backward + Adam)
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_arm(cfg, phase, rows, steps, warmup, seed=0):
+    from oracle import pvae_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(seed)
+    m = orc.OracleModel(cfg["dsb"], cfg["da"], cfg["z"], orc.gen_layers(*cfg["te"]), orc.gen_layers(*cfg["md"]), orc.gen_layers(*cfg["wm"]))
+    X, Y = synthetic_arrays(cfg, rows, seed + 1)
+    tr = orc.OracleTrainer(m, X, Y, batch_size=rows, max_iter_world_model=0 if phase == "vae" else 10 ** 9)
+    for _ in range(warmup):
+        tr.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step()
+    dt = time.perf_counter() - t0
+    return rows * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    value, ms, cores = cpu_arm(cfg, args.phase, args.cpu_sample, steps, warmup)
+    from oracle import pvae_oracle as orc
+    sample = "%d steps of %d transitions (%s phase, %s dims), fp32 torch-CPU, compute_loss+backward+Adam+item" % (
+        steps, args.cpu_sample, args.phase, args.config)
+    line = {"impl": "reference", "metric": "transitions/sec (world-model+VAE step)", "value": value, "unit": "transitions/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload(args, cfg),
+            "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload(args, cfg):
+    return {"workload": "%s-phase train step, dim_state_body=%d dim_action=%d latent=%d, TE %dx%d MD %dx%d WM %dx%d, batch=%d per GPU" % (
+        args.phase, cfg["dsb"], cfg["da"], cfg["z"], cfg["te"][0], cfg["te"][1], cfg["md"][0], cfg["md"][1], cfg["wm"][0], cfg["wm"][1],
+        args.batch), "phase": args.phase, "dims": args.config, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+        "precision": args.precision if args.impl == "b200" else "fp32", "parallelism": "dp%d" % args.gpus,
+        "resident_rows_per_gpu": 4 * args.batch,
+        "l2": "not flushed: the per-step working set (resident transitions + activations, >1 GB at batch 65536) exceeds the 126 MB L2"}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------------------------
+def run_b200(args, cfg):
+    import torch.distributed as dist
+    from physicsvae_b200 import _abi, parallel
+    from physicsvae_b200 import train_physics_vae as tp
+    from physicsvae_b200 import torch_models as tm
+    from oracle import pvae_oracle as orc     # FLOP model + (rank 0) the cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    B, phase = args.batch, args.phase
+    n_rows = 4 * B
+
+    class BenchTrainer(tp.TrainModel):
+        dp_local_shards = True
+
+        def load_dataset(self, file):
+            X, Y = synthetic_arrays(cfg, n_rows, seed=1000 + rank)
+            return tm.DatasetBase(X, Y, normalize_x=False, normalize_y=False)
+
+        def _local_rows(self, batch_size):
+            return batch_size          # weak scaling: `batch` rows per GPU, each rank owns its shard of the global batch
+
+    box = lambda n: tp.Box(low=-np.ones(n), high=np.ones(n), dtype=np.float64)
+    custom = dict(tp.MODEL_CONFIG)
+    custom.update(observation_space=box(2 * cfg["dsb"]), observation_space_body=box(cfg["dsb"]), observation_space_task=box(cfg["dsb"]),
+                  action_space=box(cfg["da"]), engine_precision=args.precision, engine_max_batch=B)
+    config = {"max_iter_world_model": 0 if phase == "vae" else 10 ** 9, "model": {"custom_model": "physics_vae", "custom_model_config": custom},
+              "lr": 5e-4, "lr_schedule": "step", "lr_schedule_params": {"step_size": 50, "gamma": 0.7}, "weight_decay": 0.0,
+              "dataset_train": ["synthetic"], "dataset_test": None, "loss": "MSE", "loss_test": "MSE", "batch_size": B,
+              "latent_dim": cfg["z"], "latent_prior_type": "normal_zero_mean_one_std", "act_fn": "relu",
+              "MD_width": cfg["md"][0], "MD_depth": cfg["md"][1], "TE_width": cfg["te"][0], "TE_depth": cfg["te"][1],
+              "lookahead": 1, "world_model_width": cfg["wm"][0], "world_model_depth": cfg["wm"][1], "vae_kl_coeff": 1.0,
+              "motor_decoder_a_rec_coeff": 1.0, "world_model_s_rec_coeff": 0.0, "vae_cycle_coeff": 1e-3,
+              "engine_precision": args.precision, "optimizer_capturable": True}
+    torch.manual_seed(0)                      # same init on every rank (replicated parameters)
+    tr = BenchTrainer(config)
+    if phase == "vae":
+        tr.model.set_learnable_task_encoder(True); tr.model.set_learnable_motor_decoder(True); tr.model.set_learnable_world_model(False)
+        tr.read_loss_fn_coeff(world=False)
+    eng, model = tr.engine, tr.model
+    nets = ["world_model"] if phase == "world" else ["task_encoder", "motor_decoder"]
+    grads = [model.flat_grads(n) for n in nets]
+
+    def one_step():
+        """The hot path on rows [cursor, cursor + B) of this rank's resident shard."""
+        if phase == "world":
+            eng.world_step(B, s_coeff=1.0)
+        else:
+            eng.vae_step(B, eps=None, seed=1234, offset=rank, noise=True, a_coeff=1.0, kl_coeff=1.0, cyc_coeff=1e-3)
+        if world > 1:
+            parallel.allreduce_avg_(grads)
+        tr.optimizer.step()
+        eng.sync_weights(nets)
+        eng.advance_cursor(B, B, n_rows)
+
+    eng.set_cursor(0)
+    model.sync_weights()
+    n0 = _abi.launch_count()
+    one_step()
+    launches_per_step = _abi.launch_count() - n0
+    for _ in range(2):
+        one_step()
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    one_step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = g
+        except Exception as e:  # noqa
+            if rank == 0:
+                print("[bench] CUDA graph capture failed (%s); running eagerly" % (repr(e)[:200]), file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    run = (lambda: graph.replay()) if graph is not None else one_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        run()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        run()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    loss_after = float(eng.loss[0].item())
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---- roofline leg: the tensor-core kernel sequence alone (forward + loss + backward launches of one step), CUDA events
+    #      on the launching stream around pvae_{world,vae}_step only (no Adam / all-reduce / shadow refresh)
+    fl_world, fl_vae = orc.flops_per_transition(cfg["dsb"], cfg["da"], cfg["z"], [cfg["te"][0]] * cfg["te"][1],
+                                                [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
+    flops_step = (fl_world if phase == "world" else fl_vae) * B
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    n0 = _abi.launch_count()
+    for i in range(max(5, min(args.steps, 20))):
+        k0.record()
+        if phase == "world":
+            eng.world_step(B, s_coeff=1.0)
+        else:
+            eng.vae_step(B, eps=None, seed=1234, offset=rank, noise=True, a_coeff=1.0, kl_coeff=1.0, cyc_coeff=1e-3)
+        k1.record()
+        k1.synchronize()
+        kms.append(k0.elapsed_time(k1))
+        eng.advance_cursor(B, B, n_rows)
+    gemm_launches = {"world": 3 * cfg["wm"][1] + 4}.get(phase)
+    kernel_ms = statistics.median(kms)
+    pk, pk_src = peaks()
+    achieved = flops_step / (kernel_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_src + " (sustained; burst %.1f)" % pk["bf16_tflops"],
+                "kernel": "pvae_gemm_kernel", "kernel_ms_per_step": kernel_ms, "algorithmic_flops_per_step": flops_step,
+                "whole_step_tflops": flops_step / (ms / args.steps * 1e-3) / 1e12}
+
+    # ---- end-to-end leg: the reference-facing call with HOST buffers.  Per step, exactly what torch_models.TrainModel.step
+    #      does per mini-batch: x, y (pinned host fp32, as the DataLoader hands them over) -> device, compute_loss, backward,
+    #      optimizer.step, loss.item()
+    xh = torch.from_numpy(synthetic_arrays(cfg, B, seed=77 + rank)[0]).float().pin_memory()
+    yh = torch.from_numpy(synthetic_arrays(cfg, B, seed=77 + rank)[1]).pin_memory()
+    h2d = xh.numel() * 4 + yh.numel() * 4
+
+    def e2e_step():
+        x = xh.to(dev, non_blocking=True)
+        y = yh.to(dev, non_blocking=True)
+        loss = tr.compute_loss(y, x)
+        loss.backward()
+        tr.optimizer.step()
+        model.mark_weights_dirty()
+        return loss.item()
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ems = e0.elapsed_time(e1)
+    t = torch.tensor([ems], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ems = float(t.item())
+    e2e = {"value": B * world * e2e_steps / (ems * 1e-3), "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "steps": e2e_steps, "ms_per_step": ems / e2e_steps, "api": "TrainModel.compute_loss(y, x) + backward + optimizer.step + loss.item()"}
+
+    if rank == 0:
+        line = {"metric": "transitions/sec (world-model+VAE step)", "value": value, "unit": "transitions/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3(fp32-accurate)",
+                "data": "synthetic", "config": workload(args, cfg), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+                "cuda_graph": graph is not None, "roofline": roofline, "loss_after": loss_after}
+        if not args.no_cpu_baseline:
+            rows = args.cpu_sample
+            v, cms, cores = cpu_arm(cfg, phase, rows, 3, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port",
+                                    "sample": "3 steps of %d transitions (%s phase), oracle port of compute_loss+backward+Adam, fp32 torch-CPU" % (rows, phase)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    c = CONFIGS[a.config]
+    if a.impl == "reference":
+        run_reference(a, c)
+    else:
+        run_b200(a, c)

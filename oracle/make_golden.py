@@ -1,0 +1,113 @@
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF (imported unchanged under oracle/ref_stub) in this container.
+Run: python oracle/make_golden.py      (needs /root/reference; the fixtures are committed, this script documents them)
+
+Fixtures
+  ref_small_step.npz   reduced-width model (dsb 37, da 11, z 8): seeded normc init state dict, a 64-row transition batch,
+                       eps, and the reference's forward outputs, world/VAE losses and every parameter gradient.
+  ref_loco_ckpt.npz    outputs of the shipped checkpoint data/pretrained/loco_modelV1.pt on a seeded input
+                        -- weights are NOT copied (12.5 MB), only sha256 + outputs.
+  ref_dataset.npz      load_dataset_for_PhysicsVAE on a synthetic README-format pickle: X / Y arrays and batch sizes.
+"""
+import hashlib
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refload, pvae_oracle as orc  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def small_step():
+    tpv, tm, rmt = refload.load()
+    dsb, da, z = 37, 11, 8
+    te, md, wm = tpv.gen_layers(48, 2), tpv.gen_layers(64, 3), tpv.gen_layers(96, 2)
+    for l in (te, md, wm):
+        l[-1]["init_weight"] = {"name": "normc", "std": 0.3}
+    torch.manual_seed(0)
+    model = refload.build_reference_model(dsb, da, z, te, md, wm, vf_layers=tpv.gen_layers(48, 2))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    B = 64
+    data = orc.synthetic_episodes(1, 129, dsb, da, seed=5)
+    X, Y = orc.build_transitions(data["episodes"], num_samples=B)
+    x = torch.Tensor(X)
+    y = torch.Tensor(Y)
+    out = {"B": B, "dsb": dsb, "da": da, "z": z, "X": X, "Y": Y}
+    for k, v in sd.items():
+        out["sd/" + k] = v.numpy()
+    # forward with the noise draw pinned: eps is the first RNG draw of forward()
+    torch.manual_seed(7)
+    eps = torch.randn(B, z)
+    out["eps"] = eps.numpy()
+    torch.manual_seed(7)
+    logits, state = model(input_dict={"obs": x[:, 0, :], "obs_flat": x[:, 0, :]}, state=None, seq_lens=None)
+    out["logits"] = logits.detach().numpy()
+    out["mu"] = model._cur_task_encoder_mu.detach().numpy()
+    out["logvar"] = model._cur_task_encoder_logvar.detach().numpy()
+    out["z_task"] = model._cur_task_encoder_variable.detach().numpy()
+    out["future"] = model._cur_future_state.detach().numpy()
+    out["value"] = model._cur_value.detach().numpy()
+    for world in (True, False):
+        model.zero_grad()
+        model.set_learnable_task_encoder(not world)
+        model.set_learnable_motor_decoder(not world)
+        model.set_learnable_world_model(world)
+        torch.manual_seed(7)
+        loss = refload.reference_compute_loss(model, x, y, world, kl_coeff=1.0, cyc_coeff=0.05)
+        loss.backward()
+        tag = "world" if world else "vae"
+        out[tag + "/loss"] = float(loss)
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                out[tag + "/grad/" + k] = p.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "ref_small_step.npz"), **out)
+    print("ref_small_step.npz: world loss %.8f vae loss %.8f" % (out["world/loss"], out["vae/loss"]))
+
+
+def loco_ckpt():
+    tpv, tm, rmt = refload.load()
+    path = os.path.join(refload.REFERENCE, "data", "pretrained", "loco_modelV1.pt")
+    sha = hashlib.sha256(open(path, "rb").read()).hexdigest()
+    model = refload.build_reference_model(361, 54, 32, tpv.gen_layers(256, 2), tpv.gen_layers(512, 3), tpv.gen_layers(1024, 2))
+    model.load_weights(path)
+    x = torch.randn(4, 722, generator=torch.Generator().manual_seed(1234))
+    model.latent_prior_noise = False
+    logits, _ = model(input_dict={"obs": x, "obs_flat": x}, state=None, seq_lens=None)
+    np.savez_compressed(os.path.join(OUT, "ref_loco_ckpt.npz"), sha256=sha, x=x.numpy(), logits=logits.detach().numpy(),
+                        mu=model._cur_task_encoder_mu.detach().numpy(), logvar=model._cur_task_encoder_logvar.detach().numpy(),
+                        future=model._cur_future_state.detach().numpy(), value=model._cur_value.detach().numpy(),
+                        keys=np.array(list(model.state_dict().keys())))
+    print("ref_loco_ckpt.npz: sha256 %s a[0,:4] %s" % (sha[:12], logits[0, :4].tolist()))
+
+
+def dataset():
+    tpv, tm, rmt = refload.load()
+    data = orc.synthetic_episodes(3, 17, 5, 3, seed=9)
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "demo.pkl")
+        with open(f, "wb") as fh:
+            pickle.dump(data, fh)
+        ds = tpv.load_dataset_for_PhysicsVAE([f], num_samples=None, lookahead=1)
+        ds_cap = tpv.load_dataset_for_PhysicsVAE([f], num_samples=20, lookahead=1)
+        ds_rel = tpv.load_dataset_for_PhysicsVAE([f], num_samples=None, lookahead=2, cond="rel", use_a_gt=True)
+        loader = torch.utils.data.DataLoader(ds, batch_size=7, shuffle=None)
+        sizes = [int(xb.shape[0]) for xb, yb in loader]
+        x0, y0 = next(iter(loader))
+    np.savez_compressed(os.path.join(OUT, "ref_dataset.npz"), pickle_bytes=np.frombuffer(pickle.dumps(data), dtype=np.uint8),
+                        X=ds.X, Y=ds.Y, X_cap=ds_cap.X, Y_cap=ds_cap.Y, X_rel=ds_rel.X, Y_rel=ds_rel.Y,
+                        batch_sizes=np.array(sizes), x0=x0.numpy(), y0=y0.numpy())
+    print("ref_dataset.npz: X %s %s Y %s %s batches %s" % (ds.X.shape, ds.X.dtype, ds.Y.shape, ds.Y.dtype, sizes))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    small_step()
+    loco_ckpt()
+    dataset()

@@ -214,8 +214,8 @@ def loss_and_grads(model, x, y, world, **kw):
     finally:
         model.params = saved
     grads = {k: t.grad.detach().clone() for k, t in leaf.items() if t.grad is not None}
-    parts = {k: float(v) for k, v in parts.items()}
-    return float(total), parts, grads
+    parts = {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in parts.items()}
+    return float(total.detach()), parts, grads
 
 
 class OracleTrainer:

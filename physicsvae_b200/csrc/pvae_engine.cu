@@ -156,7 +156,8 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   p.epi.n_valid = d.N;
   const int units = p.m_tiles * n_tiles * splits;
   const int grid = units < dev.sms ? units : dev.sms;
-  pvae_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+  GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act);
+  fn<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return PVAE_OK;
@@ -408,7 +409,9 @@ uint64_t pvae_launch_count(void) { return g_launches.load(); }
 
 static int ensure_kernel_attr(Device& dev) {
   if (dev.attr_set) return PVAE_OK;
-  CK(cudaFuncSetAttribute(pvae_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  for (int epi = 0; epi < 4; ++epi)
+    for (int act = 0; act <= ACT_SWISH; ++act)
+      CK(cudaFuncSetAttribute(select_kernel(epi, act), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   dev.attr_set = true;
   return PVAE_OK;
 }

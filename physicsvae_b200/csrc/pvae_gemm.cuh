@@ -32,8 +32,10 @@ constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;    // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 256;              // warps 0..3: TMA / MMA / TMEM-alloc / idle, warps 4..7: epilogue
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;                  // two warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warps 0..3: TMA / MMA / TMEM-alloc / idle, warps 4..11: epilogue
+constexpr int BIAS_BYTES = EPI_WARPS * MAX_BN * 4;   // per-epilogue-warp bias tile
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + BIAS_BYTES;
 
 enum : int { EPI_STORE = 0, EPI_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD = 3 };
 enum : int { ACT_LINEAR = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3, ACT_ELU = 4, ACT_SWISH = 5 };
@@ -101,19 +103,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return done;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("pvae_gemm: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0) {
+    if ((++spins & 0xFFFu) == 0) {
       uint64_t t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000ull) {   // 4 s
-        printf("pvae_gemm: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
-               (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-        __trap();
-      }
+      else if (t - t0 > 4000000000ull) mbar_timeout(bar, parity);   // 4 s
     }
   }
 }
@@ -180,7 +182,7 @@ __device__ __forceinline__ uint32_t umma_idesc(int n, int a_major, int b_major) 
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float act_fwd(float v, int act) {
+template <int act> __device__ __forceinline__ float act_fwd(float v) {
   switch (act) {
     case ACT_RELU:    return fmaxf(v, 0.f);
     case ACT_TANH:    return tanhf(v);
@@ -191,7 +193,7 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
   }
 }
 // derivative of the activation expressed through its OUTPUT y (what the forward pass stored)
-__device__ __forceinline__ float act_bwd_from_out(float y, int act) {
+template <int act> __device__ __forceinline__ float act_bwd_from_out(float y) {
   switch (act) {
     case ACT_RELU:    return y > 0.f ? 1.f : 0.f;
     case ACT_TANH:    return 1.f - y * y;
@@ -210,15 +212,22 @@ __device__ __forceinline__ float bf16_lo_part(float v) {  // v - bf16(v)
 
 // Load 32 consecutive bf16 (hi plane + optional lo plane) of one row as floats; columns >= nvalid read as 0.
 __device__ __forceinline__ void load_row32(const __nv_bfloat16* base, int64_t ps, int planes, int nvalid, float (&v)[32]) {
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ps & 7) == 0);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ps & 7) == 0) && nvalid == 32;
+  if (vec_ok) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = 0.f;
-  for (int pl = 0; pl < planes; ++pl) {
-    const __nv_bfloat16* p = base + pl * ps;
-    if (vec_ok && nvalid >= 32) {
+    for (int g = 0; g < 4; ++g) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(base) + g);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[g * 8 + 2 * j]     = __uint_as_float(w[j] << 16);
+        v[g * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    }
+    if (planes > 1) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint4 q = __ldg(reinterpret_cast<const uint4*>(p) + g);
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + ps) + g);
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -226,36 +235,50 @@ __device__ __forceinline__ void load_row32(const __nv_bfloat16* base, int64_t ps
           v[g * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
         }
       }
-    } else {
+    }
+  } else {
+    const unsigned short* p0 = reinterpret_cast<const unsigned short*>(base);
+    const unsigned short* p1 = reinterpret_cast<const unsigned short*>(base + ps);
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nvalid) v[i] += __bfloat162float(p[i]);
+    for (int i = 0; i < 32; ++i) {
+      float t = 0.f;
+      if (i < nvalid) {
+        t = __uint_as_float((uint32_t)__ldg(p0 + i) << 16);
+        if (planes > 1) t += __uint_as_float((uint32_t)__ldg(p1 + i) << 16);
+      }
+      v[i] = t;
     }
   }
 }
 // Store 32 consecutive values of one row as bf16 hi (+lo) planes; 8-column groups that start at or past
 // nvalid are skipped, columns past nvalid inside a written group are zero. Row base must be 16B aligned.
-__device__ __forceinline__ void store_row32(__nv_bfloat16* base, int64_t ps, int planes, int nvalid, const float (&v)[32]) {
+__device__ __forceinline__ void store_row32(__nv_bfloat16* base, int64_t ps, int planes, int nvalid, float (&v)[32]) {
+  if (nvalid < 32) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? v[i] : 0.f;
+  }
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     if (g * 8 < nvalid) {
-      float t[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = (g * 8 + j < nvalid) ? v[g * 8 + j] : 0.f;
       uint4 q;
-      q.x = pack_bf16x2(t[0], t[1]); q.y = pack_bf16x2(t[2], t[3]);
-      q.z = pack_bf16x2(t[4], t[5]); q.w = pack_bf16x2(t[6], t[7]);
+      q.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); q.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+      q.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); q.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
       *(reinterpret_cast<uint4*>(base) + g) = q;
       if (planes > 1) {
         uint4 l;
-        l.x = pack_bf16x2(bf16_lo_part(t[0]), bf16_lo_part(t[1]));
-        l.y = pack_bf16x2(bf16_lo_part(t[2]), bf16_lo_part(t[3]));
-        l.z = pack_bf16x2(bf16_lo_part(t[4]), bf16_lo_part(t[5]));
-        l.w = pack_bf16x2(bf16_lo_part(t[6]), bf16_lo_part(t[7]));
+        l.x = pack_bf16x2(bf16_lo_part(v[g * 8 + 0]), bf16_lo_part(v[g * 8 + 1]));
+        l.y = pack_bf16x2(bf16_lo_part(v[g * 8 + 2]), bf16_lo_part(v[g * 8 + 3]));
+        l.z = pack_bf16x2(bf16_lo_part(v[g * 8 + 4]), bf16_lo_part(v[g * 8 + 5]));
+        l.w = pack_bf16x2(bf16_lo_part(v[g * 8 + 6]), bf16_lo_part(v[g * 8 + 7]));
         *(reinterpret_cast<uint4*>(base + ps) + g) = l;
       }
     }
   }
+}
+__device__ __forceinline__ void store_f32_row32(float* dst, int64_t sn, int nvalid, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < nvalid) dst[(int64_t)i * sn] = v[i];
 }
 // Transposing butterfly: on return lane j holds sum over the 32 lanes of v[j].
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -273,8 +296,116 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// epilogue of one 32-column chunk of one output row (compile-time epilogue type and activation keep
+// the instruction footprint of every instantiation small enough to stay in the instruction cache)
+// ------------------------------------------------------------------------------------------------
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float (&v)[32], const float* bias_s, int row, bool row_ok,
+                                               int col0, int nv, int row0, int lane, double& loss_local) {
+  if (EPI == EPI_WGRAD) {
+    if (row_ok) {
+      float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
+      const int64_t sn = e.f32_sn;
+      if (e.f32_atomic) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nv) atomicAdd(dst + (int64_t)i * sn, v[i]);
+      } else {
+        store_f32_row32(dst, sn, nv, v);
+      }
+    }
+    return;
+  }
+  if (EPI != EPI_DGRAD) {
+    if (e.bias) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + g * 4);
+        v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
+      }
+    }
+  }
+  if (EPI == EPI_STORE) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
+    if (row_ok) {
+      if (e.out_f32) store_f32_row32(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn, e.f32_sn, nv, v);
+      if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
+    }
+  } else if (EPI == EPI_MSE) {
+    float t[32];
+    if (row_ok) {
+      const int64_t arow = (int64_t)row + (e.aux_dyn ? row0 : 0);
+      load_row32(e.aux + arow * e.aux_ld + col0, e.aux_ps, e.aux_planes, nv, t);
+      if (e.out_f32) store_f32_row32(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn, e.f32_sn, nv, v);
+    }
+    float sq = 0.f;
+    const float scale = e.scale;
+    float d[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float di = (row_ok && i < nv) ? (v[i] - t[i]) : 0.f;
+      sq += di * di;
+      d[i] = scale * di;
+    }
+    loss_local += (double)sq;
+    if (row_ok) {
+      if (e.out2) store_row32(e.out2 + (int64_t)row * e.out2_ld + col0, e.out2_ps, e.out2_planes, nv, v);
+      if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, d);
+    }
+    if (e.colsum) {
+      const float s = warp_colsum32(d, lane);
+      if (lane < nv) atomicAdd(e.colsum + col0 + lane, s);
+    }
+  } else {  // EPI_DGRAD
+    if (row_ok) {
+      if (e.add) {
+        float a[32];
+        load_row32(e.add + (int64_t)row * e.add_ld + col0, e.add_ps, e.add_planes, nv, a);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += a[i];
+      }
+      if (ACT != ACT_LINEAR) {
+        float y[32];
+        load_row32(e.aux + (int64_t)row * e.aux_ld + col0, e.aux_ps, e.aux_planes, nv, y);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= act_bwd_from_out<ACT>(y[i]);
+      }
+      if (e.out_f32) store_f32_row32(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn, e.f32_sn, nv, v);
+      if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
+    }
+    if (e.colsum) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (row_ok && i < nv) ? v[i] : 0.f;
+      const float s = warp_colsum32(v, lane);
+      if (lane < nv) atomicAdd(e.colsum + col0 + lane, s);
+    }
+  }
+}
+
+// position inside the (pass, segment, k-block) iteration space of one output tile
+struct KIter {
+  int pass, seg, r;
+  __device__ __forceinline__ void init(int it, int kb0, int kb_total) {
+    pass = it / kb_total;
+    const int rem = it - pass * kb_total;
+    seg = rem >= kb0 ? 1 : 0;
+    r = seg ? rem - kb0 : rem;
+  }
+  __device__ __forceinline__ void next(int kb0, int kb1) {
+    ++r;
+    if (r == (seg ? kb1 : kb0)) {
+      r = 0;
+      if (seg == 0 && kb1 > 0) seg = 1;
+      else { seg = 0; ++pass; }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle atoms need 1024 B alignment
@@ -284,7 +415,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));    // generic pointer to the aligned base
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  float* bias_all = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -296,7 +429,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -324,11 +457,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         const int m_tile = tile / p.n_tiles;
         const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
         const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
-        for (int it = it_begin; it < it_end; ++it) {
-          const int pass = it / kb_total;
-          int r = it - pass * kb_total;
-          const int seg = (r >= p.kb[0]) ? 1 : 0;
-          if (seg) r -= p.kb[0];
+        KIter ki; ki.init(it_begin, p.kb[0], kb_total);
+        for (int it = it_begin; it < it_end; ++it, ki.next(p.kb[0], p.kb[1])) {
+          const int pass = ki.pass, seg = ki.seg, r = ki.r;
           const int a_plane = (pass == 2) ? 1 : 0;
           const int b_plane = (pass == 1) ? 1 : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -368,11 +499,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
-        for (int it = it_begin; it < it_end; ++it) {
-          const int pass = it / kb_total;
-          int r = it - pass * kb_total;
-          const int seg = (r >= p.kb[0]) ? 1 : 0;
-          if (seg) r -= p.kb[0];
+        KIter ki; ki.init(it_begin, p.kb[0], kb_total);
+        for (int it = it_begin; it < it_end; ++it, ki.next(p.kb[0], p.kb[1])) {
+          const int seg = ki.seg, r = ki.r;
           int k16 = (p.klen[seg] - r * BK + 15) >> 4;
           k16 = k16 > 4 ? 4 : (k16 < 1 ? 1 : k16);
           mbar_wait(full_bar(stage), phase);
@@ -393,22 +522,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   } else if (warp >= 4) {
     // ================================ epilogue ================================
     const EpiParams& e = p.epi;
-    const int q = warp - 4;                       // TMEM lane quarter this warp may read
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 4) >> 2;             // which of the two interleaved chunk sets
+    float* bias_s = bias_all + (warp - 4) * MAX_BN;
+    const int m_valid = e.m_valid, n_valid = e.n_valid;
+    const float* bias = (EPI == EPI_STORE || EPI == EPI_MSE) ? e.bias : nullptr;
     int acc = 0; uint32_t acc_phase = 0;
     double loss_local = 0.0;
+    const int nchunks = (bn + 31) >> 5;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int tile = u / p.splits;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int row = m_tile * BM + q * 32 + lane;
-      const bool row_ok = row < e.m_valid;
+      const bool row_ok = row < m_valid;
+      if (bias) {                                 // stage this tile's bias slice once, padded with zeros
+        __syncwarp();
+        for (int j = lane; j < nchunks * 32; j += 32) {
+          const int col = n_tile * bn + j;
+          bias_s[j] = (j < bn && col < n_valid) ? __ldg(bias + col) : 0.f;
+        }
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int nchunks = (bn + 31) >> 5;
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = half; c < nchunks; c += 2) {
         const int col0 = n_tile * bn + c * 32;
-        if (col0 >= e.n_valid) break;             // warp-uniform
-        int nv = e.n_valid - col0; nv = nv > 32 ? 32 : nv;
+        if (col0 >= n_valid) break;               // warp-uniform
+        int nv = n_valid - col0; nv = nv > 32 ? 32 : nv;
         const int tile_nv = bn - c * 32;          // columns of this chunk that belong to this tile
         if (tile_nv < nv) nv = tile_nv;
         uint32_t raw[32];
@@ -417,97 +558,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-
-        if (e.type == EPI_WGRAD) {
-          if (row_ok) {
-            float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < nv) {
-                if (e.f32_atomic) atomicAdd(dst + (int64_t)i * e.f32_sn, v[i]);
-                else dst[(int64_t)i * e.f32_sn] = v[i];
-              }
-            }
-          }
-          continue;
-        }
-
-        if (e.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += (i < nv) ? __ldg(e.bias + col0 + i) : 0.f;
-        }
-
-        if (e.type == EPI_STORE) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_fwd(v[i], e.act);
-          if (row_ok) {
-            if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
-            if (e.out_f32) {
-              float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
-            }
-          }
-        } else if (e.type == EPI_MSE) {
-          float t[32];
-          const int64_t arow = (int64_t)row + (e.aux_dyn ? row0 : 0);
-          if (row_ok) load_row32(e.aux + arow * e.aux_ld + col0, e.aux_ps, e.aux_planes, nv, t);
-          if (row_ok) {
-            if (e.out2) store_row32(e.out2 + (int64_t)row * e.out2_ld + col0, e.out2_ps, e.out2_planes, nv, v);
-            if (e.out_f32) {
-              float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
-            }
-          }
-          float sq = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float d = (row_ok && i < nv) ? (v[i] - t[i]) : 0.f;
-            sq += d * d;
-            v[i] = e.scale * d;
-          }
-          loss_local += (double)sq;
-          if (row_ok && e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
-          if (e.colsum) {
-            const float s = warp_colsum32(v, lane);
-            if (lane < nv) atomicAdd(e.colsum + col0 + lane, s);
-          }
-        } else {  // EPI_DGRAD
-          if (row_ok) {
-            if (e.add) {
-              float a[32];
-              load_row32(e.add + (int64_t)row * e.add_ld + col0, e.add_ps, e.add_planes, nv, a);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += a[i];
-            }
-            if (e.aux) {
-              float y[32];
-              load_row32(e.aux + (int64_t)row * e.aux_ld + col0, e.aux_ps, e.aux_planes, nv, y);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= act_bwd_from_out(y[i], e.act);
-            }
-            if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
-            if (e.out_f32) {
-              float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
-            }
-          }
-          if (e.colsum) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (row_ok && i < nv) ? v[i] : 0.f;
-            const float s = warp_colsum32(v, lane);
-            if (lane < nv) atomicAdd(e.colsum + col0 + lane, s);
-          }
-        }
+        epilogue_chunk<EPI, ACT>(e, v, bias_s + c * 32, row, row_ok, col0, nv, row0, lane, loss_local);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
-    if (e.type == EPI_MSE && e.loss) {
+    if (EPI == EPI_MSE && e.loss) {
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, off);
       if (lane == 0 && loss_local != 0.0) atomicAdd(e.loss, loss_local);
@@ -517,6 +575,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+typedef void (*GemmKernelFn)(const GemmParams);
+// host-side dispatch table: [epilogue type][activation]
+template <int EPI> struct KernelRow {
+  static GemmKernelFn get(int act) {
+    switch (act) {
+      case ACT_RELU:    return pvae_gemm_kernel<EPI, ACT_RELU>;
+      case ACT_TANH:    return pvae_gemm_kernel<EPI, ACT_TANH>;
+      case ACT_SIGMOID: return pvae_gemm_kernel<EPI, ACT_SIGMOID>;
+      case ACT_ELU:     return pvae_gemm_kernel<EPI, ACT_ELU>;
+      case ACT_SWISH:   return pvae_gemm_kernel<EPI, ACT_SWISH>;
+      default:          return pvae_gemm_kernel<EPI, ACT_LINEAR>;
+    }
+  }
+};
+static inline GemmKernelFn select_kernel(int epi, int act) {
+  switch (epi) {
+    case EPI_STORE: return KernelRow<EPI_STORE>::get(act);
+    case EPI_DGRAD: return KernelRow<EPI_DGRAD>::get(act);
+    case EPI_MSE:   return pvae_gemm_kernel<EPI_MSE, ACT_LINEAR>;
+    default:        return pvae_gemm_kernel<EPI_WGRAD, ACT_LINEAR>;
+  }
 }
 
 }  // namespace pvae

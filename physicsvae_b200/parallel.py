@@ -1,0 +1,51 @@
+"""Data-parallel plumbing: the only multi-GPU strategy the path has.  One process per GPU; every
+global mini-batch [lo, hi) is cut into contiguous per-rank row ranges; each rank's loss coefficients are weighted by
+n_rank * R / n so that the AVERAGE of the per-rank gradients (one all-reduce over the flat fp32 gradient buffers) equals
+the gradient of the global mean loss exactly, also for ragged last batches.  torch.distributed (NCCL over NVLink on GPUs,
+gloo in the CPU tests) is plumbing; there is no other collective on the path."""
+import torch
+import torch.distributed as dist
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_rows(lo, hi, r, world):
+    """Contiguous slice of rows [lo, hi) owned by rank r of `world`: sizes differ by at most one, earlier ranks larger."""
+    n = hi - lo
+    base, rem = divmod(n, world)
+    start = lo + r * base + min(r, rem)
+    return start, start + base + (1 if r < rem else 0)
+
+
+def max_shard_rows(batch_size, world):
+    return (batch_size + world - 1) // world
+
+
+def shard_weight(lo, hi, r, world):
+    """n_r * R / n: multiply the rank's loss coefficients by this and all-reduce-AVERAGE the gradients."""
+    s, e = shard_rows(lo, hi, r, world)
+    return (e - s) * world / float(hi - lo)
+
+
+def allreduce_avg_(tensors, group=None):
+    """In-place average of the given flat tensors over all ranks (one collective per tensor; a step has at most three:
+    two gradient buffers + the loss slots)."""
+    w = world_size()
+    if w == 1:
+        return
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.div_(w)
+
+
+def broadcast_(tensors, src=0):
+    if world_size() == 1:
+        return
+    for t in tensors:
+        dist.broadcast(t, src=src)

@@ -1,0 +1,306 @@
+"""Host-side mirror of the reference's generic trainer (torch_models.py:21-216): `get_lr_scheduler`, `DatasetBase`,
+`get_loss_fn`, `TrainModel` with the Ray Tune `Trainable` protocol (`setup(config)`, `step() -> dict`,
+`save_checkpoint(dir) -> path`, `load_checkpoint(path)`), plus the `WorldModel` / `Motor` views the task framing names.
+
+What changed underneath: the mini-batch loop does not collate tensors on the host.  The dataset is converted once into a
+GPU-resident transition buffer (engine.ingest) and every mini-batch is a row range of it; forward, loss and backward are
+one library call; the loss is accumulated on the device and read back once per epoch instead of `.item()` per batch.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.optim as optim
+import torch.utils.data as data
+
+from . import _abi, parallel
+
+try:  # pragma: no cover - ray is not installed in the build image
+    from ray import tune
+    _TrainableBase = tune.Trainable
+except Exception:  # noqa
+    import copy as _copy
+
+    class _TrainableBase(object):
+        """Stand-in for ray.tune.Trainable: the constructor calls setup(config), train() calls step()."""
+
+        def __init__(self, config=None, logger_creator=None):
+            self.config = config or {}
+            self._iteration = 0
+            self.setup(_copy.deepcopy(self.config))
+
+        def train(self):
+            result = dict(self.step())
+            self._iteration += 1
+            result["training_iteration"] = self._iteration
+            return result
+
+        @property
+        def training_iteration(self):
+            return self._iteration
+
+        def save(self, checkpoint_dir):
+            os.makedirs(checkpoint_dir, exist_ok=True)
+            return self.save_checkpoint(checkpoint_dir)
+
+        def restore(self, checkpoint_path):
+            self.load_checkpoint(checkpoint_path)
+
+        def stop(self):
+            pass
+
+EPSILON = np.finfo(np.float32).eps
+
+
+def get_lr_scheduler(optimizer, name, params):
+    """torch_models.py:21-37."""
+    lr_scheduler = None
+    if name == "cosine":
+        lr_scheduler = optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=params["T_max"])
+    elif name == "cosine_restart":
+        lr_scheduler = optim.lr_scheduler.CosineAnnealingWarmRestarts(optimizer, T_0=params["T_0"], T_mult=params["T_mult"])
+    elif name == "step":
+        lr_scheduler = optim.lr_scheduler.StepLR(optimizer, step_size=params["step_size"], gamma=params["gamma"])
+    return lr_scheduler
+
+
+class DatasetBase(data.Dataset):
+    """torch_models.py:39-95: holds X [N, lookahead, 2*dsb] float64 and Y [N, lookahead, da]; optional normalisation."""
+
+    def __init__(self, X, Y, normalize_x=True, normalize_y=True):
+        self.X = X
+        self.Y = Y
+        self.normalize_x = normalize_x
+        self.normalize_y = normalize_y
+        if normalize_x:
+            self.X_mean, self.X_std = np.mean(self.X, axis=0), np.std(self.X, axis=0)
+        if normalize_y:
+            self.Y_mean, self.Y_std = np.mean(self.Y, axis=0), np.std(self.Y, axis=0)
+
+    def __getitem__(self, index):
+        return self.preprocess_x(self.X[index]), self.preprocess_y(self.Y[index])
+
+    def __len__(self):
+        return len(self.X)
+
+    def preprocess_x(self, x, return_tensor=True):
+        x_new = (x - self.X_mean) / (self.X_std + EPSILON) if self.normalize_x else x
+        return torch.Tensor(x_new) if return_tensor else x_new
+
+    def postprocess_x(self, x, return_tensor=True):
+        x_new = self.X_mean + np.multiply(x, self.X_std) if self.normalize_x else x
+        return torch.Tensor(x_new) if return_tensor else x_new
+
+    def preprocess_y(self, y, return_tensor=True):
+        y_new = (y - self.Y_mean) / (self.Y_std + EPSILON) if self.normalize_y else y
+        return torch.Tensor(y_new) if return_tensor else y_new
+
+    def postprocess_y(self, y, return_tensor=True):
+        y_new = self.Y_mean + np.multiply(y, self.Y_std) if self.normalize_y else y
+        return torch.Tensor(y_new) if return_tensor else y_new
+
+    def arrays(self):
+        """(X, Y) as the engine ingests them: the preprocessed arrays, X float64 / Y float32, [N, L, dim]."""
+        X = self.preprocess_x(np.asarray(self.X), return_tensor=False)
+        Y = self.preprocess_y(np.asarray(self.Y), return_tensor=False)
+        return np.ascontiguousarray(X, dtype=np.float64), np.ascontiguousarray(Y, dtype=np.float32)
+
+
+def get_loss_fn(loss):
+    """torch_models.py:97-107.  The engine fuses the MSE reduction into the last GEMM's epilogue, so only "MSE" is
+    executable on the hot path; the others keep the reference's error behaviour for unknown names."""
+    if loss == "MSE":
+        return torch.nn.MSELoss()
+    elif loss == "MAE" or loss == "L1":
+        return torch.nn.L1Loss()
+    elif loss == "CrossEntropy":
+        return torch.nn.CrossEntropyLoss()
+    elif loss == "NLLLoss":
+        return torch.nn.NLLLoss()
+    else:
+        raise NotImplementedError
+
+
+class ResidentLoader(object):
+    """What `DataLoader(dataset, batch_size, shuffle=None)` is on the reference path (SequentialSampler, drop_last=False;
+    SURVEY.md F4): consecutive row ranges of the GPU-resident transition buffer."""
+
+    def __init__(self, dataset, batch_size, shuffle=None):
+        if shuffle:
+            raise NotImplementedError("the reference never shuffles on this path (config key typo, SURVEY.md F4)")
+        self.dataset = dataset
+        self.batch_size = int(batch_size)
+        self.n = len(dataset)
+
+    def __len__(self):
+        return (self.n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for lo in range(0, self.n, self.batch_size):
+            yield lo, min(lo + self.batch_size, self.n)
+
+
+class _DepositedLoss(torch.autograd.Function):
+    """The engine deposits gradients straight into `.grad`; `loss.backward()` of reference-style callers is a no-op."""
+
+    @staticmethod
+    def forward(ctx, anchor, loss):
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None
+
+
+class TrainModel(_TrainableBase):
+    """torch_models.py:109-216."""
+
+    def setup(self, config):
+        self.model = self.create_model(config)
+        self.prepare_data(config)
+        if not torch.cuda.is_available():
+            raise _abi.PvaeError("physicsvae_b200.TrainModel needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.model = self.model.to(self.device)
+        self.engine = self.model.engine(max_batch=self._local_rows(config.get("batch_size")),
+                                        precision=config.get("engine_precision", "bf16x3"))
+        capturable = bool(config.get("optimizer_capturable", False))     # CUDA-graph replay of the whole step (bench.py)
+        lr = config.get("lr", 1e-3)
+        self.optimizer = optim.Adam(self.model.parameters(), lr=torch.tensor(float(lr), device=self.device) if capturable else lr,
+                                    weight_decay=config.get("weight_decay", 0.0), fused=True, capturable=capturable)
+        self.lr_scheduler = get_lr_scheduler(self.optimizer, config.get("lr_schedule", None), config.get("lr_schedule_params", None))
+        self.loss_fn = get_loss_fn(config.get("loss", "MSE"))
+        self.loss_fn_test = get_loss_fn(config.get("loss_test", "MSE"))
+        if config.get("loss", "MSE") != "MSE" or config.get("loss_test", "MSE") != "MSE":
+            raise NotImplementedError("only the MSE loss is fused into the sm_100a engine")
+        self.iter = 0
+        self._upload(self.train_loader, "train")
+        self._anchor = torch.zeros((), device=self.device, requires_grad=True)
+
+    def _local_rows(self, batch_size):
+        return max(parallel.max_shard_rows(int(batch_size), parallel.world_size()), 2)
+
+    # ---- data -------------------------------------------------------------------------------------------------------
+    def load_dataset(self, file):
+        raise NotImplementedError
+
+    def get_data_loader(self, dataset, batch_size, shuffle):
+        return ResidentLoader(dataset, batch_size, shuffle)
+
+    def prepare_data(self, config):
+        dataset_train = config.get("dataset_train")
+        dataset_test = config.get("dataset_test")
+        batch_size = config.get("batch_size")
+        shuffle_data = config.get("shuffle_data")      # the CLI sets "suffle_data": this stays None
+        dataset_train = self.load_dataset(dataset_train)
+        if dataset_test is not None:
+            dataset_test = self.load_dataset(dataset_test)
+        self.train_loader = self.get_data_loader(dataset_train, batch_size, shuffle_data)
+        self.test_loader = self.get_data_loader(dataset_test, batch_size, shuffle_data) if dataset_test is not None else None
+
+    def _upload(self, loader, which):
+        """DatasetBase -> resident bf16 transition buffer (replaces per-item torch.Tensor + collate, torch_models.py:52-68)."""
+        X, Y = loader.dataset.arrays()
+        if X.ndim == 3 and X.shape[1] != 1:
+            raise NotImplementedError("lookahead > 1 is not on the hot path (train_physics_vae.py:277 hard-wires 1)")
+        n = X.shape[0]
+        eng = self.engine
+        eng.alloc_transitions(n)
+        chunk = 1 << 18
+        for lo in range(0, n, chunk):
+            hi = min(lo + chunk, n)
+            eng.ingest(torch.from_numpy(X[lo:hi].reshape(hi - lo, -1)).to(self.device),
+                       torch.from_numpy(Y[lo:hi].reshape(hi - lo, -1)).to(self.device), dst_row=lo)
+        self._resident = which
+
+    # ---- the SGD loop (torch_models.py:131-161) -----------------------------------------------------------------------
+    def step(self):
+        self.iter += 1
+        self.model.train()
+        if self._resident != "train":
+            self._upload(self.train_loader, "train")
+        loss_acc = torch.zeros((), device=self.device)
+        for lo, hi in self.train_loader:
+            loss = self.train_batch(lo, hi)
+            loss_acc += loss
+        mean_train_loss = float(loss_acc.item()) / len(self.train_loader)
+
+        mean_test_loss = 0.0
+        if self.test_loader:
+            self._upload(self.test_loader, "test")
+            loss_acc = torch.zeros((), device=self.device)
+            for lo, hi in self.test_loader:
+                loss_acc += self.batch_loss(lo, hi)
+            mean_test_loss = float(loss_acc.item()) / len(self.test_loader)
+
+        if self.lr_scheduler:
+            self.lr_scheduler.step()
+        return {"mean_train_loss": mean_train_loss, "mean_test_loss": mean_test_loss}
+
+    def train_batch(self, lo, hi):
+        """zero_grad -> compute_loss -> backward -> [all-reduce] -> Adam, for rows [lo, hi) of the resident buffer."""
+        loss = self.batch_loss(lo, hi)
+        self.optimizer.step()
+        self.model.mark_weights_dirty()
+        return loss
+
+    def batch_loss(self, lo, hi):
+        raise NotImplementedError
+
+    def create_model(self, config):
+        return config.get("model")
+
+    def compute_model(self, x):
+        return self.model(x)
+
+    def compute_loss(self, y, x):
+        raise NotImplementedError
+
+    def compute_test_loss(self, y, x):
+        return self.compute_loss(y, x)
+
+    # ---- checkpoints (torch_models.py:209-216) ---------------------------------------------------------------------------
+    def save_checkpoint(self, checkpoint_dir):
+        print(checkpoint_dir)
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        checkpoint_path = os.path.join(checkpoint_dir, "model.pth")
+        torch.save({k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}, checkpoint_path)
+        return checkpoint_path
+
+    def load_checkpoint(self, checkpoint_path):
+        self.model.load_state_dict(torch.load(checkpoint_path, map_location="cpu"))
+
+
+class WorldModel(object):
+    """View of a PhysicsVAE's world model: predicts s_{t+1} from (s_t, a_t) (`_world_model` + `forward_world`,
+    rllib_model_torch.py:682-689, 839-844).  The reference has no class of this name; this is the thin
+    alias the task framing asks for, sharing the PhysicsVAE's parameters."""
+
+    def __init__(self, physics_vae):
+        self.vae = physics_vae
+
+    def __call__(self, s, a):
+        return self.vae.forward_world(s, a)
+
+    def parameters(self):
+        return self.vae._world_model.parameters()
+
+    def state_dict(self):
+        return self.vae._world_model.state_dict()
+
+
+class Motor(object):
+    """View of the (s_body, s_task) -> z -> a stack: `_task_encoder` + reparameterisation + `_motor_decoder`
+    (rllib_model_torch.py:638-668, 773-837)."""
+
+    def __init__(self, physics_vae):
+        self.vae = physics_vae
+
+    def __call__(self, s_body, s_task, eps=None):
+        obs = torch.cat([s_body, s_task], dim=-1)
+        z_body, z_task, _ = self.vae.forward_encoder(obs, [], None, 0, eps=eps)
+        logits, _ = self.vae.forward_decoder(z_body, z_task, [], None, 0)
+        return logits[..., :self.vae.dim_action]
+
+    def parameters(self):
+        return list(self.vae._task_encoder.parameters()) + list(self.vae._motor_decoder.parameters())

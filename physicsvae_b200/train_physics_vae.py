@@ -1,0 +1,419 @@
+"""Host-side mirror of the reference's training script (train_physics_vae.py:30-521): same CLI flags, dataset format,
+layer-spec DSL, trainer config, two-phase schedule and checkpoint file set -- over the sm_100a engine.
+
+Differences that are deliberate: the dataset is built by vectorised numpy instead of an O(N) hstack loop;
+the discarded full-model forward of the world phase is not executed; `--output` works; Ray Tune's trial loop is replaced
+by a local sweep over the grid points when ray is absent.
+"""
+import argparse
+import copy
+import itertools
+import json
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from . import _abi, parallel
+from . import torch_models
+from . import rllib_model_torch as policy_models
+
+try:  # pragma: no cover
+    from gym.spaces import Box
+except Exception:  # noqa
+    class Box(object):
+        """gym.spaces.Box stand-in: only .shape / .low / .high / .dtype are used (train_physics_vae.py:216-233)."""
+
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low = np.asarray(low, dtype=dtype)
+            self.high = np.asarray(high, dtype=dtype)
+            self.shape = self.low.shape if shape is None else tuple(shape)
+            self.dtype = np.dtype(dtype)
+
+args = None      # the reference reads a module-global `args` in load_dataset (train_physics_vae.py:339, 471)
+
+
+def grid_search(values):
+    return {"grid_search": values}
+
+
+def arg_parser():
+    """Same flags and defaults as train_physics_vae.py:30-55 (list flags append to their defaults, appendix B.7)."""
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--max_iter_world_model", type=int, default=0)
+    parser.add_argument("--max_iter", type=int, default=100)
+    parser.add_argument("--num_cpus", type=int, default=1)
+    parser.add_argument("--num_gpus", type=int, default=0)
+    parser.add_argument("--data_train", action="append", required=True, type=str, default=None)
+    parser.add_argument("--data_test", action="append", type=str, default=None)
+    parser.add_argument("--num_data", type=int, default=None)
+    parser.add_argument("--output", type=str, default=None)
+    parser.add_argument("--lr", type=float, default=0.0005)
+    parser.add_argument("--lr_schedule", type=str, default="step")
+    parser.add_argument("--batch_size", type=int, default=256)
+    parser.add_argument("--checkpoint_freq", type=int, default=100)
+    parser.add_argument("--checkpoint", type=str, default=None)
+    parser.add_argument("--cluster", action="store_true")
+    parser.add_argument("--resume", action="store_true")
+    parser.add_argument("--name", type=str, default=None)
+    parser.add_argument("--local_dir", type=str, default="~/ray_results")
+    parser.add_argument("--world_model", type=str, default=None)
+    parser.add_argument("--latent_dim", type=int, default=32)
+    parser.add_argument("--vae_kl_coeff", type=float, action="append", default=[1.0])
+    parser.add_argument("--vae_cycle_coeff", type=float, action="append", default=[1e-3])
+    parser.add_argument("--latent_prior_type", type=str, action="append", default=["normal_zero_mean_one_std"])
+    # engine knob (not in the reference): "bf16x3" reproduces fp32 results, "bf16" is the fast path
+    parser.add_argument("--precision", type=str, default="bf16x3", choices=["bf16", "bf16x3"])
+    return parser
+
+
+def merge_dataset(files):
+    """train_physics_vae.py:94-114."""
+    data_all = None
+    for i, file in enumerate(files):
+        with open(file, "rb") as f:
+            data = pickle.load(f)
+            print(file, "is loaded")
+            if i == 0:
+                data_all = data
+            else:
+                for key in ("iter_per_episode", "dim_state", "dim_state_body", "dim_state_task", "dim_action", "exp_std"):
+                    assert data_all[key] == data[key]
+                data_all["episodes"] = data_all["episodes"] + data["episodes"]
+    return data_all
+
+
+def episodes_to_transitions(episodes, num_samples=None, lookahead=1, cond="abs", use_a_gt=False):
+    """Vectorised equivalent of the reference's per-transition loop (train_physics_vae.py:133-156): an episode of T steps
+    yields T - lookahead items x_i = [[sb_{i+j}, sb_{i+j+1}] for j < lookahead], y_i = [action_{i+j}]; items never cross
+    episode boundaries; `num_samples` caps the total.  Returns X float64 [N, lookahead, 2*dsb], Y [N, lookahead, da]."""
+    assert lookahead >= 1
+    Xs, Ys = [], []
+    count = 0
+    for ep in episodes:
+        num_tuples = len(ep["time"])
+        assert num_tuples >= lookahead
+        n = num_tuples - lookahead
+        if num_samples is not None:
+            n = min(n, num_samples - count)
+        if n <= 0:
+            continue
+        sb = np.asarray(ep["state_body"])
+        act = np.asarray(ep["action_gt"] if use_a_gt else ep["action"])
+        idx = np.arange(n)[:, None] + np.arange(lookahead)[None, :]            # [n, lookahead]
+        s1, s2 = sb[idx], sb[idx + 1]
+        if cond == "abs":
+            x = np.concatenate([s1, s2], axis=-1)
+        elif cond == "rel":
+            x = np.concatenate([s1, s2 - s1], axis=-1)
+        else:
+            raise NotImplementedError
+        Xs.append(x)
+        Ys.append(act[idx])
+        count += n
+    if not Xs:
+        return np.array([]), np.array([])
+    return np.concatenate(Xs, axis=0), np.concatenate(Ys, axis=0)
+
+
+def load_dataset_for_PhysicsVAE(files, num_samples=None, lookahead=1, cond="abs", use_a_gt=False):
+    """train_physics_vae.py:117-164."""
+    assert files
+    assert len(files) > 0
+    data = merge_dataset(files)
+    episodes = data["episodes"]
+    X, Y = episodes_to_transitions(episodes, num_samples, lookahead, cond, use_a_gt)
+    print("------------------Data Loaded------------------")
+    print("File:", files)
+    print("Num Episodes:", len(episodes))
+    print("Num Transitions (Tuples):", len(X))
+    print("-----------------------------------------------")
+    return torch_models.DatasetBase(X, Y, normalize_x=False, normalize_y=False)
+
+
+def create_model(config):
+    """train_physics_vae.py:166-176."""
+    model_config = config["model"]
+    obs_space = model_config["custom_model_config"]["observation_space"]
+    action_space = model_config["custom_model_config"]["action_space"]
+    return policy_models.PhysicsVAE(obs_space=obs_space, action_space=action_space, num_outputs=2 * action_space.shape[0],
+                                    model_config=model_config, name="physics_vae")
+
+
+MODEL_CONFIG = copy.deepcopy(policy_models.PhysicsVAE.DEFAULT_CONFIG)
+
+
+def gen_layers(width, depth, out_size="output", act_hidden="relu", act_out="linear", add_softmax=False):
+    """train_physics_vae.py:180-192."""
+    assert depth > 0 and width > 0
+    layers = []
+    for i in range(depth):
+        layers.append({"type": "fc", "hidden_size": width, "activation": act_hidden, "init_weight": {"name": "normc", "std": 1.0}})
+    layers.append({"type": "fc", "hidden_size": out_size, "activation": act_out, "init_weight": {"name": "normc", "std": 0.01}})
+    if add_softmax:
+        layers.append({"type": "softmax"})
+    return layers
+
+
+def inspect_dataset(file):
+    with open(file, "rb") as f:
+        data = pickle.load(f)
+        ep0 = data["episodes"][0]
+        dim_state_body = len(ep0["state_body"][0])
+        dim_action = len(ep0["action"][0])
+        return 2 * dim_state_body, dim_state_body, dim_state_body, dim_action
+
+
+def get_trainer_config(args):
+    """train_physics_vae.py:194-288: the task state at t is the body state at t+1, so dim_state = 2 * dim_state_body."""
+    assert args.max_iter_world_model <= args.max_iter
+    dim_state, dim_state_body, dim_state_task, dim_action = inspect_dataset(args.data_train[0])
+    ob_scale, ac_scale = 1000.0, 3.0
+    obs_space = Box(low=-ob_scale * np.ones(dim_state), high=ob_scale * np.ones(dim_state), dtype=np.float64)
+    obs_space_body = Box(low=-ob_scale * np.ones(dim_state_body), high=ob_scale * np.ones(dim_state_body), dtype=np.float64)
+    obs_space_task = Box(low=-ob_scale * np.ones(dim_state_task), high=ob_scale * np.ones(dim_state_task), dtype=np.float64)
+    action_space = Box(low=-ac_scale * np.ones(dim_action), high=ac_scale * np.ones(dim_action), dtype=np.float64)
+
+    model_config = {"custom_model": "physics_vae", "custom_model_config": MODEL_CONFIG.copy()}
+    custom_model_config = model_config["custom_model_config"]
+    custom_model_config["observation_space"] = obs_space
+    custom_model_config["observation_space_body"] = obs_space_body
+    custom_model_config["observation_space_task"] = obs_space_task
+    custom_model_config["action_space"] = action_space
+    custom_model_config["world_model_load_weights"] = args.world_model
+    custom_model_config["engine_precision"] = getattr(args, "precision", "bf16x3")
+
+    trainer_config = {
+        "max_iter_world_model": args.max_iter_world_model,
+        "model": model_config,
+        "lr": args.lr,
+        "lr_schedule_params": {"step_size": 50, "gamma": 0.70},
+        "lr_schedule": args.lr_schedule,
+        "weight_decay": 0.0,
+        "dataset_train": args.data_train,
+        "dataset_test": args.data_test,
+        "use_gpu": False,
+        "loss": "MSE",
+        "loss_test": "MSE",
+        "batch_size": args.batch_size,
+        "suffle_data": True,       # sic: the loader reads "shuffle_data", so nothing is shuffled
+        "latent_dim": args.latent_dim,
+        "latent_prior_type": grid_search(args.latent_prior_type),
+        "act_fn": "relu",
+        "MD_width": grid_search([512]),
+        "MD_depth": grid_search([3]),
+        "TE_width": grid_search([256]),
+        "TE_depth": grid_search([2]),
+        "lookahead": 1,
+        "world_model_width": grid_search([1024]),
+        "world_model_depth": grid_search([2]),
+        "vae_kl_coeff": grid_search(args.vae_kl_coeff),
+        "motor_decoder_a_rec_coeff": 1.0,
+        "world_model_s_rec_coeff": 0.0,
+        "vae_cycle_coeff": grid_search(args.vae_cycle_coeff),
+        "engine_precision": getattr(args, "precision", "bf16x3"),
+        "num_data": getattr(args, "num_data", None),
+    }
+    return trainer_config
+
+
+def resolve_grid(config):
+    """All grid points of a config whose leaves may be {"grid_search": [...]} (what tune.run expands)."""
+    keys = [k for k, v in config.items() if isinstance(v, dict) and set(v.keys()) == {"grid_search"}]
+    points = []
+    for combo in itertools.product(*[config[k]["grid_search"] for k in keys]):
+        c = copy.copy(config)
+        c["model"] = copy.deepcopy(config["model"])
+        for k, v in zip(keys, combo):
+            c[k] = v
+        points.append(c)
+    return points
+
+
+def update_model_config(trainer_config):
+    """train_physics_vae.py:290-311."""
+    model_config = trainer_config["model"]["custom_model_config"]
+    model_config["task_encoder_output_dim"] = trainer_config.get("latent_dim")
+    model_config["task_encoder_layers"] = gen_layers(width=trainer_config.get("TE_width"), depth=trainer_config.get("TE_depth"),
+                                                     act_hidden=trainer_config.get("act_fn"))
+    model_config["motor_decoder_layers"] = gen_layers(width=trainer_config.get("MD_width"), depth=trainer_config.get("MD_depth"),
+                                                      act_hidden=trainer_config.get("act_fn"))
+    model_config["latent_prior_type"] = trainer_config.get("latent_prior_type")
+    model_config["world_model_layers"] = gen_layers(width=trainer_config.get("world_model_width"),
+                                                    depth=trainer_config.get("world_model_depth"),
+                                                    act_hidden=trainer_config.get("act_fn"))
+    if trainer_config.get("engine_precision"):
+        model_config["engine_precision"] = trainer_config.get("engine_precision")
+
+
+class TrainModel(torch_models.TrainModel):
+    """train_physics_vae.py:313-467: world-model phase first ((a, kl, s, cyc) = (0, 0, 1, 0), world model trainable), then
+    from iteration `max_iter_world_model` on the VAE phase ((1, kl, 0, cyc), encoder + decoder trainable, world model
+    frozen but differentiated through)."""
+
+    def setup(self, config):
+        update_model_config(config)
+        self.config = config
+        self.max_iter_world_model = config.get("max_iter_world_model")
+        self.latent_prior_type = config.get("latent_prior_type")
+        self.lookahead = config.get("lookahead")
+        if self.lookahead != 1:
+            raise NotImplementedError("lookahead is hard-wired to 1 on this path (train_physics_vae.py:277)")
+        self.noise_seed = int(config.get("noise_seed", 0))
+        self._noise_step = 0
+        super().setup(config)
+        self.model.set_learnable_task_encoder(False)
+        self.model.set_learnable_motor_decoder(False)
+        self.model.set_learnable_world_model(True)
+        self.read_loss_fn_coeff(world=True)
+
+    def read_loss_fn_coeff(self, world):
+        self.vae_kl_coeff = 0.0 if world else self.config.get("vae_kl_coeff")
+        self.a_rec_coeff = 0.0 if world else self.config.get("motor_decoder_a_rec_coeff")
+        self.s_rec_coeff = 1.0 if world else self.config.get("world_model_s_rec_coeff")
+        self.vae_cycle_coeff = 0.0 if world else self.config.get("vae_cycle_coeff")
+        self.world_phase = bool(world)
+
+    def load_dataset(self, file):
+        num_data = args.num_data if args is not None else self.config.get("num_data")
+        return load_dataset_for_PhysicsVAE(file, num_samples=num_data, lookahead=self.lookahead)
+
+    def step(self):
+        if self.iter == self.max_iter_world_model:
+            # end-to-end learning of the VAE starts (train_physics_vae.py:342-350)
+            self.model.set_learnable_task_encoder(True)
+            self.model.set_learnable_motor_decoder(True)
+            self.model.set_learnable_world_model(False)
+            self.read_loss_fn_coeff(world=False)
+        return super().step()
+
+    def create_model(self, config):
+        return create_model(config)
+
+    def compute_model(self, x):
+        logits, _ = self.model(input_dict={"obs": x, "obs_flat": x}, state=None, seq_lens=None)
+        return logits[..., :logits.shape[1] // 2]
+
+    # ---- one mini-batch on the engine ---------------------------------------------------------------------------------
+    def batch_loss(self, lo, hi, eps=None):
+        """Forward + loss + backward for rows [lo, hi) of the resident buffer; gradients land in `.grad` (all-reduced when
+        torch.distributed is initialised).  Returns the global mini-batch loss as a 0-dim device tensor."""
+        eng = self.engine
+        if self.model._weights_dirty:
+            self.model.sync_weights()
+        world, r = parallel.world_size(), parallel.rank()
+        if getattr(self, "dp_local_shards", False):
+            # every rank holds its OWN shard of the global batch as rows [lo, hi) of its resident buffer (equal sizes)
+            s, e, w = lo, hi, 1.0
+        else:
+            # every rank holds the whole dataset and takes its contiguous slice of the global batch
+            s, e = parallel.shard_rows(lo, hi, r, world)
+            w = parallel.shard_weight(lo, hi, r, world)
+        n = e - s
+        if self.world_phase:
+            if self.s_rec_coeff <= 0:
+                raise ValueError("world phase needs s_rec_coeff > 0")
+            nets = ["world_model"]
+            if n > 0:
+                eng.set_cursor(s)
+                eng.world_step(n, s_coeff=self.s_rec_coeff * w)
+        else:
+            if self.s_rec_coeff and self.s_rec_coeff > 0:
+                raise NotImplementedError("world_model_s_rec_coeff > 0 in the VAE phase is not used by the CLI (it is 0.0)")
+            nets = ["task_encoder", "motor_decoder"]
+            kl = self.vae_kl_coeff if self.latent_prior_type else 0.0
+            if n > 0:
+                eng.set_cursor(s)
+                self._noise_step += 1
+                eng.vae_step(n, eps=eps, seed=self.noise_seed, offset=self._noise_step * world + r,
+                             noise=bool(self.model.latent_prior_noise), a_coeff=self.a_rec_coeff * w, kl_coeff=kl * w,
+                             cyc_coeff=self.vae_cycle_coeff * w)
+        if n == 0:
+            for name in nets:
+                self.model.flat_grads(name).zero_()
+            eng.loss.zero_()
+        if world > 1:
+            parallel.allreduce_avg_([self.model.flat_grads(name) for name in nets] + [eng.loss])
+        return eng.loss[0].clone()
+
+    def compute_loss(self, y, x, eps=None):
+        """Reference signature (train_physics_vae.py:361-435): x [B, 1, 2*dsb], y [B, 1, da] -> scalar loss.  The batch is
+        staged into the resident buffer and run through the engine; gradients are deposited into `.grad`, and the returned
+        tensor's backward() is a no-op."""
+        B = x.shape[0]
+        if B < 2:
+            raise ValueError("compute_loss needs at least 2 transitions (the reference squeezes the batch axis)")
+        eng = self.model.engine(max_batch=B)
+        self.engine = eng
+        if self._resident != "adhoc" or eng.n_rows != B:
+            eng.alloc_transitions(B)
+        eng.ingest(x.reshape(B, -1).to(self.device), y.reshape(B, -1).to(self.device))
+        self._resident = "adhoc"
+        loss = self.batch_loss(0, B, eps=eps)
+        return torch_models._DepositedLoss.apply(self._anchor, loss)
+
+    def compute_test_loss(self, y, x):
+        return self.compute_loss(y, x)
+
+    def save_checkpoint(self, checkpoint_dir):
+        """train_physics_vae.py:440-467: model.pth + model.pt + task_encoder.pt + motor_decoder.pt + world_model.pt."""
+        checkpoint_path = super().save_checkpoint(checkpoint_dir)
+        checkpoint = os.path.join(checkpoint_dir, "model.pt")
+        self.model.save_weights(checkpoint)
+        print("Saved:", checkpoint)
+        if self.model._task_encoder:
+            checkpoint = os.path.join(checkpoint_dir, "task_encoder.pt")
+            self.model.save_weights_task_encoder(checkpoint)
+            print("Saved:", checkpoint)
+        if self.model._motor_decoder:
+            checkpoint = os.path.join(checkpoint_dir, "motor_decoder.pt")
+            self.model.save_weights_motor_decoder(checkpoint)
+            print("Saved:", checkpoint)
+        if self.model._world_model:
+            checkpoint = os.path.join(checkpoint_dir, "world_model.pt")
+            self.model.save_weights_world_model(checkpoint)
+            print("Saved:", checkpoint)
+        return checkpoint_path
+
+
+def run_trial(config, max_iter, checkpoint_freq, trial_dir, restore=None):
+    """What one Ray Tune trial does (train_physics_vae.py:484-502): train() until training_iteration == max_iter,
+    checkpoint every `checkpoint_freq` iterations and at the end; results go to result.json like Tune's JSON logger."""
+    os.makedirs(trial_dir, exist_ok=True)
+    trainer = TrainModel(config)
+    if restore:
+        trainer.restore(restore)
+    last = None
+    with open(os.path.join(trial_dir, "result.json"), "a") as log:
+        for it in range(1, max_iter + 1):
+            result = trainer.train()
+            log.write(json.dumps(result) + "\n")
+            log.flush()
+            if parallel.rank() == 0 and ((checkpoint_freq and it % checkpoint_freq == 0) or it == max_iter):
+                last = trainer.save(os.path.join(trial_dir, "checkpoint_%06d" % it))
+    return trainer, last
+
+
+def main(argv=None):
+    global args
+    args = arg_parser().parse_args(argv)
+    trainer_config = get_trainer_config(args)
+    checkpoint = args.checkpoint
+    if args.checkpoint is None:
+        local_dir = os.path.expanduser(args.local_dir)
+        name = args.name or "TrainModel"
+        for i, point in enumerate(resolve_grid(trainer_config)):
+            trial_dir = os.path.join(local_dir, name, "trial_%05d" % i)
+            _, checkpoint = run_trial(point, args.max_iter, args.checkpoint_freq, trial_dir)
+    if args.output is not None:
+        # the reference's --output branch instantiates the abstract base trainer and always fails;
+        # here it exports the full state dict of the checkpoint
+        sd = torch.load(checkpoint, map_location="cpu")
+        torch.save(sd, args.output)
+        print("Model Saved:", args.output)
+    return checkpoint
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference's Python surface: CLI flags, layer-spec DSL, trainer config, dataset builder, module
+signatures and state-dict keys, seeded init, freezing, checkpoint file formats, loaders, data-parallel sharding.  CPU only."""
+import argparse
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pvae_oracle as orc
+from physicsvae_b200 import _abi, parallel
+from physicsvae_b200 import rllib_model_torch as pm
+from physicsvae_b200 import torch_models as tm
+from physicsvae_b200 import train_physics_vae as tp
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _small_model(prior="normal_zero_mean_one_std"):
+    g = np.load(os.path.join(G, "ref_small_step.npz"))
+    dsb, da, z = int(g["dsb"]), int(g["da"]), int(g["z"])
+    te, md, wm = tp.gen_layers(48, 2), tp.gen_layers(64, 3), tp.gen_layers(96, 2)
+    for l in (te, md, wm):
+        l[-1]["init_weight"] = {"name": "normc", "std": 0.3}
+    box = lambda n: tp.Box(low=-np.ones(n), high=np.ones(n), dtype=np.float64)
+    custom = dict(pm.PhysicsVAE.DEFAULT_CONFIG)
+    custom.update(observation_space=box(2 * dsb), observation_space_body=box(dsb), observation_space_task=box(dsb), action_space=box(da),
+                  task_encoder_output_dim=z, task_encoder_layers=te, motor_decoder_layers=md, world_model_layers=wm,
+                  value_fn_layers=tp.gen_layers(48, 2), latent_prior_type=prior)
+    torch.manual_seed(0)
+    m = pm.PhysicsVAE(box(2 * dsb), box(da), 2 * da, {"custom_model_config": custom}, "physics_vae")
+    return g, m
+
+
+def test_cli_flags_and_defaults():
+    a = tp.arg_parser().parse_args(["--data_train", "d.pkl"])
+    assert (a.max_iter, a.max_iter_world_model, a.lr, a.lr_schedule, a.batch_size, a.checkpoint_freq, a.latent_dim) == \
+        (100, 0, 0.0005, "step", 256, 100, 32)
+    assert a.vae_kl_coeff == [1.0] and a.vae_cycle_coeff == [1e-3] and a.latent_prior_type == ["normal_zero_mean_one_std"]
+    assert a.local_dir == "~/ray_results" and a.data_test is None and a.num_data is None
+    # list flags append to their defaults
+    b = tp.arg_parser().parse_args(["--data_train", "a", "--data_train", "b", "--vae_kl_coeff", "0.5"])
+    assert b.data_train == ["a", "b"] and b.vae_kl_coeff == [1.0, 0.5]
+    with pytest.raises(SystemExit):
+        tp.arg_parser().parse_args([])
+
+
+def test_gen_layers_dsl():
+    assert tp.gen_layers(256, 2) == orc.gen_layers(256, 2) == pm.DEFAULT_FC_256X2
+    l = tp.gen_layers(8, 1, act_hidden="elu", add_softmax=True)
+    assert l[-1] == {"type": "softmax"} and l[0]["activation"] == "elu" and l[1]["hidden_size"] == "output"
+    with pytest.raises(AssertionError):
+        tp.gen_layers(0, 1)
+
+
+def test_activation_registry():
+    assert pm.get_activation_fn("linear") is None and pm.get_activation_fn(None) is None
+    assert pm.get_activation_fn("relu") is torch.nn.ReLU and pm.get_activation_fn("elu") is torch.nn.ELU
+    with pytest.raises(ValueError):
+        pm.get_activation_fn("gelu")
+    with pytest.raises(NotImplementedError):
+        pm.get_initializer({"name": "orthogonal"})
+    with pytest.raises(NotImplementedError):
+        tm.get_loss_fn("Huber")
+
+
+def test_state_dict_keys_and_seeded_init_match_reference():
+    g, m = _small_model()
+    ref = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())            # same names, same order, no log_std entry (constant type)
+    for k in ref:
+        assert np.array_equal(sd[k].numpy(), ref[k]), k    # same RNG consumption as the reference constructor
+    assert len(list(m.parameters())) == 2 * (3 + 4 + 3 + 3)
+
+
+def test_loco_checkpoint_key_layout():
+    g = np.load(os.path.join(G, "ref_loco_ckpt.npz"))
+    box = lambda n: tp.Box(low=-np.ones(n), high=np.ones(n), dtype=np.float64)
+    custom = dict(pm.PhysicsVAE.DEFAULT_CONFIG)
+    custom.update(observation_space=box(722), observation_space_body=box(361), observation_space_task=box(361), action_space=box(54))
+    m = pm.PhysicsVAE(box(722), box(54), 108, {"custom_model_config": custom}, "physics_vae")
+    assert list(m.state_dict().keys()) == g["keys"].tolist()
+    assert sum(p.numel() for p in m.parameters()) == 3118816
+
+
+def test_model_attributes_and_errors():
+    g, m = _small_model()
+    assert (m.dim_state, m.dim_state_body, m.dim_state_task, m.dim_action) == (74, 37, 37, 11)
+    assert m.latent_prior_noise is True and m.get_initial_state() == []
+    with pytest.raises(AssertionError):
+        m.value_function()
+    # no eager fallback: CPU tensors cannot be run
+    x = torch.zeros(4, 74)
+    with pytest.raises(_abi.PvaeError):
+        m(input_dict={"obs": x, "obs_flat": x}, state=None, seq_lens=None)
+    with pytest.raises(_abi.PvaeError):
+        m._world_model(torch.zeros(2, 48))
+    # AppendLogStd semantics
+    app = m._motor_decoder._model[-1]
+    out = app(torch.zeros(3, 11))
+    assert out.shape == (3, 22) and torch.allclose(out[:, 11:], torch.full((3, 11), float(np.log(0.1))))
+    m.set_exploration_std(0.05)
+    assert torch.allclose(app(torch.zeros(1, 11))[:, 11:], torch.full((1, 11), float(np.log(0.05))))
+    with pytest.raises(AssertionError):
+        box = tp.Box(low=-np.ones(4), high=np.ones(4))
+        pm.PhysicsVAE(box, box, 3, {}, "x")
+
+
+def test_broken_upstream_priors_raise_clearly():
+    for prior in ("normal_state_mean_one_std", "hypersphere_uniform", "bogus"):
+        with pytest.raises(NotImplementedError):
+            _small_model(prior)
+    g, m = _small_model(False)
+    assert m._task_encoder.layer_spec()[-1][0] == 8        # no prior: the encoder emits z directly
+
+
+def test_freezing_and_partial_checkpoints(tmp_path):
+    g, m = _small_model()
+    m.set_learnable_task_encoder(False)
+    m.set_learnable_motor_decoder(False)
+    assert all(not p.requires_grad for p in m._task_encoder.parameters())
+    assert all(p.requires_grad for p in m._world_model.parameters())
+    f = {n: str(tmp_path / (n + ".pt")) for n in ("model", "task_encoder", "motor_decoder", "world_model")}
+    m.save_weights(f["model"]); m.save_weights_task_encoder(f["task_encoder"])
+    m.save_weights_motor_decoder(f["motor_decoder"]); m.save_weights_world_model(f["world_model"])
+    assert list(torch.load(f["task_encoder"]).keys()) == ["task_encoder"]
+    assert list(torch.load(f["world_model"]).keys())[0] == "_model.0._model.0.weight"
+    torch.manual_seed(1)
+    g2, m2 = _small_model()
+    torch.manual_seed(2)
+    for p in m2.parameters():
+        p.data.normal_()
+    m2.load_weights_world_model(f["world_model"]); m2.load_weights_task_encoder(f["task_encoder"]); m2.load_weights_motor_decoder(f["motor_decoder"])
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        if not k.startswith("_value_branch"):
+            assert torch.equal(a, b), k
+    assert not m2._world_model.training            # load_weights* switch the sub-module to eval (appendix B.3)
+    m2.load_weights(f["model"])
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_dataset_builder_matches_reference_fixture(tmp_path):
+    g = np.load(os.path.join(G, "ref_dataset.npz"))
+    data = pickle.loads(g["pickle_bytes"].tobytes())
+    f = str(tmp_path / "demo.pkl")
+    pickle.dump(data, open(f, "wb"))
+    ds = tp.load_dataset_for_PhysicsVAE([f])
+    assert ds.X.dtype == np.float64 and np.array_equal(ds.X, g["X"]) and np.array_equal(ds.Y, g["Y"]) and ds.Y.dtype == g["Y"].dtype
+    ds = tp.load_dataset_for_PhysicsVAE([f], num_samples=20)
+    assert np.array_equal(ds.X, g["X_cap"]) and np.array_equal(ds.Y, g["Y_cap"])
+    ds = tp.load_dataset_for_PhysicsVAE([f], lookahead=2, cond="rel", use_a_gt=True)
+    assert np.array_equal(ds.X, g["X_rel"]) and np.array_equal(ds.Y, g["Y_rel"])
+    # merge of two files concatenates episodes; mismatching metadata asserts
+    ds2 = tp.load_dataset_for_PhysicsVAE([f, f])
+    assert len(ds2) == 2 * len(g["X"])
+    bad = dict(data); bad["dim_action"] = 99
+    f2 = str(tmp_path / "bad.pkl")
+    pickle.dump(bad, open(f2, "wb"))
+    with pytest.raises(AssertionError):
+        tp.merge_dataset([f, f2])
+    with pytest.raises(AssertionError):
+        tp.load_dataset_for_PhysicsVAE([])
+    with pytest.raises(NotImplementedError):
+        tp.episodes_to_transitions(data["episodes"], cond="delta")
+    # __getitem__ hands out float32 tensors like the reference's DatasetBase
+    x0, y0 = tp.load_dataset_for_PhysicsVAE([f])[0]
+    assert x0.dtype == torch.float32 and x0.shape == (1, 10) and y0.shape == (1, 3)
+    # sequential loader with a short last batch
+    loader = tm.ResidentLoader(tp.load_dataset_for_PhysicsVAE([f]), 7, None)
+    assert [hi - lo for lo, hi in loader] == g["batch_sizes"].tolist() and len(loader) == 7
+    with pytest.raises(NotImplementedError):
+        tm.ResidentLoader(ds, 7, True)
+
+
+def test_dataset_normalisation_roundtrip():
+    rng = np.random.default_rng(0)
+    X, Y = rng.standard_normal((50, 1, 6)) * 3 + 1, rng.standard_normal((50, 1, 2)).astype(np.float32)
+    ds = tm.DatasetBase(X, Y, normalize_x=True, normalize_y=True)
+    x, y = ds[3]
+    assert np.allclose(ds.postprocess_x(x.numpy(), return_tensor=False), X[3], atol=1e-5)
+    assert np.allclose(ds.postprocess_y(y.numpy(), return_tensor=False), Y[3], atol=1e-5)
+    Xa, Ya = ds.arrays()
+    assert abs(Xa.mean()) < 1e-9 and Xa.dtype == np.float64 and Ya.dtype == np.float32
+
+
+def test_trainer_config_and_grid(tmp_path):
+    data = orc.synthetic_episodes(2, 9, 5, 3, seed=1)
+    f = str(tmp_path / "demo.pkl")
+    pickle.dump(data, open(f, "wb"))
+    a = tp.arg_parser().parse_args(["--data_train", f, "--vae_kl_coeff", "0.5", "--max_iter_world_model", "3"])
+    cfg = tp.get_trainer_config(a)
+    assert cfg["lr_schedule_params"] == {"step_size": 50, "gamma": 0.70} and cfg["batch_size"] == 256 and cfg["lookahead"] == 1
+    assert "shuffle_data" not in cfg and cfg["suffle_data"] is True          # the reference's typo is part of the behaviour
+    assert cfg["vae_kl_coeff"] == {"grid_search": [1.0, 0.5]}
+    mc = cfg["model"]["custom_model_config"]
+    assert mc["observation_space"].shape == (10,) and mc["observation_space_body"].shape == (5,) and mc["action_space"].shape == (3,)
+    pts = tp.resolve_grid(cfg)
+    assert len(pts) == 2 and sorted(p["vae_kl_coeff"] for p in pts) == [0.5, 1.0] and pts[0]["MD_width"] == 512
+    tp.update_model_config(pts[0])
+    mc = pts[0]["model"]["custom_model_config"]
+    assert [l["hidden_size"] for l in mc["world_model_layers"]] == [1024, 1024, "output"]
+    assert [l["hidden_size"] for l in mc["motor_decoder_layers"]] == [512, 512, 512, "output"]
+    assert mc["task_encoder_output_dim"] == 32 and mc["latent_prior_type"] == "normal_zero_mean_one_std"
+    with pytest.raises(AssertionError):
+        tp.get_trainer_config(argparse.Namespace(max_iter_world_model=5, max_iter=2, data_train=[f]))
+    model = tp.create_model(pts[0])
+    assert model.dim_state_body == 5 and model.dim_action == 3 and model.num_outputs == 6
+
+
+def test_lr_scheduler_factory():
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    opt = torch.optim.Adam(p, lr=5e-4)
+    s = tm.get_lr_scheduler(opt, "step", {"step_size": 50, "gamma": 0.7})
+    assert isinstance(s, torch.optim.lr_scheduler.StepLR) and s.step_size == 50
+    assert tm.get_lr_scheduler(opt, None, None) is None
+    assert isinstance(tm.get_lr_scheduler(opt, "cosine", {"T_max": 3}), torch.optim.lr_scheduler.CosineAnnealingLR)
+
+
+def test_shard_rows_partition_and_weights():
+    for lo, hi, world in ((0, 256, 2), (300, 424, 8), (0, 5, 8), (10, 11, 2), (0, 65536, 4)):
+        parts = [parallel.shard_rows(lo, hi, r, world) for r in range(world)]
+        assert parts[0][0] == lo and parts[-1][1] == hi
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        sizes = [e - s for s, e in parts]
+        assert max(sizes) - min(sizes) <= 1 and max(sizes) <= parallel.max_shard_rows(hi - lo, world)
+        w = [parallel.shard_weight(lo, hi, r, world) for r in range(world)]
+        assert abs(sum(w) / world - 1.0) < 1e-12

@@ -1,0 +1,99 @@
+"""Live check of the oracle against the reference's own files imported unchanged under oracle/ref_stub.  Runs only where
+/root/reference is mounted (the build container); skipped on the GPU box.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pvae_oracle as orc
+from oracle import refload
+
+pytestmark = pytest.mark.skipif(not refload.available(), reason="/root/reference is not mounted here")
+
+
+def test_default_dims_step_matches_live_reference():
+    tpv, tm, rmt = refload.load()
+    dsb, da, z, B = 197, 45, 32, 32
+    torch.manual_seed(3)
+    ref = refload.build_reference_model(dsb, da, z, tpv.gen_layers(256, 2), tpv.gen_layers(512, 3), tpv.gen_layers(1024, 2))
+    torch.manual_seed(3)
+    m = orc.OracleModel(dsb, da, z)
+    for k, v in ref.state_dict().items():
+        assert torch.equal(m.params[k], v), k
+    X, Y = orc.build_transitions(orc.synthetic_episodes(1, 129, dsb, da, seed=1)["episodes"], num_samples=B)
+    x, y = torch.Tensor(X), torch.Tensor(Y)
+    for world in (True, False):
+        ref.zero_grad()
+        ref.set_learnable_task_encoder(not world)
+        ref.set_learnable_motor_decoder(not world)
+        ref.set_learnable_world_model(world)
+        torch.manual_seed(11)
+        eps = torch.randn(B, z)
+        torch.manual_seed(11)
+        loss = refload.reference_compute_loss(ref, x, y, world)
+        loss.backward()
+        o_loss, _, grads = orc.loss_and_grads(m, x[:, 0, :], y[:, 0, :], world, eps=eps)
+        assert abs(o_loss - float(loss)) <= 1e-6 * abs(float(loss))
+        ref_grads = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+        assert set(ref_grads) == set(grads)
+        for k in grads:
+            np.testing.assert_allclose(grads[k].numpy(), ref_grads[k].numpy(), rtol=1e-5, atol=1e-10, err_msg=k)
+
+
+def test_shipped_checkpoint_golden_vector():
+    # strict load of data/pretrained/loco_modelV1.pt into the oracle + the committed outputs
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_loco_ckpt.npz"))
+    sd = torch.load(os.path.join(refload.REFERENCE, "data", "pretrained", "loco_modelV1.pt"))
+    m = orc.OracleModel(361, 54, 32)
+    m.load_state_dict(sd)
+    assert list(sd.keys()) == g["keys"].tolist()
+    m.latent_prior_noise = False
+    logits = m.forward(torch.from_numpy(g["x"]))
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.cur["future"].numpy(), g["future"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.cur["value"].numpy(), g["value"], rtol=1e-5, atol=1e-6)
+    assert abs(float(logits[0, 0]) - (-0.24995048)) < 1e-6 and abs(float(logits[0, -1]) - np.log(0.1)) < 1e-6
+
+
+def test_trainer_trajectory_matches_live_reference():
+    """A few epochs of the reference's own TrainModel.step (Adam + StepLR + phase switch) vs OracleTrainer."""
+    import pickle
+    import tempfile
+    tpv, tm, rmt = refload.load()
+    dsb, da = 13, 5
+    data = orc.synthetic_episodes(2, 41, dsb, da, seed=2)
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "demo.pkl")
+        pickle.dump(data, open(f, "wb"))
+        import argparse
+        args = argparse.Namespace(max_iter_world_model=2, max_iter=4, data_train=[f], data_test=None, world_model=None, lr=5e-4,
+                                  lr_schedule="step", batch_size=32, latent_dim=4, latent_prior_type=["normal_zero_mean_one_std"],
+                                  vae_kl_coeff=[1.0], vae_cycle_coeff=[1e-3], num_data=None)
+        tpv.args = args
+        cfg = tpv.get_trainer_config(args)
+        for k, v in list(cfg.items()):
+            if isinstance(v, dict) and set(v) == {"grid_search"}:
+                cfg[k] = v["grid_search"][0]
+        cfg.update(TE_width=16, MD_width=24, world_model_width=32)
+        torch.manual_seed(5)
+        ref = tpv.TrainModel(cfg)
+    torch.manual_seed(5)
+    m = orc.OracleModel(dsb, da, 4, orc.gen_layers(16, 2), orc.gen_layers(24, 3), orc.gen_layers(32, 2))
+    for k, v in ref.model.state_dict().items():
+        assert torch.equal(m.params[k], v), k
+    X, Y = orc.build_transitions(data["episodes"])
+    tr = orc.OracleTrainer(m, X, Y, batch_size=32, lr=5e-4, max_iter_world_model=2)
+    for it in range(4):
+        # the reference draws eps with torch.randn_like inside forward: replay the same global-RNG stream on both sides.
+        # In the world phase the reference's discarded full forward (train_physics_vae.py:377-378) also consumes one draw.
+        torch.manual_seed(100 + it)
+        r = ref.step()
+        torch.manual_seed(100 + it)
+        torch.empty((), dtype=torch.int64).random_()      # the DataLoader iterator draws its base seed from the global RNG
+        def eps_fn(i, b, n):
+            return torch.randn(n, 4)
+        o = tr.step(eps_fn=eps_fn)
+        assert abs(o["mean_train_loss"] - r["mean_train_loss"]) <= 2e-6 * abs(r["mean_train_loss"]), (it, o, r)
+    for k, v in ref.model.state_dict().items():
+        np.testing.assert_allclose(m.params[k].numpy(), v.numpy(), rtol=2e-5, atol=2e-7, err_msg=k)
