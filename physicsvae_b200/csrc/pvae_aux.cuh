@@ -15,16 +15,24 @@ namespace pvae {
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
 
 // ---- ingest: one thread per (row, 2 columns) pair; rows are contiguous so warps read/write whole lines ------
+// source column of destination column c when the first w0 source columns stay at [0, w0) and the remaining ones start at
+// the 16-byte aligned destination column p0 (the (s_t | s_{t+1}) split of a transition row); -1 = padding
+__device__ __forceinline__ int split_src_col(int c, int w0, int p0, int width) {
+  if (c < p0) return c < w0 ? c : -1;
+  const int j = w0 + (c - p0);
+  return j < width ? j : -1;
+}
 template <typename SrcT>
-__global__ void ingest_kernel(const SrcT* __restrict__ src, int64_t src_ld, int width, __nv_bfloat16* __restrict__ dst,
+__global__ void ingest_kernel(const SrcT* __restrict__ src, int64_t src_ld, int width, int w0, int p0, __nv_bfloat16* __restrict__ dst,
                               int64_t dst_ld, int64_t dst_ps, int planes, int64_t n_rows) {
   const int64_t pairs_per_row = dst_ld >> 1;   // dst_ld is a multiple of 8
   const int64_t total = n_rows * pairs_per_row;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / pairs_per_row;
     const int c = (int)(i - r * pairs_per_row) * 2;
-    const float v0 = (c < width) ? (float)src[r * src_ld + c] : 0.f;
-    const float v1 = (c + 1 < width) ? (float)src[r * src_ld + c + 1] : 0.f;
+    const int s0 = split_src_col(c, w0, p0, width), s1 = split_src_col(c + 1, w0, p0, width);
+    const float v0 = (s0 >= 0) ? (float)src[r * src_ld + s0] : 0.f;
+    const float v1 = (s1 >= 0) ? (float)src[r * src_ld + s1] : 0.f;
     __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
     *reinterpret_cast<__nv_bfloat162*>(dst + r * dst_ld + c) = h;
     if (planes > 1) {
@@ -149,13 +157,14 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
 }
 
 // ---- fp32 [B][w] -> bf16 planes (decoder / world inputs handed in by the inference API) -------------------------
-__global__ void f32_to_planes_kernel(const float* __restrict__ src, int64_t src_ld, int width, __nv_bfloat16* __restrict__ dst,
-                                     int64_t dst_ld, int64_t dst_ps, int planes, int64_t n_rows) {
+__global__ void f32_to_planes_kernel(const float* __restrict__ src, int64_t src_ld, int width, int w0, int p0,
+                                     __nv_bfloat16* __restrict__ dst, int64_t dst_ld, int64_t dst_ps, int planes, int64_t n_rows) {
   const int64_t total = n_rows * dst_ld;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / dst_ld;
     const int c = (int)(i - r * dst_ld);
-    const float v = (c < width) ? src[r * src_ld + c] : 0.f;
+    const int sc = split_src_col(c, w0, p0, width);
+    const float v = (sc >= 0) ? src[r * src_ld + sc] : 0.f;
     const __nv_bfloat16 h = f2bf(v);
     dst[i] = h;
     if (planes > 1) dst[dst_ps + i] = f2bf(v - __bfloat162float(h));

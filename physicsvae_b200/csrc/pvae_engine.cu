@@ -108,6 +108,7 @@ struct Device {
   int id = 0;
   int sms = 148;
   int mn_bn_align = 64;   // UMMA N granularity used when B is MN-major (PVAE_MN_BN_ALIGN)
+  int tma_epilogue = 1;   // bf16 outputs leave through shared memory + TMA stores (PVAE_TMA_EPILOGUE=0 disables)
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
@@ -122,7 +123,9 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   p.passes = d.passes;
   p.m_tiles = cdiv(d.M, BM);
   int n_tiles = cdiv(d.N, MAX_BN);
-  int bn = rup(cdiv(d.N, n_tiles), d.b_major == MAJOR_MN ? dev.mn_bn_align : 16);
+  // one N tile: any multiple of 16 (the TMA store clips at the tensor edge); several: whole 64-column sub-tiles
+  int bn = rup(cdiv(d.N, n_tiles), (n_tiles > 1 || d.b_major == MAJOR_MN) ? 64 : 16);
+  if (d.b_major == MAJOR_MN && n_tiles == 1) bn = rup(d.N, dev.mn_bn_align);
   if (bn > MAX_BN) bn = MAX_BN;
   n_tiles = cdiv(d.N, bn);
   p.n_tiles = n_tiles;
@@ -154,9 +157,23 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   p.epi = d.epi;
   p.epi.m_valid = d.M;
   p.epi.n_valid = d.N;
+  const EpiParams& e = p.epi;
+  // TMA epilogue: one precision plane, bf16 primary output; ReLU dgrad needs the sign-bit mask its forward wrote
+  const bool has_aux = e.type == EPI_MSE || (e.type == EPI_DGRAD && e.act != ACT_LINEAR && e.act != ACT_RELU);
+  const bool tma = dev.tma_epilogue && e.type != EPI_WGRAD && e.out != nullptr && e.out_planes == 1 &&
+                   !(e.type == EPI_DGRAD && e.act == ACT_RELU && e.mask == nullptr) &&
+                   (!has_aux || (e.aux != nullptr && e.aux_planes == 1 && (reinterpret_cast<uintptr_t>(e.aux) & 15) == 0));
+  if (tma) {
+    View o; o.base = e.out; o.ld = e.out_ld; o.ps = e.out_ps; o.planes = 1; o.width = d.N; o.rows = d.M;
+    CKR(encode_map(&p.tmOut, o, 64, 32));
+    if (has_aux) {
+      View a; a.base = e.aux; a.ld = e.aux_ld; a.ps = e.aux_ps; a.planes = 1; a.width = d.N; a.rows = e.aux_rows ? e.aux_rows : d.M;
+      CKR(encode_map(&p.tmAux, a, 64, 32));
+    }
+  }
   const int units = p.m_tiles * n_tiles * splits;
   const int grid = units < dev.sms ? units : dev.sms;
-  GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act);
+  GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act, tma);
   fn<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
@@ -179,7 +196,9 @@ struct Net {
   int64_t wsh_ps[PVAE_MAX_LAYERS];
   __nv_bfloat16* act[PVAE_MAX_LAYERS];
   __nv_bfloat16* g[PVAE_MAX_LAYERS];
+  uint32_t* mask[PVAE_MAX_LAYERS];   // ReLU sign bits of act[l], [max_batch][mask_ld[l]]
   int act_ld[PVAE_MAX_LAYERS];
+  int mask_ld[PVAE_MAX_LAYERS];
   bool bound = false;
 };
 
@@ -198,7 +217,7 @@ struct pvae_engine {
   Net nets[PVAE_NUM_NETS];
   int planes = 1, passes = 1;
   int max_batch = 0;
-  int dsb = 0, da = 0, z = 0, te_out = 0;
+  int dsb = 0, dsbp = 0, da = 0, z = 0, te_out = 0;   // dsbp: 16-byte aligned column where s_{t+1} starts inside a transition row
   // workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -237,6 +256,9 @@ static size_t carve(pvae_engine* h, uint8_t* base) {
       net.act_ld[l] = rup(net.out_dims[l], 64);
       const size_t bytes = (size_t)h->planes * B * net.act_ld[l] * 2;
       net.act[l] = (l < net.n_layers - 1) ? reinterpret_cast<__nv_bfloat16*>(take(bytes)) : nullptr;
+      net.mask_ld[l] = rup(cdiv(net.out_dims[l], 32), 2);
+      net.mask[l] = (l < net.n_layers - 1 && net.acts[l] == ACT_RELU)
+                        ? reinterpret_cast<uint32_t*>(take((size_t)B * net.mask_ld[l] * 4)) : nullptr;
       net.g[l] = (n != PVAE_NET_VALUE_BRANCH) ? reinterpret_cast<__nv_bfloat16*>(take(bytes)) : nullptr;
     }
   }
@@ -245,7 +267,7 @@ static size_t carve(pvae_engine* h, uint8_t* base) {
   h->dz = reinterpret_cast<float*>(take((size_t)B * h->z * 4));
   h->zb_ld = rup(h->z, 64);
   h->a_ld = rup(h->da, 64);
-  h->x_ld = rup(2 * h->dsb, 64);
+  h->x_ld = rup(h->dsbp + h->dsb, 64);
   h->zb = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->zb_ld * 2));
   h->ahat = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
   h->ga = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
@@ -272,7 +294,7 @@ static void set_out2(EpiParams& e, const pvae_engine* h, __nv_bfloat16* p, int l
   e.out2 = p; e.out2_ld = ld; e.out2_ps = plane_elems(h, ld); e.out2_planes = h->planes;
 }
 static void set_aux(EpiParams& e, const View& v, int col0) {
-  e.aux = v.base + col0; e.aux_ld = v.ld; e.aux_ps = v.ps; e.aux_planes = v.planes; e.aux_dyn = v.dyn;
+  e.aux = v.base + col0; e.aux_ld = v.ld; e.aux_ps = v.ps; e.aux_planes = v.planes; e.aux_dyn = v.dyn; e.aux_rows = v.rows;
 }
 
 // views of the resident transition buffer: x planes then y planes
@@ -312,6 +334,7 @@ static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, con
     if (l < net.n_layers - 1) {
       d.epi.type = EPI_STORE; d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
       set_out(d.epi, h, net.act[l], net.act_ld[l]);
+      d.epi.mask = net.mask[l]; d.epi.mask_ld = net.mask_ld[l];
     } else {
       d.epi = last;
       d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
@@ -362,6 +385,7 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
       d.epi.type = EPI_DGRAD; d.epi.act = net.acts[l - 1];
       const View al = ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
       if (net.acts[l - 1] != ACT_LINEAR) set_aux(d.epi, al, 0);
+      d.epi.mask = net.mask[l - 1]; d.epi.mask_ld = net.mask_ld[l - 1];
       set_out(d.epi, h, net.g[l - 1], net.act_ld[l - 1]);
       d.epi.colsum = train ? net.grad + net.gb[l - 1] : nullptr;
       CKR(launch_gemm(h->dev, d, st));
@@ -411,7 +435,8 @@ static int ensure_kernel_attr(Device& dev) {
   if (dev.attr_set) return PVAE_OK;
   for (int epi = 0; epi < 4; ++epi)
     for (int act = 0; act <= ACT_SWISH; ++act)
-      CK(cudaFuncSetAttribute(select_kernel(epi, act), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      for (int tma = 0; tma < 2; ++tma)
+        CK(cudaFuncSetAttribute(select_kernel(epi, act, tma != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   dev.attr_set = true;
   return PVAE_OK;
 }
@@ -429,6 +454,8 @@ static int init_device(Device& dev, int device) {
   dev.sms = prop.multiProcessorCount;
   const char* env = getenv("PVAE_MN_BN_ALIGN");
   if (env) { int v = atoi(env); if (v == 16 || v == 32 || v == 64) dev.mn_bn_align = v; }
+  env = getenv("PVAE_TMA_EPILOGUE");
+  if (env) dev.tma_epilogue = atoi(env) != 0;
   CKR(resolve_driver());
   CKR(ensure_kernel_attr(dev));
   return PVAE_OK;
@@ -450,7 +477,8 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
   h->max_batch = desc->max_batch;
   h->dsb = desc->dim_state_body; h->da = desc->dim_action; h->z = desc->latent_dim;
   h->te_out = desc->latent_prior ? 2 * h->z : h->z;
-  h->tx_ld = rup(2 * h->dsb, 8);
+  h->dsbp = rup(h->dsb, 8);
+  h->tx_ld = 2 * h->dsbp;
   h->ty_ld = rup(h->da, 8);
   for (int n = 0; n < PVAE_NUM_NETS; ++n) {
     Net& net = h->nets[n];
@@ -459,10 +487,10 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
     net.n_layers = nd.n_layers;
     if (nd.n_layers == 0) continue;
     switch (n) {
-      case PVAE_NET_TASK_ENCODER: net.k0 = 2 * h->dsb; net.k1 = 0; break;
+      case PVAE_NET_TASK_ENCODER: net.k0 = h->dsb; net.k1 = h->dsb; break;       // (s_t | s_{t+1}) as two segments
       case PVAE_NET_MOTOR_DECODER: net.k0 = h->dsb; net.k1 = h->z; break;
       case PVAE_NET_WORLD_MODEL: net.k0 = h->dsb; net.k1 = h->da; break;
-      default: net.k0 = 2 * h->dsb; net.k1 = 0; break;
+      default: net.k0 = h->dsb; net.k1 = h->dsb; break;
     }
     net.in_dim = net.k0 + net.k1;
     net.K0pad = rup(net.k0, 64);
@@ -590,12 +618,12 @@ int pvae_ingest(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t dst_row,
   __nv_bfloat16* yb = xb + (int64_t)h->planes * buf_rows * h->tx_ld;
   const int64_t xt = n_rows * (h->tx_ld / 2), yt = n_rows * (h->ty_ld / 2);
   if (x_is_f64)
-    ingest_kernel<double><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const double*>(x_raw_dev), 2 * h->dsb, 2 * h->dsb,
+    ingest_kernel<double><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const double*>(x_raw_dev), 2 * h->dsb, 2 * h->dsb, h->dsb, h->dsbp,
                                                                          xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
   else
-    ingest_kernel<float><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const float*>(x_raw_dev), 2 * h->dsb, 2 * h->dsb,
+    ingest_kernel<float><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const float*>(x_raw_dev), 2 * h->dsb, 2 * h->dsb, h->dsb, h->dsbp,
                                                                         xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
-  ingest_kernel<float><<<grid_for(yt, 256, h->dev.sms), 256, 0, st>>>(y_raw_dev, h->da, h->da, yb + dst_row * h->ty_ld, h->ty_ld,
+  ingest_kernel<float><<<grid_for(yt, 256, h->dev.sms), 256, 0, st>>>(y_raw_dev, h->da, h->da, h->da, 1 << 30, yb + dst_row * h->ty_ld, h->ty_ld,
                                                                       buf_rows * h->ty_ld, h->planes, n_rows);
   g_launches.fetch_add(2, std::memory_order_relaxed);
   CK(cudaGetLastError());
@@ -652,7 +680,7 @@ int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pv
   EpiParams last;
   memset(&last, 0, sizeof(last));
   last.type = EPI_MSE;
-  set_aux(last, tx_view(h, 0, 2 * h->dsb), h->dsb);
+  set_aux(last, tx_view(h, h->dsbp, h->dsb), 0);
   last.scale = 2.f * s_coeff / ((float)batch * (float)h->dsb);
   set_out(last, h, wm.g[L - 1], wm.act_ld[L - 1]);
   last.colsum = wm.grad + wm.gb[L - 1];
@@ -687,7 +715,7 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
   const int z = h->z, Lte = te.n_layers, Lmd = md.n_layers, Lwm = wm.n_layers;
 
   // encoder: h = TE(cat[s1, s2]) -> (mu | logvar)                      rllib_model_torch.py:773-800
-  NetIO te_in; te_in.nseg = 1; te_in.seg[0] = tx_view(h, 0, 2 * h->dsb);
+  NetIO te_in; te_in.nseg = 2; te_in.seg[0] = tx_view(h, 0, h->dsb); te_in.seg[1] = tx_view(h, h->dsbp, h->dsb);
   EpiParams e;
   memset(&e, 0, sizeof(e));
   e.type = EPI_STORE; e.out_f32 = h->ml; e.f32_sm = h->te_out; e.f32_sn = 1;
@@ -722,7 +750,7 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
     wm_in.nseg = 2; wm_in.seg[0] = tx_view(h, 0, h->dsb); wm_in.seg[1] = ws_view(h, h->ahat, h->a_ld, h->da, batch);
     memset(&e, 0, sizeof(e));
     e.type = EPI_MSE;
-    set_aux(e, tx_view(h, 0, 2 * h->dsb), h->dsb);
+    set_aux(e, tx_view(h, h->dsbp, h->dsb), 0);
     e.scale = 2.f * cyc_coeff / ((float)batch * (float)h->dsb);
     e.loss = h->acc + 3;
     set_out(e, h, wm.g[Lwm - 1], wm.act_ld[Lwm - 1]);
@@ -772,14 +800,14 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
   if (obs_ld < obs_w) return fail(PVAE_ERR_INVALID, "obs row stride %lld < %d", (long long)obs_ld, obs_w);
   {
     const int64_t total = (int64_t)batch * h->x_ld;
-    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(obs_dev, obs_ld, obs_w, h->xin, h->x_ld, plane_elems(h, h->x_ld), h->planes, batch);
+    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(obs_dev, obs_ld, obs_w, h->dsb, h->dsbp, h->xin, h->x_ld, plane_elems(h, h->x_ld), h->planes, batch);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   EpiParams e;
   if (enc) {
     Net& te = h->nets[PVAE_NET_TASK_ENCODER];
     if (te.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no task encoder");
-    NetIO in; in.nseg = 1; in.seg[0] = ws_view(h, h->xin, h->x_ld, 2 * h->dsb, batch);
+    NetIO in; in.nseg = 2; in.seg[0] = ws_view(h, h->xin, h->x_ld, h->dsb, batch); in.seg[1] = ws_view(h, h->xin + h->dsbp, h->x_ld, h->dsb, batch);
     memset(&e, 0, sizeof(e));
     e.type = EPI_STORE; e.out_f32 = h->ml; e.f32_sm = h->te_out; e.f32_sn = 1;
     CKR(net_forward(h, te, in, batch, e, st));
@@ -792,7 +820,7 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
   } else if (dec) {
     if (!z_in_dev) return fail(PVAE_ERR_INVALID, "decoder without encoder needs z_in_dev");
     const int64_t total = (int64_t)batch * h->zb_ld;
-    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(z_in_dev, z, z, h->zb, h->zb_ld, plane_elems(h, h->zb_ld), h->planes, batch);
+    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(z_in_dev, z, z, z, 1 << 30, h->zb, h->zb_ld, plane_elems(h, h->zb_ld), h->planes, batch);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   const __nv_bfloat16* act_planes = h->ahat;
@@ -808,7 +836,7 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
   } else if (wld) {
     if (!act_in_dev) return fail(PVAE_ERR_INVALID, "world model without decoder needs act_in_dev");
     const int64_t total = (int64_t)batch * h->a_ld;
-    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(act_in_dev, act_in_ld, h->da, h->ain, h->a_ld, plane_elems(h, h->a_ld), h->planes, batch);
+    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(act_in_dev, act_in_ld, h->da, h->da, 1 << 30, h->ain, h->a_ld, plane_elems(h, h->a_ld), h->planes, batch);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     act_planes = h->ain;
   }
@@ -825,7 +853,7 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
     Net& vb = h->nets[PVAE_NET_VALUE_BRANCH];
     if (vb.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no value branch");
     if (!value_dev) return fail(PVAE_ERR_INVALID, "value part needs value_dev");
-    NetIO in; in.nseg = 1; in.seg[0] = ws_view(h, h->xin, h->x_ld, 2 * h->dsb, batch);
+    NetIO in; in.nseg = 2; in.seg[0] = ws_view(h, h->xin, h->x_ld, h->dsb, batch); in.seg[1] = ws_view(h, h->xin + h->dsbp, h->x_ld, h->dsb, batch);
     memset(&e, 0, sizeof(e));
     e.type = EPI_STORE; e.out_f32 = value_dev; e.f32_sm = 1; e.f32_sn = 1;
     CKR(net_forward(h, vb, in, batch, e, st));

@@ -34,8 +34,13 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;                  // two warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warps 0..3: TMA / MMA / TMEM-alloc / idle, warps 4..11: epilogue
-constexpr int BIAS_BYTES = EPI_WARPS * MAX_BN * 4;   // per-epilogue-warp bias tile
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + BIAS_BYTES;
+constexpr int SLAB_BYTES = 32 * 128;          // per-epilogue-warp staging slab: 32 rows x 64 bf16 (TMA store / aux load box)
+constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
+constexpr int OFF_BARS = OFF_STAGING + EPI_WARPS * SLAB_BYTES;
+constexpr int OFF_BIAS = OFF_BARS + 256;
+constexpr int BIAS_BYTES = EPI_WARPS * 32 * 4;      // per-epilogue-warp bias slice of the current 32 columns
+constexpr int SMEM_BYTES = OFF_BIAS + BIAS_BYTES + 1024 /*alignment slack*/;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB of shared memory a CTA may use");
 
 enum : int { EPI_STORE = 0, EPI_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD = 3 };
 enum : int { ACT_LINEAR = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3, ACT_ELU = 4, ACT_SWISH = 5 };
@@ -53,11 +58,14 @@ struct EpiParams {
   float* out_f32; int64_t f32_sm, f32_sn;
   // aux bf16 input: EPI_MSE target / EPI_DGRAD forward activation (for act')
   const __nv_bfloat16* aux; int64_t aux_ld, aux_ps; int32_t aux_planes; int32_t aux_dyn;
+  int64_t aux_rows;                // rows of the aux tensor (host side: extent of its TMA descriptor)
   // addend bf16 input (EPI_DGRAD: g = acc + add)
   const __nv_bfloat16* add; int64_t add_ld, add_ps; int32_t add_planes; int32_t pad2;
   float scale;                     // EPI_MSE: d = scale * (pred - target)
   int32_t f32_atomic;              // EPI_WGRAD: 1 = red.global.add, 0 = plain store
   float* colsum;                   // [n_valid] fp32, atomically accumulated column sums of the primary output (bias grad)
+  uint32_t* mask;                  // ReLU sign bits [rows][mask_ld] (1 bit per output): written by EPI_STORE, read by EPI_DGRAD
+  int64_t mask_ld;                 // in 32-bit words, even
   double* loss;                    // EPI_MSE: sum of squared errors accumulated here
 };
 
@@ -76,6 +84,8 @@ struct GemmParams {
   int32_t passes;                  // 1 = bf16, 3 = bf16x3
   int32_t m_tiles, n_tiles, bn, splits;
   const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
+  CUtensorMap tmOut;               // TMA-store epilogue: the primary bf16 output, box 64 cols x 32 rows (one warp's slab)
+  CUtensorMap tmAux;               // TMA-store epilogue: the aux input (same box)
   EpiParams epi;
 };
 
@@ -133,6 +143,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -405,19 +421,26 @@ struct KIter {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int ACT>
+// TMAEPI: the primary bf16 output (one precision plane) leaves through shared memory and cp.async.bulk.tensor stores, the
+// aux operand (forward activation for act', MSE target) arrives the same way; the epilogue warps then touch only TMEM,
+// shared memory and registers.  Without it (bf16x3 planes, fp32-only outputs) rows are read / written directly.
+template <int EPI, int ACT, bool TMAEPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle atoms need 1024 B alignment
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = smem_base + OFF_BARS;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  auto auxfull_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + w); };   // one per epilogue warp
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + EPI_WARPS);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));    // generic pointer to the aligned base
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
-  float* bias_all = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
+  float* bias_all = reinterpret_cast<float*>(smem_gen + OFF_BIAS);
+  // aux operand through TMA: the MSE target, or the forward activation for act' (ReLU uses the sign-bit mask instead)
+  constexpr bool HAS_AUX = TMAEPI && (EPI == EPI_MSE || (EPI == EPI_DGRAD && ACT != ACT_LINEAR && ACT != ACT_RELU));
+  constexpr bool USE_MASK = TMAEPI && EPI == EPI_DGRAD && ACT == ACT_RELU;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -426,10 +449,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     tma_prefetch_desc(&p.tmA[0]);
     if (p.kb[1] > 0) tma_prefetch_desc(&p.tmA[1]);
     tma_prefetch_desc(&p.tmB);
+    if (TMAEPI) tma_prefetch_desc(&p.tmOut);
+    if (HAS_AUX) tma_prefetch_desc(&p.tmAux);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(auxfull_bar(w), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -523,48 +549,233 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     // ================================ epilogue ================================
     const EpiParams& e = p.epi;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id % 4)
-    const int half = (warp - 4) >> 2;             // which of the two interleaved chunk sets
-    float* bias_s = bias_all + (warp - 4) * MAX_BN;
+    const int half = (warp - 4) >> 2;             // which 32-column half of a 64-column sub-tile / which chunk parity
+    float* bias_s = bias_all + (warp - 4) * 32;
     const int m_valid = e.m_valid, n_valid = e.n_valid;
     const float* bias = (EPI == EPI_STORE || EPI == EPI_MSE) ? e.bias : nullptr;
     int acc = 0; uint32_t acc_phase = 0;
     double loss_local = 0.0;
-    const int nchunks = (bn + 31) >> 5;
+    uint32_t aux_phase = 0;
+    const uint32_t slab = smem_base + OFF_STAGING + (warp - 4) * SLAB_BYTES;      // this warp's private staging slab
+    uint8_t* slab_gen = smem_gen + OFF_STAGING + (warp - 4) * SLAB_BYTES;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int tile = u / p.splits;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
-      const int row = m_tile * BM + q * 32 + lane;
+      const int row_in_tile = q * 32 + lane;
+      const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < m_valid;
-      if (bias) {                                 // stage this tile's bias slice once, padded with zeros
-        __syncwarp();
-        for (int j = lane; j < nchunks * 32; j += 32) {
-          const int col = n_tile * bn + j;
-          bias_s[j] = (j < bn && col < n_valid) ? __ldg(bias + col) : 0.f;
+      if (HAS_AUX) {
+        // fetch the aux slab of this warp's first sub-tile while the main loop of the tile is still running
+        const int col0s = n_tile * bn + half * 64;
+        if (col0s < n_valid && half * 64 < bn) {
+          if (lane == 0) {
+            tma_store_wait_read<0>();             // the slab's previous store has been read out
+            mbar_expect_tx(auxfull_bar(warp - 4), SLAB_BYTES);
+            tma_load_3d(slab, &p.tmAux, auxfull_bar(warp - 4), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      for (int c = half; c < nchunks; c += 2) {
-        const int col0 = n_tile * bn + c * 32;
-        if (col0 >= n_valid) break;               // warp-uniform
-        int nv = n_valid - col0; nv = nv > 32 ? 32 : nv;
-        const int tile_nv = bn - c * 32;          // columns of this chunk that belong to this tile
-        if (tile_nv < nv) nv = tile_nv;
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + c * 32), raw);
-        tmem_ld_wait();
-        float v[32];
+      if (!TMAEPI) {
+        const int nchunks = (bn + 31) >> 5;
+        for (int c = half; c < nchunks; c += 2) {
+          const int col0 = n_tile * bn + c * 32;
+          if (col0 >= n_valid) break;             // warp-uniform
+          int nv = n_valid - col0; nv = nv > 32 ? 32 : nv;
+          const int tile_nv = bn - c * 32;        // columns of this chunk that belong to this tile
+          if (tile_nv < nv) nv = tile_nv;
+          if (bias) {
+            __syncwarp();
+            bias_s[lane] = (lane < nv) ? __ldg(bias + col0 + lane) : 0.f;
+            __syncwarp();
+          }
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + c * 32), raw);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        epilogue_chunk<EPI, ACT>(e, v, bias_s + c * 32, row, row_ok, col0, nv, row0, lane, loss_local);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          epilogue_chunk<EPI, ACT>(e, v, bias_s, row, row_ok, col0, nv, row0, lane, loss_local);
+        }
+      } else {
+        // Each warp owns the 32 rows of its TMEM lane quarter and every other 64-column sub-tile; it stages its 32 x 64 bf16
+        // slab in private shared memory and stores it with one TMA instruction -- no cross-warp synchronisation.
+        const int nsub = (bn + 63) >> 6;
+        const int sw = lane & 7;
+        uint8_t* srow = slab_gen + lane * 128;
+        for (int s = half; s < nsub; s += 2) {
+          const int col0s = n_tile * bn + s * 64;
+          if (col0s >= n_valid) break;            // warp-uniform
+          int nv = n_valid - col0s; nv = nv > 64 ? 64 : nv;
+          const int tile_nv = bn - s * 64;        // columns of this sub-tile that belong to this tile
+          if (tile_nv < nv) nv = tile_nv;
+          uint2 mbits = make_uint2(0u, 0u);
+          if (USE_MASK && row_ok) mbits = __ldg(reinterpret_cast<const uint2*>(e.mask + (int64_t)row * e.mask_ld + (col0s >> 5)));
+          float bias_lo = 0.f, bias_hi = 0.f;     // lane -> bias of columns lane and lane + 32 of the sub-tile
+          if (bias) {
+            bias_lo = (lane < nv) ? __ldg(bias + col0s + lane) : 0.f;
+            bias_hi = (lane + 32 < nv) ? __ldg(bias + col0s + lane + 32) : 0.f;
+          }
+          if (HAS_AUX && s != half) {             // later sub-tiles of the tile: the aux load is exposed
+            if (lane == 0) {
+              tma_store_wait_read<0>();
+              mbar_expect_tx(auxfull_bar(warp - 4), SLAB_BYTES);
+              tma_load_3d(slab, &p.tmAux, auxfull_bar(warp - 4), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
+            }
+            __syncwarp();
+          }
+          uint32_t raw[64];
+          {
+            uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[0]);
+            uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[32]);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + s * 64);
+            tmem_ld32(taddr, r0);
+            tmem_ld32(taddr + 32, r1);
+            tmem_ld_wait();
+          }
+          float v[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(raw[i]);
+          if (bias) {
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+              __syncwarp();
+              bias_s[lane] = hb ? bias_hi : bias_lo;
+              __syncwarp();
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_s + g * 4);
+                v[hb * 32 + g * 4 + 0] += b.x; v[hb * 32 + g * 4 + 1] += b.y; v[hb * 32 + g * 4 + 2] += b.z; v[hb * 32 + g * 4 + 3] += b.w;
+              }
+            }
+          }
+          if (EPI == EPI_STORE) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = (row_ok && i < nv) ? act_fwd<ACT>(v[i]) : 0.f;
+            if (row_ok) {
+              if (e.out_f32) {
+                float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
+              }
+              if (ACT == ACT_RELU && e.mask) {
+                uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { m0 |= (v[i] > 0.f ? 1u : 0u) << i; m1 |= (v[32 + i] > 0.f ? 1u : 0u) << i; }
+                *reinterpret_cast<uint2*>(e.mask + (int64_t)row * e.mask_ld + (col0s >> 5)) = make_uint2(m0, m1);
+              }
+            }
+          } else {
+            float y[64];
+            if (HAS_AUX) {
+              mbar_wait(auxfull_bar(warp - 4), aux_phase);
+              aux_phase ^= 1u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 qv = *reinterpret_cast<const uint4*>(srow + ((j ^ sw) << 4));
+                const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  y[j * 8 + 2 * t]     = __uint_as_float(w[t] << 16);
+                  y[j * 8 + 2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u);
+                }
+              }
+              __syncwarp();                       // every lane has read the aux slab before it is overwritten below
+            }
+            if (EPI == EPI_MSE) {
+              if (row_ok) {
+                if (e.out_f32) {
+                  float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn;
+#pragma unroll
+                  for (int i = 0; i < 64; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
+                }
+                if (e.out2) {
+                  float (&v0)[32] = *reinterpret_cast<float (*)[32]>(&v[0]);
+                  float (&v1)[32] = *reinterpret_cast<float (*)[32]>(&v[32]);
+                  store_row32(e.out2 + (int64_t)row * e.out2_ld + col0s, e.out2_ps, e.out2_planes, nv > 32 ? 32 : nv, v0);
+                  if (nv > 32) store_row32(e.out2 + (int64_t)row * e.out2_ld + col0s + 32, e.out2_ps, e.out2_planes, nv - 32, v1);
+                }
+              }
+              float sq = 0.f;
+              const float scale = e.scale;
+#pragma unroll
+              for (int i = 0; i < 64; ++i) {
+                const float di = (row_ok && i < nv) ? (v[i] - y[i]) : 0.f;
+                sq += di * di;
+                v[i] = scale * di;
+              }
+              loss_local += (double)sq;
+            } else {  // EPI_DGRAD
+              if (e.add && row_ok) {
+                float a[32];
+                load_row32(e.add + (int64_t)row * e.add_ld + col0s, e.add_ps, e.add_planes, nv > 32 ? 32 : nv, a);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += a[i];
+                if (nv > 32) {
+                  load_row32(e.add + (int64_t)row * e.add_ld + col0s + 32, e.add_ps, e.add_planes, nv - 32, a);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[32 + i] += a[i];
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 64; ++i) {
+                float g = v[i];
+                if (USE_MASK) g = ((i < 32 ? mbits.x >> i : mbits.y >> (i - 32)) & 1u) ? g : 0.f;
+                else if (ACT != ACT_LINEAR) g *= act_bwd_from_out<ACT>(y[i]);
+                v[i] = (row_ok && i < nv) ? g : 0.f;
+              }
+              if (row_ok && e.out_f32) {
+                float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
+              }
+            }
+          }
+          if (!HAS_AUX) {                         // (with aux the slab was already claimed before the aux load)
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 qv;
+            qv.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); qv.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+            qv.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); qv.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = qv;
+          }
+          fence_proxy_async();                    // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&p.tmOut, slab, col0s, m_tile * BM + q * 32, 0);
+            tma_store_commit();
+          }
+          if (EPI != EPI_STORE && e.colsum) {
+            // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> columns lane, lane + 32
+#pragma unroll
+            for (int hcol = 0; hcol < 2; ++hcol) {
+              const int col = lane + 32 * hcol;
+              if (col < nv) {
+                float sum = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  const unsigned short hv = *reinterpret_cast<const unsigned short*>(slab_gen + r * 128 + ((((col >> 3) ^ (r & 7)) << 4) | ((col & 7) << 1)));
+                  sum += __uint_as_float((uint32_t)hv << 16);
+                }
+                atomicAdd(e.colsum + col0s + col, sum);
+              }
+            }
+            __syncwarp();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
+    if (TMAEPI && lane == 0) tma_store_wait_read<0>();
     if (EPI == EPI_MSE && e.loss) {
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, off);
@@ -578,25 +789,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 }
 
 typedef void (*GemmKernelFn)(const GemmParams);
-// host-side dispatch table: [epilogue type][activation]
-template <int EPI> struct KernelRow {
+// host-side dispatch table: [epilogue type][activation][tma epilogue]
+template <int EPI, bool T> struct KernelRow {
   static GemmKernelFn get(int act) {
     switch (act) {
-      case ACT_RELU:    return pvae_gemm_kernel<EPI, ACT_RELU>;
-      case ACT_TANH:    return pvae_gemm_kernel<EPI, ACT_TANH>;
-      case ACT_SIGMOID: return pvae_gemm_kernel<EPI, ACT_SIGMOID>;
-      case ACT_ELU:     return pvae_gemm_kernel<EPI, ACT_ELU>;
-      case ACT_SWISH:   return pvae_gemm_kernel<EPI, ACT_SWISH>;
-      default:          return pvae_gemm_kernel<EPI, ACT_LINEAR>;
+      case ACT_RELU:    return pvae_gemm_kernel<EPI, ACT_RELU, T>;
+      case ACT_TANH:    return pvae_gemm_kernel<EPI, ACT_TANH, T>;
+      case ACT_SIGMOID: return pvae_gemm_kernel<EPI, ACT_SIGMOID, T>;
+      case ACT_ELU:     return pvae_gemm_kernel<EPI, ACT_ELU, T>;
+      case ACT_SWISH:   return pvae_gemm_kernel<EPI, ACT_SWISH, T>;
+      default:          return pvae_gemm_kernel<EPI, ACT_LINEAR, T>;
     }
   }
 };
-static inline GemmKernelFn select_kernel(int epi, int act) {
+static inline GemmKernelFn select_kernel(int epi, int act, bool tma) {
   switch (epi) {
-    case EPI_STORE: return KernelRow<EPI_STORE>::get(act);
-    case EPI_DGRAD: return KernelRow<EPI_DGRAD>::get(act);
-    case EPI_MSE:   return pvae_gemm_kernel<EPI_MSE, ACT_LINEAR>;
-    default:        return pvae_gemm_kernel<EPI_WGRAD, ACT_LINEAR>;
+    case EPI_STORE: return tma ? KernelRow<EPI_STORE, true>::get(act) : KernelRow<EPI_STORE, false>::get(act);
+    case EPI_DGRAD: return tma ? KernelRow<EPI_DGRAD, true>::get(act) : KernelRow<EPI_DGRAD, false>::get(act);
+    case EPI_MSE:   return tma ? pvae_gemm_kernel<EPI_MSE, ACT_LINEAR, true> : pvae_gemm_kernel<EPI_MSE, ACT_LINEAR, false>;
+    default:        return pvae_gemm_kernel<EPI_WGRAD, ACT_LINEAR, false>;
   }
 }
 
