@@ -109,6 +109,7 @@ struct Device {
   int sms = 148;
   int mn_bn_align = 64;   // UMMA N granularity used when B is MN-major (PVAE_MN_BN_ALIGN)
   int tma_epilogue = 1;   // bf16 outputs leave through shared memory + TMA stores (PVAE_TMA_EPILOGUE=0 disables)
+  int cluster = 2;        // CTA pairs share the B tile through TMA multicast (PVAE_CLUSTER=1 disables)
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
@@ -142,12 +143,14 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   if (d.nseg == 1) p.tmA[1] = p.tmA[0];
   p.b_n0 = d.b_n0;
   p.b_dyn = d.B.dyn;
-  CKR(encode_map(&p.tmB, d.B, 64, d.b_major == MAJOR_K ? bn : BK));
+  const int cluster = (dev.cluster == 2 && p.m_tiles >= 2) ? 2 : 1;
+  p.cluster = cluster;
+  CKR(encode_map(&p.tmB, d.B, 64, d.b_major == MAJOR_K ? bn / cluster : BK));
   const int kb_total = p.kb[0] + p.kb[1];
   const int iters = kb_total * d.passes;
   int splits = 1;
   if (d.split) {
-    const int tiles = p.m_tiles * n_tiles;
+    const int tiles = cdiv(p.m_tiles, cluster) * cluster * n_tiles;
     splits = cdiv(2 * dev.sms, tiles);
     if (splits > iters) splits = iters;
     if (splits < 1) splits = 1;
@@ -171,10 +174,22 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
       CKR(encode_map(&p.tmAux, a, 64, 32));
     }
   }
-  const int units = p.m_tiles * n_tiles * splits;
-  const int grid = units < dev.sms ? units : dev.sms;
+  const int units = cdiv(p.m_tiles, cluster) * n_tiles * splits;       // units per CTA (pair)
+  const int slots = dev.sms / cluster;
+  const int grid = (units < slots ? units : slots) * cluster;
   GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act, tma);
-  fn<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, fn, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return PVAE_OK;
@@ -456,6 +471,8 @@ static int init_device(Device& dev, int device) {
   if (env) { int v = atoi(env); if (v == 16 || v == 32 || v == 64) dev.mn_bn_align = v; }
   env = getenv("PVAE_TMA_EPILOGUE");
   if (env) dev.tma_epilogue = atoi(env) != 0;
+  env = getenv("PVAE_CLUSTER");
+  if (env) dev.cluster = atoi(env) == 1 ? 1 : 2;
   CKR(resolve_driver());
   CKR(ensure_kernel_attr(dev));
   return PVAE_OK;

@@ -83,6 +83,7 @@ struct GemmParams {
   int32_t b_dyn;                   // B: add *row_cursor to the k row coordinate (MN-major)
   int32_t passes;                  // 1 = bf16, 3 = bf16x3
   int32_t m_tiles, n_tiles, bn, splits;
+  int32_t cluster;                 // 1, or 2: CTA pairs on adjacent M tiles share the B tile (each loads half, TMA multicast)
   const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
   CUtensorMap tmOut;               // TMA-store epilogue: the primary bf16 output, box 64 cols x 32 rows (one warp's slab)
   CUtensorMap tmAux;               // TMA-store epilogue: the aux input (same box)
@@ -143,6 +144,27 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
+// One lane of a converged warp (warp-uniform control flow around it keeps TMA / MMA operands in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -166,6 +188,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -453,7 +479,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     if (HAS_AUX) tma_prefetch_desc(&p.tmAux);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.cluster); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(auxfull_bar(w), 1);
     fence_barrier_init();
@@ -461,89 +487,118 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();        // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const int csize = p.cluster;
+  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / csize, unit_stride = gridDim.x / csize;
 
   const int row0 = p.row_cursor ? *p.row_cursor : 0;
   const int kb_total = p.kb[0] + p.kb[1];
   const int iters_total = p.passes * kb_total;
-  const int total_units = p.m_tiles * p.n_tiles * p.splits;
+  const int total_units = ((p.m_tiles + csize - 1) / csize) * p.n_tiles * p.splits;   // units of one CTA (pair)
   const int bn = p.bn;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      const int b_boxes = (bn + 63) >> 6;
-      const uint32_t stage_tx = A_STAGE_BYTES + (p.b_major == MAJOR_K ? (uint32_t)bn * (BK * 2) : (uint32_t)b_boxes * 8192u);
-      int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int split = u % p.splits;
-        const int tile = u / p.splits;
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
-        const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
-        KIter ki; ki.init(it_begin, p.kb[0], kb_total);
-        for (int it = it_begin; it < it_end; ++it, ki.next(p.kb[0], p.kb[1])) {
-          const int pass = ki.pass, seg = ki.seg, r = ki.r;
-          const int a_plane = (pass == 2) ? 1 : 0;
-          const int b_plane = (pass == 1) ? 1 : 0;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), stage_tx);
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
-          const int a_row = p.a_r0[seg] + (p.a_dyn[seg] ? row0 : 0);
-          if (p.a_major == MAJOR_K) {
-            tma_load_3d(sa, &p.tmA[seg], full_bar(stage), p.a_c0[seg] + r * BK, a_row + m_tile * BM, a_plane);
+    // The whole warp walks the loop (warp-uniform control flow); one elected lane issues the copies.
+    const int b_boxes = (bn + 63) >> 6;
+    const uint32_t stage_tx = A_STAGE_BYTES + (p.b_major == MAJOR_K ? (uint32_t)bn * (BK * 2) : (uint32_t)b_boxes * 8192u);
+    const int a_major = p.a_major, b_major = p.b_major;
+    const int hrows = bn >> 1;
+    int stage = 0; uint32_t phase = 0;
+    for (int u = unit0; u < total_units; u += unit_stride) {
+      const int split = u % p.splits;
+      const int tile = u / p.splits;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = (tile / p.n_tiles) * csize + crank;
+      const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
+      const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
+      KIter ki; ki.init(it_begin, p.kb[0], kb_total);
+      for (int it = it_begin; it < it_end; ++it, ki.next(p.kb[0], p.kb[1])) {
+        const int pass = ki.pass, seg = ki.seg, r = ki.r;
+        const int a_plane = (pass == 2) ? 1 : 0;
+        const int b_plane = (pass == 1) ? 1 : 0;
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint32_t fb = full_bar(stage);
+        const int a_row = p.a_r0[seg] + (p.a_dyn[seg] ? row0 : 0);
+        const int b_k = p.b_k0[seg] + r * BK;
+        const int b_n = p.b_n0 + n_tile * bn;
+        const CUtensorMap* tmA = &p.tmA[seg];
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(fb, stage_tx);
+          if (a_major == MAJOR_K) {
+            tma_load_3d(sa, tmA, fb, p.a_c0[seg] + r * BK, a_row + m_tile * BM, a_plane);
           } else {
-            tma_load_3d(sa,         &p.tmA[seg], full_bar(stage), p.a_c0[seg] + m_tile * BM,      a_row + r * BK, a_plane);
-            tma_load_3d(sa + 8192u, &p.tmA[seg], full_bar(stage), p.a_c0[seg] + m_tile * BM + 64, a_row + r * BK, a_plane);
+            tma_load_3d(sa,         tmA, fb, p.a_c0[seg] + m_tile * BM,      a_row + r * BK, a_plane);
+            tma_load_3d(sa + 8192u, tmA, fb, p.a_c0[seg] + m_tile * BM + 64, a_row + r * BK, a_plane);
           }
-          if (p.b_major == MAJOR_K) {
-            tma_load_3d(sb, &p.tmB, full_bar(stage), p.b_k0[seg] + r * BK, p.b_n0 + n_tile * bn, b_plane);
+          if (csize == 1) {
+            if (b_major == MAJOR_K) {
+              tma_load_3d(sb, &p.tmB, fb, b_k, b_n, b_plane);
+            } else {
+              const int b_row = b_k + (p.b_dyn ? row0 : 0);
+              for (int j = 0; j < b_boxes; ++j) tma_load_3d(sb + 8192u * j, &p.tmB, fb, b_n + 64 * j, b_row, b_plane);
+            }
           } else {
-            const int b_row = p.b_k0[seg] + r * BK + (p.b_dyn ? row0 : 0);
-            for (int j = 0; j < b_boxes; ++j)
-              tma_load_3d(sb + 8192u * j, &p.tmB, full_bar(stage), p.b_n0 + n_tile * bn + 64 * j, b_row, b_plane);
+            // CTA pair: this CTA fetches its half of the B tile and multicasts it into both CTAs' shared memory
+            if (b_major == MAJOR_K) {           // K-major: rows [crank * bn/2, +bn/2) of the tile (box rows = bn/2)
+              tma_load_3d_mc(sb + (uint32_t)(crank * hrows) * 128u, &p.tmB, fb, b_k, b_n + crank * hrows, b_plane, (uint16_t)3);
+            } else {
+              const int b_row = b_k + (p.b_dyn ? row0 : 0);
+              for (int j = crank; j < b_boxes; j += 2)
+                tma_load_3d_mc(sb + 8192u * j, &p.tmB, fb, b_n + 64 * j, b_row, b_plane, (uint16_t)3);
+            }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(bn, p.a_major, p.b_major);
-      const uint32_t a_kstep = (p.a_major == MAJOR_K) ? 2u : 128u;   // 16 k elements, in 16 B units: 32 B or 16 rows * 128 B
-      const uint32_t b_kstep = (p.b_major == MAJOR_K) ? 2u : 128u;
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int split = u % p.splits;
-        const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
-        const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    const uint32_t idesc = umma_idesc(bn, p.a_major, p.b_major);
+    const uint32_t a_kstep = (p.a_major == MAJOR_K) ? 2u : 128u;   // 16 k elements, in 16 B units: 32 B or 16 rows * 128 B
+    const uint32_t b_kstep = (p.b_major == MAJOR_K) ? 2u : 128u;
+    const uint64_t adesc0 = umma_desc(smem_base, p.a_major);
+    const uint64_t bdesc0 = umma_desc(smem_base + A_STAGE_BYTES, p.b_major);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = unit0; u < total_units; u += unit_stride) {
+      const int split = u % p.splits;
+      const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
+      const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
+      KIter ki; ki.init(it_begin, p.kb[0], kb_total);
+      uint32_t accum = 0u;
+      for (int it = it_begin; it < it_end; ++it, ki.next(p.kb[0], p.kb[1])) {
+        int k16 = (p.klen[ki.seg] - ki.r * BK + 15) >> 4;
+        k16 = k16 > 4 ? 4 : (k16 < 1 ? 1 : k16);
+        const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(stage * STAGE_BYTES) >> 4);
+        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)(stage * STAGE_BYTES) >> 4);
+        const uint32_t eb = empty_bar(stage);
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
-        KIter ki; ki.init(it_begin, p.kb[0], kb_total);
-        for (int it = it_begin; it < it_end; ++it, ki.next(p.kb[0], p.kb[1])) {
-          const int seg = ki.seg, r = ki.r;
-          int k16 = (p.klen[seg] - r * BK + 15) >> 4;
-          k16 = k16 > 4 ? 4 : (k16 < 1 ? 1 : k16);
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint64_t adesc = umma_desc(sa, p.a_major);
-          const uint64_t bdesc = umma_desc(sa + A_STAGE_BYTES, p.b_major);
-          for (int k = 0; k < k16; ++k)
-            umma_bf16(tmem_d, adesc + (uint64_t)(a_kstep * k), bdesc + (uint64_t)(b_kstep * k), idesc,
-                      (it > it_begin || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (elect_one()) {
+          umma_bf16(tmem_d, adesc, bdesc, idesc, accum);
+          if (k16 > 1) umma_bf16(tmem_d, adesc + (uint64_t)a_kstep, bdesc + (uint64_t)b_kstep, idesc, 1u);
+          if (k16 > 2) umma_bf16(tmem_d, adesc + (uint64_t)(2 * a_kstep), bdesc + (uint64_t)(2 * b_kstep), idesc, 1u);
+          if (k16 > 3) umma_bf16(tmem_d, adesc + (uint64_t)(3 * a_kstep), bdesc + (uint64_t)(3 * b_kstep), idesc, 1u);
+          if (csize == 1) umma_commit(eb);                 // frees the smem slot once these MMAs have read it
+          else umma_commit_mc(eb, (uint16_t)3);            // ... in both CTAs of the pair (both producers write both)
         }
-        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        accum = 1u;
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(tfull_bar(acc));        // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
@@ -558,10 +613,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     uint32_t aux_phase = 0;
     const uint32_t slab = smem_base + OFF_STAGING + (warp - 4) * SLAB_BYTES;      // this warp's private staging slab
     uint8_t* slab_gen = smem_gen + OFF_STAGING + (warp - 4) * SLAB_BYTES;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int u = unit0; u < total_units; u += unit_stride) {
       const int tile = u / p.splits;
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int m_tile = (tile / p.n_tiles) * csize + crank;
       const int row_in_tile = q * 32 + lane;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < m_valid;
@@ -747,7 +802,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           }
           fence_proxy_async();                    // generic-proxy writes -> visible to the TMA store
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && m_tile * BM + q * 32 < m_valid) {
             tma_store_3d(&p.tmOut, slab, col0s, m_tile * BM + q * 32, 0);
             tma_store_commit();
           }
@@ -785,6 +840,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();            // no CTA leaves while its peer may still multicast into it / signal its barriers
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 

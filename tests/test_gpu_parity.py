@@ -128,6 +128,22 @@ def test_tma_epilogue_equals_direct_epilogue(world, cfg_name, B, monkeypatch):
         assert P.rel_l2(a["grads"][k], g) < 0.15, (k, P.rel_l2(a["grads"][k], g), P.rel_l2(b["grads"][k], g))
 
 
+@pytest.mark.parametrize("world", [True, False])
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_cta_pair_multicast_equals_single_cta(world, precision, monkeypatch):
+    """CTA pairs that share the B tile through TMA multicast must reproduce the single-CTA kernel (same products, same
+    accumulation order inside a tile; only the order of the fp32 split-K atomics differs)."""
+    res = {}
+    for mode in ("2", "1"):
+        monkeypatch.setenv("PVAE_CLUSTER", mode)
+        o, p = P.step_pair(P.DEFAULT, 700, world, precision=precision, out_std=0.2, cyc_coeff=0.05, n_rows=800, cursor=50)
+        res[mode] = p
+    a, b = res["2"], res["1"]
+    assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(b["loss"])
+    for k in b["grads"]:
+        assert P.rel_l2(a["grads"][k], b["grads"][k]) < 2e-5, (k, P.rel_l2(a["grads"][k], b["grads"][k]))
+
+
 # ---- golden fixtures generated by the reference itself ---------------------------------------------------------------------
 def test_reference_fixture_forward_losses_gradients():
     g = np.load(os.path.join(G, "ref_small_step.npz"))
