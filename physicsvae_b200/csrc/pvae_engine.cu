@@ -375,19 +375,20 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
         GemmDesc d;
         d.a_major = MAJOR_MN; d.b_major = MAJOR_MN;
         d.nseg = 1;
-        d.A[0] = (l == 0) ? in.seg[s] : ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
-        d.B = gl;
+        const View xin = (l == 0) ? in.seg[s] : ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
+        const int m_in = xin.width;
         d.K[0] = batch;
-        d.M = d.A[0].width; d.N = net.out_dims[l];
         d.passes = h->passes;
         d.split = true;
         d.epi.type = EPI_WGRAD;
         d.epi.out_f32 = net.grad + net.gW[l] + col0;
-        d.epi.f32_sm = 1; d.epi.f32_sn = net.in_dims[l];
         d.epi.f32_atomic = 1;
-        // the A operand of a wgrad walks the batch along k: the dynamic cursor applies to its row coordinate
+        d.A[0] = xin; d.B = gl;
+        d.M = m_in; d.N = net.out_dims[l];
+        d.epi.f32_sm = 1; d.epi.f32_sn = net.in_dims[l];
+        // the operand that comes from the resident buffer walks the batch along k: the dynamic cursor applies to its rows
         CKR(launch_gemm(h->dev, d, st));
-        col0 += d.M;
+        col0 += m_in;
       }
     }
     if (l > 0) {

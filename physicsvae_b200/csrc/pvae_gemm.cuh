@@ -497,7 +497,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   const int row0 = p.row_cursor ? *p.row_cursor : 0;
   const int kb_total = p.kb[0] + p.kb[1];
   const int iters_total = p.passes * kb_total;
-  const int total_units = ((p.m_tiles + csize - 1) / csize) * p.n_tiles * p.splits;   // units of one CTA (pair)
+  // units of one CTA (pair): tile-minor / split-major, so that the CTAs running at the same time share K ranges through L2
+  const int tile_units = ((p.m_tiles + csize - 1) / csize) * p.n_tiles;
+  const int total_units = tile_units * p.splits;
   const int bn = p.bn;
 
   if (warp == 0) {
@@ -509,8 +511,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     const int hrows = bn >> 1;
     int stage = 0; uint32_t phase = 0;
     for (int u = unit0; u < total_units; u += unit_stride) {
-      const int split = u % p.splits;
-      const int tile = u / p.splits;
+      const int split = u / tile_units;
+      const int tile = u - split * tile_units;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = (tile / p.n_tiles) * csize + crank;
       const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = unit0; u < total_units; u += unit_stride) {
-      const int split = u % p.splits;
+      const int split = u / tile_units;
       const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
       const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -614,18 +616,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     const uint32_t slab = smem_base + OFF_STAGING + (warp - 4) * SLAB_BYTES;      // this warp's private staging slab
     uint8_t* slab_gen = smem_gen + OFF_STAGING + (warp - 4) * SLAB_BYTES;
     for (int u = unit0; u < total_units; u += unit_stride) {
-      const int tile = u / p.splits;
+      const int tile = u % tile_units;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = (tile / p.n_tiles) * csize + crank;
       const int row_in_tile = q * 32 + lane;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < m_valid;
+      // operands of this warp's (at most two) sub-tiles that do not depend on the accumulator: fetched while the main loop runs
+      float pre_bias[4] = {0.f, 0.f, 0.f, 0.f};
+      uint2 pre_mask[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+      if (TMAEPI) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int cs = n_tile * bn + (half + 2 * j) * 64;
+          if ((half + 2 * j) * 64 < bn && cs < n_valid) {
+            if (bias) {
+              pre_bias[2 * j] = (cs + lane < n_valid) ? __ldg(bias + cs + lane) : 0.f;
+              pre_bias[2 * j + 1] = (cs + lane + 32 < n_valid) ? __ldg(bias + cs + lane + 32) : 0.f;
+            }
+            if (USE_MASK && row_ok) pre_mask[j] = __ldg(reinterpret_cast<const uint2*>(e.mask + (int64_t)row * e.mask_ld + (cs >> 5)));
+          }
+        }
+      }
       if (HAS_AUX) {
         // fetch the aux slab of this warp's first sub-tile while the main loop of the tile is still running
         const int col0s = n_tile * bn + half * 64;
         if (col0s < n_valid && half * 64 < bn) {
-          if (lane == 0) {
-            tma_store_wait_read<0>();             // the slab's previous store has been read out
+          tma_store_wait_read<0>();               // the slab's previous store has been read out (groups are per thread)
+          __syncwarp();
+          if (elect_one()) {
             mbar_expect_tx(auxfull_bar(warp - 4), SLAB_BYTES);
             tma_load_3d(slab, &p.tmAux, auxfull_bar(warp - 4), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
           }
@@ -667,16 +686,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           int nv = n_valid - col0s; nv = nv > 64 ? 64 : nv;
           const int tile_nv = bn - s * 64;        // columns of this sub-tile that belong to this tile
           if (tile_nv < nv) nv = tile_nv;
-          uint2 mbits = make_uint2(0u, 0u);
-          if (USE_MASK && row_ok) mbits = __ldg(reinterpret_cast<const uint2*>(e.mask + (int64_t)row * e.mask_ld + (col0s >> 5)));
-          float bias_lo = 0.f, bias_hi = 0.f;     // lane -> bias of columns lane and lane + 32 of the sub-tile
-          if (bias) {
-            bias_lo = (lane < nv) ? __ldg(bias + col0s + lane) : 0.f;
-            bias_hi = (lane + 32 < nv) ? __ldg(bias + col0s + lane + 32) : 0.f;
-          }
+          const int sj = (s - half) >> 1;         // 0 or 1: which of this warp's sub-tiles (bn <= 256)
+          const uint2 mbits = sj ? pre_mask[1] : pre_mask[0];
+          const float bias_lo = sj ? pre_bias[2] : pre_bias[0];   // lane -> bias of columns lane and lane + 32 of the sub-tile
+          const float bias_hi = sj ? pre_bias[3] : pre_bias[1];
           if (HAS_AUX && s != half) {             // later sub-tiles of the tile: the aux load is exposed
-            if (lane == 0) {
-              tma_store_wait_read<0>();
+            tma_store_wait_read<0>();
+            __syncwarp();
+            if (elect_one()) {
               mbar_expect_tx(auxfull_bar(warp - 4), SLAB_BYTES);
               tma_load_3d(slab, &p.tmAux, auxfull_bar(warp - 4), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
             }
@@ -709,7 +726,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           }
           if (EPI == EPI_STORE) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = (row_ok && i < nv) ? act_fwd<ACT>(v[i]) : 0.f;
+            for (int i = 0; i < 64; ++i) v[i] = act_fwd<ACT>(v[i]);
+            if (nv < 64) {                        // ragged last sub-tile: keep the padding columns of the mask / slab zero
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = (i < nv) ? v[i] : 0.f;
+            }
             if (row_ok) {
               if (e.out_f32) {
                 float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn;
@@ -778,9 +799,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 #pragma unroll
               for (int i = 0; i < 64; ++i) {
                 float g = v[i];
-                if (USE_MASK) g = ((i < 32 ? mbits.x >> i : mbits.y >> (i - 32)) & 1u) ? g : 0.f;
+                if (USE_MASK) g = ((i < 32 ? mbits.x >> i : mbits.y >> (i - 32)) & 1u) ? g : 0.f;   // mask is 0 for rows >= m_valid
                 else if (ACT != ACT_LINEAR) g *= act_bwd_from_out<ACT>(y[i]);
-                v[i] = (row_ok && i < nv) ? g : 0.f;
+                v[i] = g;
+              }
+              if (nv < 64 || (!USE_MASK && !row_ok)) {   // keep what the bias-gradient column sums must not see at zero
+#pragma unroll
+                for (int i = 0; i < 64; ++i) v[i] = (row_ok && i < nv) ? v[i] : 0.f;
               }
               if (row_ok && e.out_f32) {
                 float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn;
@@ -790,7 +815,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             }
           }
           if (!HAS_AUX) {                         // (with aux the slab was already claimed before the aux load)
-            if (lane == 0) tma_store_wait_read<0>();
+            tma_store_wait_read<0>();             // bulk groups are per thread: only the electing lane ever has pending ones
             __syncwarp();
           }
 #pragma unroll
@@ -802,9 +827,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           }
           fence_proxy_async();                    // generic-proxy writes -> visible to the TMA store
           __syncwarp();
-          if (lane == 0 && m_tile * BM + q * 32 < m_valid) {
-            tma_store_3d(&p.tmOut, slab, col0s, m_tile * BM + q * 32, 0);
-            tma_store_commit();
+          if (m_tile * BM + q * 32 < m_valid) {   // warp-uniform
+            if (elect_one()) {
+              tma_store_3d(&p.tmOut, slab, col0s, m_tile * BM + q * 32, 0);
+              tma_store_commit();
+            }
+            __syncwarp();
           }
           if (EPI != EPI_STORE && e.colsum) {
             // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> columns lane, lane + 32
@@ -830,7 +858,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
-    if (TMAEPI && lane == 0) tma_store_wait_read<0>();
+    if (TMAEPI) tma_store_wait_read<0>();
     if (EPI == EPI_MSE && e.loss) {
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, off);
