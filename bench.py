@@ -207,8 +207,7 @@ def run_b200(args, cfg):
             eng.vae_step(B, eps=None, seed=1234, offset=rank, noise=True, a_coeff=1.0, kl_coeff=1.0, cyc_coeff=1e-3)
         if world > 1:
             parallel.allreduce_avg_(grads)
-        tr.optimizer.step()
-        eng.sync_weights(nets)
+        tr.optimizer.step()                 # fused Adam + shadow-weight refresh (physicsvae_b200.optim.PvaeAdam)
         eng.advance_cursor(B, B, n_rows)
 
     eng.set_cursor(0)
@@ -306,7 +305,6 @@ def run_b200(args, cfg):
         loss = tr.compute_loss(y, x)
         loss.backward()
         tr.optimizer.step()
-        model.mark_weights_dirty()
         return loss.item()
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(3):
@@ -338,9 +336,14 @@ def run_b200(args, cfg):
             line["cpu_baseline"] = {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port",
                                     "sample": "3 steps of %d transitions (%s phase), oracle port of compute_loss+backward+Adam, fp32 torch-CPU" % (rows, phase)}
         print(json.dumps(line), flush=True)
+    # Teardown: a CUDA graph that captured NCCL work keeps the communicator busy and destroy_process_group() can block on
+    # it forever; every rank is done with collectives here, so drop the graph and leave without the collective teardown.
+    graph = None
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -91,6 +91,16 @@ int64_t pvae_net_grad_elems(pvae_handle h, int net);
  * (after load_state_dict or optimizer.step()).  */
 int pvae_sync_weights(pvae_handle h, uint32_t net_mask, pvae_stream s);
 
+/* --- optimizer -------------------------------------------------------------------------------------------------------- */
+/* One Adam step for the layers of `net` selected by layer_mask (bit l), on the bound fp32 masters and the bound gradient
+ * buffer, followed -- in the same kernels -- by the refresh of the bf16 shadow operands.  exp_avg_dev / exp_avg_sq_dev: fp32
+ * state in the flat layout of the gradient buffer ([W0|b0|W1|b1|...]), owned by the caller.  step_dev: device fp32 scalar
+ * holding the number of steps taken so far by these parameters; it is incremented on the stream before the update (so the
+ * call is CUDA-graph replayable).  Arithmetic follows torch.optim.Adam(amsgrad=False, maximize=False).
+ * replaces: optimizer.step() (torch_models.py:143) + pvae_sync_weights for the stepped layers. */
+int pvae_adam_step(pvae_handle h, int net, uint32_t layer_mask, float* exp_avg_dev, float* exp_avg_sq_dev, float* step_dev,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, pvae_stream s);
+
 /* --- workspace ----------------------------------------------------------------------------------------------- */
 int pvae_workspace_bytes(pvae_handle h, size_t* bytes);
 int pvae_bind_workspace(pvae_handle h, void* ws_dev, size_t bytes);

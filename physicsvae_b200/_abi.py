@@ -25,7 +25,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libpvae_sm100.so")
 # every symbol include/pvae_sm100.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = [
     "pvae_last_error", "pvae_abi_version", "pvae_create", "pvae_destroy", "pvae_bind_net", "pvae_net_grad_elems",
-    "pvae_sync_weights", "pvae_workspace_bytes", "pvae_bind_workspace", "pvae_transitions_bytes", "pvae_ingest",
+    "pvae_sync_weights", "pvae_adam_step", "pvae_workspace_bytes", "pvae_bind_workspace", "pvae_transitions_bytes", "pvae_ingest",
     "pvae_bind_transitions", "pvae_set_cursor", "pvae_advance_cursor", "pvae_world_step", "pvae_vae_step",
     "pvae_forward", "pvae_gemm_bf16", "pvae_launch_count",
 ]
@@ -68,6 +68,7 @@ def load():
     lib.pvae_net_grad_elems.restype = i64
     lib.pvae_net_grad_elems.argtypes = [vp, i32]
     lib.pvae_sync_weights.argtypes = [vp, u32, vp]
+    lib.pvae_adam_step.argtypes = [vp, i32, u32, vp, vp, vp, f32, f32, f32, f32, f32, vp]
     lib.pvae_workspace_bytes.argtypes = [vp, C.POINTER(sz)]
     lib.pvae_bind_workspace.argtypes = [vp, vp, sz]
     lib.pvae_transitions_bytes.argtypes = [vp, i64, C.POINTER(sz)]

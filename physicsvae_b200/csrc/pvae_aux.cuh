@@ -59,6 +59,43 @@ __global__ void sync_weights_kernel(const float* __restrict__ W, int out, int in
   }
 }
 
+// ---- fused Adam + shadow refresh for one Linear layer ----------------------------------------------------------------------
+// torch.optim.Adam semantics (torch_models.py:119-122: lr, betas (0.9, 0.999), eps 1e-8, weight_decay L2, no amsgrad):
+//   g += wd * p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// and, in the same pass, the bf16 (hi / lo) shadow operand of the updated weight in its padded two-segment layout.
+// Elements [0, out*in) are the weight, [out*in, out*in + out) the bias (flat layout of one layer: W | b).
+__global__ void adam_layer_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                                  float* __restrict__ v, const float* __restrict__ step_dev, float lr, float b1, float b2,
+                                  float eps, float wd, int out, int in, int k0, int K0pad, int Kpad,
+                                  __nv_bfloat16* __restrict__ Wsh, int64_t ps, int planes) {
+  const float t = *step_dev;
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  const int64_t nw = (int64_t)out * in, total = nw + out;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float p = param[i];
+    float g = grad[i];
+    if (wd != 0.f) g += wd * p;
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    p -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    param[i] = p;
+    if (i < nw) {
+      const int o = (int)(i / in);
+      const int c = (int)(i - (int64_t)o * in);
+      const int sc = c < k0 ? c : K0pad + (c - k0);
+      const int64_t si = (int64_t)o * Kpad + sc;
+      const __nv_bfloat16 h = f2bf(p);
+      Wsh[si] = h;
+      if (planes > 1) Wsh[ps + si] = f2bf(p - __bfloat162float(h));
+    }
+  }
+}
+__global__ void add_scalar_kernel(float* x, float d) { if (threadIdx.x == 0 && blockIdx.x == 0) *x += d; }
+
 // ---- Philox4x32-10 + Box-Muller: counter-based N(0,1) stream for the (seed, offset) noise mode ----------------
 __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll

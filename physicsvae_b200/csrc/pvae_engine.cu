@@ -605,6 +605,32 @@ int pvae_sync_weights(pvae_handle h, uint32_t net_mask, pvae_stream s) {
   return PVAE_OK;
 }
 
+int pvae_adam_step(pvae_handle h, int net_id, uint32_t layer_mask, float* exp_avg_dev, float* exp_avg_sq_dev, float* step_dev,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, pvae_stream s) {
+  if (!h || net_id < 0 || net_id >= PVAE_NUM_NETS) return fail(PVAE_ERR_INVALID, "bad handle / net id");
+  if (!exp_avg_dev || !exp_avg_sq_dev || !step_dev) return fail(PVAE_ERR_INVALID, "null optimizer state");
+  Net& net = h->nets[net_id];
+  if (!net.bound || !net.grad) return fail(PVAE_ERR_STATE, "net %d has no parameters / gradient buffer bound", net_id);
+  cudaStream_t st = (cudaStream_t)s;
+  add_scalar_kernel<<<1, 32, 0, st>>>(step_dev, 1.f);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  for (int l = 0; l < net.n_layers; ++l) {
+    if (!(layer_mask & (1u << l))) continue;
+    // the flat layout requires b[l] to follow W[l] directly (true for the views physicsvae_b200 hands out)
+    if (net.b[l] != net.W[l] + (int64_t)net.in_dims[l] * net.out_dims[l])
+      return fail(PVAE_ERR_INVALID, "net %d layer %d: bias does not follow the weight in memory (flat [W|b] layout required)", net_id, l);
+    const int k0 = l == 0 ? net.k0 : net.in_dims[l];
+    const int K0pad = l == 0 && net.k1 ? net.K0pad : net.kpad[l];
+    const int64_t total = (int64_t)net.out_dims[l] * net.in_dims[l] + net.out_dims[l];
+    adam_layer_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(
+        const_cast<float*>(net.W[l]), net.grad + net.gW[l], exp_avg_dev + net.gW[l], exp_avg_sq_dev + net.gW[l], step_dev, lr, beta1,
+        beta2, eps, weight_decay, net.out_dims[l], net.in_dims[l], k0, K0pad, net.kpad[l], net.Wsh[l], net.wsh_ps[l], h->planes);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
 int pvae_workspace_bytes(pvae_handle h, size_t* bytes) {
   if (!h || !bytes) return fail(PVAE_ERR_INVALID, "null argument");
   *bytes = h->ws_bytes;

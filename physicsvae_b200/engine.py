@@ -105,6 +105,13 @@ class Engine:
         with torch.cuda.device(self.device):
             _abi.check(self.lib.pvae_sync_weights(self._h, mask, _stream()))
 
+    def adam_step(self, name, layer_mask, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+        """Fused Adam + shadow refresh for the selected layers of one net (include/pvae_sm100.h, pvae_adam_step)."""
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_adam_step(self._h, NET_NAMES.index(name), int(layer_mask), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                               _ptr(step), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                               _stream()))
+
     # ---- resident transition buffer -------------------------------------------------------------------------------
     def alloc_transitions(self, n_rows):
         nbytes = C.c_size_t(0)

@@ -14,6 +14,7 @@ import torch.optim as optim
 import torch.utils.data as data
 
 from . import _abi, parallel
+from .optim import PvaeAdam
 
 try:  # pragma: no cover - ray is not installed in the build image
     from ray import tune
@@ -164,10 +165,14 @@ class TrainModel(_TrainableBase):
         self.model = self.model.to(self.device)
         self.engine = self.model.engine(max_batch=self._local_rows(config.get("batch_size")),
                                         precision=config.get("engine_precision", "bf16x3"))
-        capturable = bool(config.get("optimizer_capturable", False))     # CUDA-graph replay of the whole step (bench.py)
         lr = config.get("lr", 1e-3)
-        self.optimizer = optim.Adam(self.model.parameters(), lr=torch.tensor(float(lr), device=self.device) if capturable else lr,
-                                    weight_decay=config.get("weight_decay", 0.0), fused=True, capturable=capturable)
+        if config.get("optimizer", "pvae_adam") == "torch_adam":
+            capturable = bool(config.get("optimizer_capturable", False))     # CUDA-graph replay of the whole step
+            self.optimizer = optim.Adam(self.model.parameters(), lr=torch.tensor(float(lr), device=self.device) if capturable else lr,
+                                        weight_decay=config.get("weight_decay", 0.0), fused=True, capturable=capturable)
+        else:
+            # same interface and arithmetic as optim.Adam, executed by the engine together with the shadow-weight refresh
+            self.optimizer = PvaeAdam(self.model, lr=lr, weight_decay=config.get("weight_decay", 0.0))
         self.lr_scheduler = get_lr_scheduler(self.optimizer, config.get("lr_schedule", None), config.get("lr_schedule_params", None))
         self.loss_fn = get_loss_fn(config.get("loss", "MSE"))
         self.loss_fn_test = get_loss_fn(config.get("loss_test", "MSE"))
@@ -241,7 +246,8 @@ class TrainModel(_TrainableBase):
         """zero_grad -> compute_loss -> backward -> [all-reduce] -> Adam, for rows [lo, hi) of the resident buffer."""
         loss = self.batch_loss(lo, hi)
         self.optimizer.step()
-        self.model.mark_weights_dirty()
+        if not isinstance(self.optimizer, PvaeAdam):
+            self.model.mark_weights_dirty()      # (PvaeAdam refreshes the shadow operands itself)
         return loss
 
     def batch_loss(self, lo, hi):

@@ -276,6 +276,41 @@ def test_trainer_trajectory_phase_switch_and_checkpoints(tmp_path):
     P.assert_close("restored forward", tr2.compute_model(x.cuda()), om2.forward(x)[:, :5])
 
 
+@pytest.mark.parametrize("weight_decay", [0.0, 0.01])
+def test_fused_adam_matches_torch_adam_and_refreshes_shadow(weight_decay):
+    """physicsvae_b200.optim.PvaeAdam (one kernel per layer: Adam update + bf16 shadow refresh) vs torch.optim.Adam on the same
+    gradients, including the lazy per-net state and frozen sub-nets; afterwards the engine's forward must see the new weights."""
+    from physicsvae_b200.optim import PvaeAdam
+    om, layers = P.oracle_model(P.SMALL, out_std=0.3)
+    m = P.product_model(P.SMALL, layers, om.state_dict(), max_batch=128)
+    eng = m.engine()
+    m.sync_weights()
+    ref = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in m.state_dict().items()}
+    topt = torch.optim.Adam(list(ref.values()), lr=3e-3, weight_decay=weight_decay)
+    opt = PvaeAdam(m, lr=3e-3, weight_decay=weight_decay)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for it in range(5):
+        world = it < 2                       # phase switch: world model first, then encoder + decoder
+        m.set_learnable_task_encoder(not world); m.set_learnable_motor_decoder(not world); m.set_learnable_world_model(world)
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                p.grad.copy_(torch.randn(p.shape, generator=gen, device="cuda") * 1e-2)
+                ref[k].grad = p.grad.clone()
+            else:
+                ref[k].grad = None
+        opt.step()
+        topt.step()
+    for k, p in m.named_parameters():
+        P.assert_close("adam " + k, p, ref[k], rtol=1e-5, atol=1e-7)
+    assert len(opt.state) == len(topt.state) == 2 * (3 + 3 + 4)
+    x = torch.randn(64, 74, device="cuda")
+    a = eng.forward(x, 15, noise=False)          # shadow operands as refreshed by the optimizer kernels
+    m.sync_weights()                             # full refresh from the fp32 masters
+    b = eng.forward(x, 15, noise=False)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_compute_loss_reference_signature(tmp_path):
     from physicsvae_b200 import train_physics_vae as tp
     f, data = _pickle(tmp_path)
