@@ -318,9 +318,21 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* base, int64_t ps, int
   }
 }
 __device__ __forceinline__ void store_f32_row32(float* dst, int64_t sn, int nvalid, const float (&v)[32]) {
+  if (sn == 1 && nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) reinterpret_cast<float4*>(dst)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 32; ++i)
     if (i < nvalid) dst[(int64_t)i * sn] = v[i];
+}
+// 64 values of one row (a TMA-epilogue sub-tile) to an fp32 output with column stride sn
+__device__ __forceinline__ void store_f32_row64(float* dst, int64_t sn, int nvalid, const float (&v)[64]) {
+  const float (&v0)[32] = *reinterpret_cast<const float (*)[32]>(&v[0]);
+  const float (&v1)[32] = *reinterpret_cast<const float (*)[32]>(&v[32]);
+  store_f32_row32(dst, sn, nvalid > 32 ? 32 : nvalid, v0);
+  if (nvalid > 32) store_f32_row32(dst + 32 * sn, sn, nvalid - 32, v1);
 }
 // Transposing butterfly: on return lane j holds sum over the 32 lanes of v[j].
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -732,11 +744,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
               for (int i = 0; i < 64; ++i) v[i] = (i < nv) ? v[i] : 0.f;
             }
             if (row_ok) {
-              if (e.out_f32) {
-                float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn;
-#pragma unroll
-                for (int i = 0; i < 64; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
-              }
+              if (e.out_f32) store_f32_row64(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn, e.f32_sn, nv, v);
               if (ACT == ACT_RELU && e.mask) {
                 uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
@@ -763,11 +771,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             }
             if (EPI == EPI_MSE) {
               if (row_ok) {
-                if (e.out_f32) {
-                  float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn;
-#pragma unroll
-                  for (int i = 0; i < 64; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
-                }
+                if (e.out_f32) store_f32_row64(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn, e.f32_sn, nv, v);
                 if (e.out2) {
                   float (&v0)[32] = *reinterpret_cast<float (*)[32]>(&v[0]);
                   float (&v1)[32] = *reinterpret_cast<float (*)[32]>(&v[32]);
@@ -807,11 +811,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 #pragma unroll
                 for (int i = 0; i < 64; ++i) v[i] = (row_ok && i < nv) ? v[i] : 0.f;
               }
-              if (row_ok && e.out_f32) {
-                float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn;
-#pragma unroll
-                for (int i = 0; i < 64; ++i) if (i < nv) dst[(int64_t)i * e.f32_sn] = v[i];
-              }
+              if (row_ok && e.out_f32) store_f32_row64(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn, e.f32_sn, nv, v);
             }
           }
           if (!HAS_AUX) {                         // (with aux the slab was already claimed before the aux load)

@@ -74,6 +74,13 @@ def test_loco_dims_step_matches_oracle(world):
 
 
 @pytest.mark.parametrize("world", [True, False])
+def test_wide_dims_step_matches_oracle(world):
+    # BASELINE.json configs[4]: dim_state 512, dim_action 128, hidden [1024, 1024, 1024] for all three trained MLPs
+    o, p = P.step_pair(P.WIDE, 160, world, out_std=0.1, cyc_coeff=0.01, n_rows=200, cursor=40)
+    P.check_step(o, p, 160)
+
+
+@pytest.mark.parametrize("world", [True, False])
 def test_smooth_activation_gradients_are_tight(world):
     # ELU has a continuous derivative, so there are no ReLU-mask flips and the backward machinery can be held to 1e-4
     o, p = P.step_pair(P.SMALL, 200, world, act="elu", out_std=0.3, cyc_coeff=0.05)
