@@ -35,8 +35,8 @@ CONFIGS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--phase", default="world", choices=["world", "vae"])
     ap.add_argument("--config", default="default", choices=sorted(CONFIGS))
@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:
@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
     def stop(self, t0, t1):
         if self.proc:
             self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for t, r in self.rows if len(r) >= 7]
+        rows = [r for t, r in self.rows if t0 - 0.02 <= t <= t1 + 0.02 and len(r) >= 7] or [r for t, r in self.rows if len(r) >= 7]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -283,13 +283,24 @@ def run_b200(args, cfg):
         k1.synchronize()
         kms.append(k0.elapsed_time(k1))
         eng.advance_cursor(B, B, n_rows)
-    gemm_launches = {"world": 3 * cfg["wm"][1] + 4}.get(phase)
+    gemm_launches = (_abi.launch_count() - n0) // len(kms) - 2          # minus finalize_loss + cursor advance
     kernel_ms = statistics.median(kms)
     pk, pk_src = peaks()
     achieved = flops_step / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the same workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s/%s/%d" % (args.config, phase, B)
+        if key in tj:
+            traffic = tj[key]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_src + " (sustained; burst %.1f)" % pk["bf16_tflops"],
-                "kernel": "pvae_gemm_kernel", "kernel_ms_per_step": kernel_ms, "algorithmic_flops_per_step": flops_step,
+                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
+                "peak_source": pk_src + " (sustained; burst %.1f)" % pk["bf16_tflops"],
+                "kernel": "pvae_gemm_kernel", "launches_per_step": int(gemm_launches),
+                "avg_launch_ms": kernel_ms / max(gemm_launches, 1), "algorithmic_flops_per_launch": flops_step / max(gemm_launches, 1),
+                "kernel_ms_per_step": kernel_ms, "algorithmic_flops_per_step": flops_step,
                 "whole_step_tflops": flops_step / (ms / args.steps * 1e-3) / 1e12}
 
     # ---- end-to-end leg: the reference-facing call with HOST buffers.  Per step, exactly what torch_models.TrainModel.step
