@@ -150,10 +150,18 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   const int iters = kb_total * d.passes;
   int splits = 1;
   if (d.split) {
-    const int tiles = cdiv(p.m_tiles, cluster) * cluster * n_tiles;
-    splits = cdiv(2 * dev.sms, tiles);
-    if (splits > iters) splits = iters;
-    if (splits < 1) splits = 1;
+    // Split K so that the work units fill whole waves of the persistent grid: the kernel lasts as long as its busiest
+    // CTA (pair), i.e. waves(s) * (k-blocks per unit + the unit's non-overlapped epilogue share).  1024x1024 wgrad at
+    // batch 65536: 16 pair tiles on 74 pairs -- 10 splits need 3 waves (72 % busy), 9 splits need 2 (97 %).
+    const int tiles = cdiv(p.m_tiles, cluster) * n_tiles;
+    const int slots = dev.sms / cluster;
+    const int epi_cost = 2;                       // k-block equivalents of the fp32 red.add epilogue that is not hidden
+    const int max_splits = iters < 96 ? iters : 96;
+    long best = -1;
+    for (int s = 1; s <= max_splits; ++s) {
+      const long cost = (long)cdiv(tiles * s, slots) * (cdiv(iters, s) + epi_cost);
+      if (best < 0 || cost < best) { best = cost; splits = s; }
+    }
   }
   p.splits = splits;
   p.row_cursor = dev.cursor;
