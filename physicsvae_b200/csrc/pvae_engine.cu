@@ -69,7 +69,7 @@ struct View {
   int dyn = 0;          // add the device-side row cursor to row coordinates
 };
 
-static int encode_map(CUtensorMap* m, const View& v, int box_cols, int box_rows) {
+static int encode_map(CUtensorMap* m, const View& v, int box_cols, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   if ((reinterpret_cast<uintptr_t>(v.base) & 15) != 0) return fail(PVAE_ERR_INVALID, "operand base %p is not 16-byte aligned", (const void*)v.base);
   if ((v.ld & 7) != 0) return fail(PVAE_ERR_INVALID, "operand row stride %lld is not a multiple of 8 elements", (long long)v.ld);
   if (v.planes > 1 && (v.ps & 7) != 0) return fail(PVAE_ERR_INVALID, "operand plane stride %lld is not a multiple of 8 elements", (long long)v.ps);
@@ -79,7 +79,7 @@ static int encode_map(CUtensorMap* m, const View& v, int box_cols, int box_rows)
   cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(v.base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d x %lld x %d, ld %lld, box %d x %d", (int)r, v.width,
@@ -109,7 +109,7 @@ struct Device {
   int sms = 148;
   int mn_bn_align = 64;   // UMMA N granularity used when B is MN-major (PVAE_MN_BN_ALIGN)
   int tma_epilogue = 1;   // bf16 outputs leave through shared memory + TMA stores (PVAE_TMA_EPILOGUE=0 disables)
-  int cluster = 2;        // CTA pairs share the B tile through TMA multicast (PVAE_CLUSTER=1 disables)
+  int cluster = 2;        // CTA pairs run tcgen05.mma.cta_group::2 on two adjacent M tiles (PVAE_CLUSTER=1 disables)
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
@@ -123,10 +123,15 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   p.b_major = d.b_major;
   p.passes = d.passes;
   p.m_tiles = cdiv(d.M, BM);
+  // CTA pairs (tcgen05.mma.cta_group::2, 256 x bn per instruction) whenever there are two M tiles to pair
+  const int cluster = (dev.cluster == 2 && p.m_tiles >= 2) ? 2 : 1;
+  p.cg = cluster;
   int n_tiles = cdiv(d.N, MAX_BN);
-  // one N tile: any multiple of 16 (the TMA store clips at the tensor edge); several: whole 64-column sub-tiles
-  int bn = rup(cdiv(d.N, n_tiles), (n_tiles > 1 || d.b_major == MAJOR_MN) ? 64 : 16);
-  if (d.b_major == MAJOR_MN && n_tiles == 1) bn = rup(d.N, dev.mn_bn_align);
+  // bn: K-major B -- one N tile: any multiple of 16 (the TMA store clips at the tensor edge), several: whole 64-column
+  // sub-tiles; MN-major B -- whole 64-column TMA boxes per CTA (each CTA of a pair stages bn / 2 columns)
+  int bn;
+  if (d.b_major == MAJOR_MN) bn = rup(cdiv(d.N, n_tiles), (n_tiles > 1 ? 64 : dev.mn_bn_align) * cluster);
+  else bn = rup(cdiv(d.N, n_tiles), n_tiles > 1 ? 64 : 16);
   if (bn > MAX_BN) bn = MAX_BN;
   n_tiles = cdiv(d.N, bn);
   p.n_tiles = n_tiles;
@@ -135,6 +140,8 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
     if (s < d.nseg) {
       p.kb[s] = cdiv(d.K[s], BK);
       p.klen[s] = d.K[s];
+      p.a_c0[s] = 0;
+      p.a_r0[s] = 0;
       p.a_dyn[s] = d.A[s].dyn;
       p.b_k0[s] = d.b_k0[s];
       CKR(encode_map(&p.tmA[s], d.A[s], 64, d.a_major == MAJOR_K ? BM : BK));
@@ -143,8 +150,6 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   if (d.nseg == 1) p.tmA[1] = p.tmA[0];
   p.b_n0 = d.b_n0;
   p.b_dyn = d.B.dyn;
-  const int cluster = (dev.cluster == 2 && p.m_tiles >= 2) ? 2 : 1;
-  p.cluster = cluster;
   CKR(encode_map(&p.tmB, d.B, 64, d.b_major == MAJOR_K ? bn / cluster : BK));
   const int kb_total = p.kb[0] + p.kb[1];
   const int iters = kb_total * d.passes;
@@ -176,16 +181,16 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
                    (!has_aux || (e.aux != nullptr && e.aux_planes == 1 && (reinterpret_cast<uintptr_t>(e.aux) & 15) == 0));
   if (tma) {
     View o; o.base = e.out; o.ld = e.out_ld; o.ps = e.out_ps; o.planes = 1; o.width = d.N; o.rows = d.M;
-    CKR(encode_map(&p.tmOut, o, 64, 32));
+    CKR(encode_map(&p.tmOut, o, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));   // one epilogue warp's 32 x 32 chunk
     if (has_aux) {
       View a; a.base = e.aux; a.ld = e.aux_ld; a.ps = e.aux_ps; a.planes = 1; a.width = d.N; a.rows = e.aux_rows ? e.aux_rows : d.M;
-      CKR(encode_map(&p.tmAux, a, 64, 32));
+      CKR(encode_map(&p.tmAux, a, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     }
   }
   const int units = cdiv(p.m_tiles, cluster) * n_tiles * splits;       // units per CTA (pair)
   const int slots = dev.sms / cluster;
   const int grid = (units < slots ? units : slots) * cluster;
-  GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act, tma);
+  GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act, tma, cluster);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid, 1, 1);
@@ -219,7 +224,7 @@ struct Net {
   int64_t wsh_ps[PVAE_MAX_LAYERS];
   __nv_bfloat16* act[PVAE_MAX_LAYERS];
   __nv_bfloat16* g[PVAE_MAX_LAYERS];
-  uint32_t* mask[PVAE_MAX_LAYERS];   // ReLU sign bits of act[l], [max_batch][mask_ld[l]]
+  uint32_t* mask[PVAE_MAX_LAYERS];   // ReLU sign bits of act[l], [mask_ld[l] words of 32 columns][max_batch]
   int act_ld[PVAE_MAX_LAYERS];
   int mask_ld[PVAE_MAX_LAYERS];
   bool bound = false;
@@ -357,7 +362,7 @@ static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, con
     if (l < net.n_layers - 1) {
       d.epi.type = EPI_STORE; d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
       set_out(d.epi, h, net.act[l], net.act_ld[l]);
-      d.epi.mask = net.mask[l]; d.epi.mask_ld = net.mask_ld[l];
+      d.epi.mask = net.mask[l]; d.epi.mask_ld = h->max_batch;
     } else {
       d.epi = last;
       d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
@@ -409,7 +414,7 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
       d.epi.type = EPI_DGRAD; d.epi.act = net.acts[l - 1];
       const View al = ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
       if (net.acts[l - 1] != ACT_LINEAR) set_aux(d.epi, al, 0);
-      d.epi.mask = net.mask[l - 1]; d.epi.mask_ld = net.mask_ld[l - 1];
+      d.epi.mask = net.mask[l - 1]; d.epi.mask_ld = h->max_batch;
       set_out(d.epi, h, net.g[l - 1], net.act_ld[l - 1]);
       d.epi.colsum = train ? net.grad + net.gb[l - 1] : nullptr;
       CKR(launch_gemm(h->dev, d, st));
@@ -460,7 +465,8 @@ static int ensure_kernel_attr(Device& dev) {
   for (int epi = 0; epi < 4; ++epi)
     for (int act = 0; act <= ACT_SWISH; ++act)
       for (int tma = 0; tma < 2; ++tma)
-        CK(cudaFuncSetAttribute(select_kernel(epi, act, tma != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        for (int cg = 1; cg <= 2; ++cg)
+          CK(cudaFuncSetAttribute(select_kernel(epi, act, tma != 0, cg), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   dev.attr_set = true;
   return PVAE_OK;
 }

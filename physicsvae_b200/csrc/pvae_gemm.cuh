@@ -2,8 +2,10 @@
 //
 // A persistent, warp-specialised sm_100a GEMM:  D[M,N] = epilogue( A[M,K] . B[N,K]^T )
 //   * operands arrive in shared memory by TMA (cp.async.bulk.tensor, 128B swizzle),
-//   * products are issued by one thread as tcgen05.mma (cta_group::1, 128 x bn x 16, bf16 -> fp32),
-//   * accumulators live in TMEM (2 stages x 256 columns) and are drained by four epilogue warps
+//   * products are issued by one thread as tcgen05.mma: CG = 2 (the normal case) pairs two CTAs of a cluster on a
+//     256 x bn x 16 instruction (cta_group::2) -- each CTA stages its own 128 rows of A and HALF of the B tile, the
+//     leader CTA issues for both; CG = 1 (single M tile) is the plain 128 x bn x 16 form,
+//   * accumulators live in TMEM (2 stages x 256 columns) and are drained by eight epilogue warps
 //     with tcgen05.ld while the next tile's main loop runs.
 // Everything a Linear layer of the reference needs is expressed by parameters of this kernel:
 //   forward   y = act(x W^T + b)            A = x  (K-major)   B = W shadow (K-major)
@@ -26,20 +28,26 @@ namespace pvae {
 constexpr int BM = 128;                       // tile rows  (UMMA M)
 constexpr int BK = 64;                        // k elements per pipeline stage (= one 128B swizzle span)
 constexpr int MAX_BN = 256;                   // tile cols  (UMMA N), runtime value bn <= 256, multiple of 16
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KiB
-constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;    // 32 KiB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+// Pipeline geometry per MMA mode: CG = 2 stages half a B tile per CTA (32 KiB slots, 6 deep), CG = 1 a whole one (48 KiB, 4 deep).
+template <int CG> struct Geo {
+  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int B_STAGE_BYTES = MAX_BN * BK * 2 / CG;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+};
+constexpr int MAX_STAGES = 8;
+constexpr int PIPE_BYTES = 196608;                // 6 x 32 KiB = 4 x 48 KiB
+static_assert(Geo<1>::STAGES * Geo<1>::STAGE_BYTES == PIPE_BYTES && Geo<2>::STAGES * Geo<2>::STAGE_BYTES == PIPE_BYTES, "pipeline size");
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_WARPS = 8;                  // two warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int EPI_WARPS = 16;                 // four warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warps 0..3: TMA / MMA / TMEM-alloc / idle, warps 4..11: epilogue
-constexpr int SLAB_BYTES = 32 * 128;          // per-epilogue-warp staging slab: 32 rows x 64 bf16 (TMA store / aux load box)
-constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
+constexpr int SLAB_BYTES = 32 * 64;           // per-epilogue-warp staging slab: 32 rows x 32 bf16 (TMA store / aux load box, 64B swizzle)
+constexpr int OFF_STAGING = PIPE_BYTES;
 constexpr int OFF_BARS = OFF_STAGING + EPI_WARPS * SLAB_BYTES;
-constexpr int OFF_BIAS = OFF_BARS + 256;
+constexpr int OFF_BIAS = OFF_BARS + 512;
 constexpr int BIAS_BYTES = EPI_WARPS * 32 * 4;      // per-epilogue-warp bias slice of the current 32 columns
-constexpr int SMEM_BYTES = OFF_BIAS + BIAS_BYTES + 1024 /*alignment slack*/;
+constexpr int SMEM_BYTES = OFF_BIAS + BIAS_BYTES + 512 /*alignment slack: the dynamic window starts 1 KiB aligned in practice; checked*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB of shared memory a CTA may use");
 
 enum : int { EPI_STORE = 0, EPI_MSE = 1, EPI_DGRAD = 2, EPI_WGRAD = 3 };
@@ -64,8 +72,8 @@ struct EpiParams {
   float scale;                     // EPI_MSE: d = scale * (pred - target)
   int32_t f32_atomic;              // EPI_WGRAD: 1 = red.global.add, 0 = plain store
   float* colsum;                   // [n_valid] fp32, atomically accumulated column sums of the primary output (bias grad)
-  uint32_t* mask;                  // ReLU sign bits [rows][mask_ld] (1 bit per output): written by EPI_STORE, read by EPI_DGRAD
-  int64_t mask_ld;                 // in 32-bit words, even
+  uint32_t* mask;                  // ReLU sign bits [32-column word][mask_ld rows] (1 bit per output): written by EPI_STORE, read by EPI_DGRAD
+  int64_t mask_ld;                 // rows per 32-column word plane (the workspace batch capacity)
   double* loss;                    // EPI_MSE: sum of squared errors accumulated here
 };
 
@@ -83,7 +91,7 @@ struct GemmParams {
   int32_t b_dyn;                   // B: add *row_cursor to the k row coordinate (MN-major)
   int32_t passes;                  // 1 = bf16, 3 = bf16x3
   int32_t m_tiles, n_tiles, bn, splits;
-  int32_t cluster;                 // 1, or 2: CTA pairs on adjacent M tiles share the B tile (each loads half, TMA multicast)
+  int32_t cg;                      // 1, or 2: CTA pairs on adjacent M tiles run one 256-row tcgen05.mma.cta_group::2 (kernel template CG)
   const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
   CUtensorMap tmOut;               // TMA-store epilogue: the primary bf16 output, box 64 cols x 32 rows (one warp's slab)
   CUtensorMap tmAux;               // TMA-store epilogue: the aux input (same box)
@@ -113,12 +121,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
-  printf("pvae_gemm: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-  __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.  The spinning part lives out of
+// line so that the pipeline loops (one iteration per 64-wide k-block) stay a few dozen instructions long.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -126,9 +131,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       uint64_t t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000ull) mbar_timeout(bar, parity);   // 4 s
+      else if (t - t0 > 4000000000ull) {   // 4 s
+        printf("pvae_gemm: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -138,17 +149,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// Tile load.  CG = 2: the copy may signal an mbarrier of the peer CTA (`bar` is then a shared::cluster address of the
+// leader's barrier, obtained with mapa) -- both CTAs of a pair report their bytes to the leader's "full" barrier.
+template <int CG>
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
-      : "memory");
+  if (CG == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
 // One lane of a converged warp (warp-uniform control flow around it keeps TMA / MMA operands in uniform registers).
 __device__ __forceinline__ bool elect_one() {
@@ -165,33 +179,65 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+// TMEM allocation: CG = 2 is a collective of the same warp of both CTAs of the pair.
+template <int CG> __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  if (CG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+template <int CG> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+// D[tmem] (+)= A[smem] . B[smem]; descriptors are passed as their low words (start address | LBO) plus the shared high word.
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(cta_mask) : "memory");
+// "all MMAs issued so far by this thread have completed" -> mbarrier arrive.  CG = 2: delivered to the barrier at the same
+// offset in both CTAs of the pair.
+template <int CG> __device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (CG == 2)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -206,19 +252,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1, 128B swizzle).
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1, 128B swizzle), split into the
+// low word (start address >> 4 | LBO << 16) and the high word (SBO | version | swizzle), which is the same for all operands.
 //   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1).
 //   MN-major: 64-element (128 B) MN atoms x 8 k-rows; next 8 k-rows 1024 B on (SBO);
 //             next MN atom one whole TMA box on = 64 k-rows * 128 B = 8192 B (LBO).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int major) {
-  const uint64_t lbo = (major == MAJOR_K) ? 1ull : (8192ull >> 4);
-  const uint64_t sbo = 1024ull >> 4;
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+constexpr uint32_t UMMA_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, int major) {
+  const uint32_t lbo = (major == MAJOR_K) ? 1u : (8192u >> 4);
+  return ((saddr & 0x3FFFFu) >> 4) | (lbo << 16);
 }
-// tcgen05 instruction descriptor, kind::f16, A/B = bf16, D = fp32, M = 128.
-__device__ __forceinline__ uint32_t umma_idesc(int n, int a_major, int b_major) {
+// tcgen05 instruction descriptor, kind::f16, A/B = bf16, D = fp32, M = 128 per CTA (256 for a CTA pair).
+template <int CG> __device__ __forceinline__ uint32_t umma_idesc(int n, int a_major, int b_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -247,6 +294,12 @@ template <int act> __device__ __forceinline__ float act_bwd_from_out(float y) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// relu fused into the conversion (negative -> +0)
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 __device__ __forceinline__ float bf16_lo_part(float v) {  // v - bf16(v)
   return v - __bfloat162float(__float2bfloat16_rn(v));
@@ -437,22 +490,20 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float (&v)[32
   }
 }
 
-// position inside the (pass, segment, k-block) iteration space of one output tile
-struct KIter {
-  int pass, seg, r;
-  __device__ __forceinline__ void init(int it, int kb0, int kb_total) {
+// A run of consecutive k-blocks of one output tile that stay inside one (precision pass, K segment): the unit of the
+// pipeline loops' outer level, so that their inner level is a plain counted loop with constant coordinate increments.
+struct KRun {
+  int pass, seg, r0, n;        // r0: first k-block inside the segment; n: k-blocks in the run
+  bool ends_seg;               // the run contains the segment's last (possibly ragged) k-block
+  __device__ __forceinline__ void init(int it, int it_end, int kb0, int kb1) {
+    const int kb_total = kb0 + kb1;
     pass = it / kb_total;
     const int rem = it - pass * kb_total;
     seg = rem >= kb0 ? 1 : 0;
-    r = seg ? rem - kb0 : rem;
-  }
-  __device__ __forceinline__ void next(int kb0, int kb1) {
-    ++r;
-    if (r == (seg ? kb1 : kb0)) {
-      r = 0;
-      if (seg == 0 && kb1 > 0) seg = 1;
-      else { seg = 0; ++pass; }
-    }
+    r0 = seg ? rem - kb0 : rem;
+    const int left = (seg ? kb1 : kb0) - r0;
+    n = left < it_end - it ? left : it_end - it;
+    ends_seg = (n == left);
   }
 };
 
@@ -462,17 +513,25 @@ struct KIter {
 // TMAEPI: the primary bf16 output (one precision plane) leaves through shared memory and cp.async.bulk.tensor stores, the
 // aux operand (forward activation for act', MSE target) arrives the same way; the epilogue warps then touch only TMEM,
 // shared memory and registers.  Without it (bf16x3 planes, fp32-only outputs) rows are read / written directly.
-template <int EPI, int ACT, bool TMAEPI>
+// CG: CTAs per MMA instruction (see the top of the file); the launch uses clusters of CG CTAs.
+template <int EPI, int ACT, bool TMAEPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int STAGES = Geo<CG>::STAGES;
+  constexpr int STAGE_BYTES = Geo<CG>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle atoms need 1024 B alignment
+  if (smem_base - smem_u32(smem_raw) > 512u) {                        // the carve-out assumes at most 512 B of alignment slack
+    if (threadIdx.x == 0) printf("pvae_gemm: dynamic shared memory base 0x%x leaves too little room after 1 KiB alignment\n", smem_u32(smem_raw));
+    __trap();
+  }
   const uint32_t bar_base = smem_base + OFF_BARS;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
-  auto auxfull_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + w); };   // one per epilogue warp
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + EPI_WARPS);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + ACC_STAGES + s); };
+  auto auxfull_bar = [&](int w) { return bar_base + 8u * (2 * MAX_STAGES + 2 * ACC_STAGES + w); };   // one per epilogue warp
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 2 * ACC_STAGES + EPI_WARPS);
+  static_assert(8 * (2 * MAX_STAGES + 2 * ACC_STAGES + EPI_WARPS + 1) <= 512, "barrier block");
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));    // generic pointer to the aligned base
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
   float* bias_all = reinterpret_cast<float*>(smem_gen + OFF_BIAS);
@@ -491,19 +550,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     if (HAS_AUX) tma_prefetch_desc(&p.tmAux);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.cluster); }
-    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
+    // full: one arrive.expect_tx by the (leader's) producer + the bytes of both CTAs; empty / tfull: one tcgen05.commit
+    // (delivered to both CTAs for CG = 2); tempty (used in the leader only): every epilogue warp of the pair.
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG * EPI_WARPS); }
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(auxfull_bar(w), 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();        // the peer's barriers are initialised before anything arrives on them
+  if (CG > 1) cluster_sync_all();               // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int csize = p.cluster;
-  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+  constexpr int csize = CG;
+  const int crank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int unit0 = blockIdx.x / csize, unit_stride = gridDim.x / csize;
 
   const int row0 = p.row_cursor ? *p.row_cursor : 0;
@@ -516,117 +577,127 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    // The whole warp walks the loop (warp-uniform control flow); one elected lane issues the copies.
-    const int b_boxes = (bn + 63) >> 6;
-    const uint32_t stage_tx = A_STAGE_BYTES + (p.b_major == MAJOR_K ? (uint32_t)bn * (BK * 2) : (uint32_t)b_boxes * 8192u);
-    const int a_major = p.a_major, b_major = p.b_major;
-    const int hrows = bn >> 1;
+    // The whole warp walks the loops (warp-uniform control flow); one elected lane issues the copies.  Each CTA stages
+    // its own 128 rows of A and its 1/CG share of the B tile; for CG = 2 both CTAs' bytes are reported to the leader's
+    // "full" barrier, whose single arrival (with the byte count of the pair) comes from the leader's producer.
+    const bool a_mn = p.a_major == MAJOR_MN, b_mn = p.b_major == MAJOR_MN;
+    const int bn_loc = bn / CG;                           // B rows (n) staged by this CTA
+    const int b_boxes = b_mn ? (bn_loc + 63) >> 6 : 1;
+    const uint32_t stage_tx = (uint32_t)CG * (A_STAGE_BYTES + (b_mn ? (uint32_t)b_boxes * 8192u : (uint32_t)bn_loc * (BK * 2)));
+    const bool leader = (CG == 1) || crank == 0;
+    const uint32_t full0 = (CG == 2) ? mapa_u32(full_bar(0), 0u) : full_bar(0);
     int stage = 0; uint32_t phase = 0;
     for (int u = unit0; u < total_units; u += unit_stride) {
       const int split = u / tile_units;
       const int tile = u - split * tile_units;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = (tile / p.n_tiles) * csize + crank;
-      const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
       const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
-      KIter ki; ki.init(it_begin, p.kb[0], kb_total);
-      for (int it = it_begin; it < it_end; ++it, ki.next(p.kb[0], p.kb[1])) {
-        const int pass = ki.pass, seg = ki.seg, r = ki.r;
-        const int a_plane = (pass == 2) ? 1 : 0;
-        const int b_plane = (pass == 1) ? 1 : 0;
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        const uint32_t sb = sa + A_STAGE_BYTES;
-        const uint32_t fb = full_bar(stage);
-        const int a_row = p.a_r0[seg] + (p.a_dyn[seg] ? row0 : 0);
-        const int b_k = p.b_k0[seg] + r * BK;
-        const int b_n = p.b_n0 + n_tile * bn;
+      int it = (int)(((int64_t)iters_total * split) / p.splits);
+      const int b_n = p.b_n0 + n_tile * bn + crank * bn_loc;
+      while (it < it_end) {
+        KRun run; run.init(it, it_end, p.kb[0], p.kb[1]);
+        it += run.n;
+        const int seg = run.seg;
+        const int a_plane = (run.pass == 2) ? 1 : 0;
+        const int b_plane = (run.pass == 1) ? 1 : 0;
         const CUtensorMap* tmA = &p.tmA[seg];
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (elect_one()) {
-          mbar_expect_tx(fb, stage_tx);
-          if (a_major == MAJOR_K) {
-            tma_load_3d(sa, tmA, fb, p.a_c0[seg] + r * BK, a_row + m_tile * BM, a_plane);
-          } else {
-            tma_load_3d(sa,         tmA, fb, p.a_c0[seg] + m_tile * BM,      a_row + r * BK, a_plane);
-            tma_load_3d(sa + 8192u, tmA, fb, p.a_c0[seg] + m_tile * BM + 64, a_row + r * BK, a_plane);
+        const int a_row = p.a_r0[seg] + (p.a_dyn[seg] ? row0 : 0);
+        // coordinates of the run's first k-block; a k-block further on moves the K coordinate by BK
+        int ac0 = a_mn ? p.a_c0[seg] + m_tile * BM : p.a_c0[seg] + run.r0 * BK;
+        int ac1 = a_mn ? a_row + run.r0 * BK : a_row + m_tile * BM;
+        int bc0 = b_mn ? b_n : p.b_k0[seg] + run.r0 * BK;
+        int bc1 = b_mn ? p.b_k0[seg] + run.r0 * BK + (p.b_dyn ? row0 : 0) : b_n;
+        for (int j = 0; j < run.n; ++j) {
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(full_bar(stage), stage_tx);
+            const uint32_t fb = full0 + 8u * stage;
+            tma_load_3d<CG>(sa, tmA, fb, ac0, ac1, a_plane);
+            if (a_mn) tma_load_3d<CG>(sa + 8192u, tmA, fb, ac0 + 64, ac1, a_plane);
+            tma_load_3d<CG>(sb, &p.tmB, fb, bc0, bc1, b_plane);
+            for (int x = 1; x < b_boxes; ++x) tma_load_3d<CG>(sb + 8192u * x, &p.tmB, fb, bc0 + 64 * x, bc1, b_plane);
           }
-          if (csize == 1) {
-            if (b_major == MAJOR_K) {
-              tma_load_3d(sb, &p.tmB, fb, b_k, b_n, b_plane);
-            } else {
-              const int b_row = b_k + (p.b_dyn ? row0 : 0);
-              for (int j = 0; j < b_boxes; ++j) tma_load_3d(sb + 8192u * j, &p.tmB, fb, b_n + 64 * j, b_row, b_plane);
-            }
-          } else {
-            // CTA pair: this CTA fetches its half of the B tile and multicasts it into both CTAs' shared memory
-            if (b_major == MAJOR_K) {           // K-major: rows [crank * bn/2, +bn/2) of the tile (box rows = bn/2)
-              tma_load_3d_mc(sb + (uint32_t)(crank * hrows) * 128u, &p.tmB, fb, b_k, b_n + crank * hrows, b_plane, (uint16_t)3);
-            } else {
-              const int b_row = b_k + (p.b_dyn ? row0 : 0);
-              for (int j = crank; j < b_boxes; j += 2)
-                tma_load_3d_mc(sb + 8192u * j, &p.tmB, fb, b_n + 64 * j, b_row, b_plane, (uint16_t)3);
-            }
-          }
+          __syncwarp();
+          if (a_mn) ac1 += BK; else ac0 += BK;
+          if (b_mn) bc1 += BK; else bc0 += BK;
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    const uint32_t idesc = umma_idesc(bn, p.a_major, p.b_major);
-    const uint32_t a_kstep = (p.a_major == MAJOR_K) ? 2u : 128u;   // 16 k elements, in 16 B units: 32 B or 16 rows * 128 B
-    const uint32_t b_kstep = (p.b_major == MAJOR_K) ? 2u : 128u;
-    const uint64_t adesc0 = umma_desc(smem_base, p.a_major);
-    const uint64_t bdesc0 = umma_desc(smem_base + A_STAGE_BYTES, p.b_major);
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int u = unit0; u < total_units; u += unit_stride) {
-      const int split = u / tile_units;
-      const int it_begin = (int)(((int64_t)iters_total * split) / p.splits);
-      const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
-      KIter ki; ki.init(it_begin, p.kb[0], kb_total);
-      uint32_t accum = 0u;
-      for (int it = it_begin; it < it_end; ++it, ki.next(p.kb[0], p.kb[1])) {
-        int k16 = (p.klen[ki.seg] - ki.r * BK + 15) >> 4;
-        k16 = k16 > 4 ? 4 : (k16 < 1 ? 1 : k16);
-        const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(stage * STAGE_BYTES) >> 4);
-        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)(stage * STAGE_BYTES) >> 4);
-        const uint32_t eb = empty_bar(stage);
+    // ================================ MMA issuer (leader CTA of the pair only) ================================
+    if (CG == 1 || crank == 0) {
+      const uint32_t idesc = umma_idesc<CG>(bn, p.a_major, p.b_major);
+      const uint32_t a_kstep = (p.a_major == MAJOR_K) ? 2u : 128u;   // 16 k elements, in 16 B units: 32 B or 16 rows * 128 B
+      const uint32_t b_kstep = (p.b_major == MAJOR_K) ? 2u : 128u;
+      const uint32_t a_lo0 = umma_desc_lo(smem_base, p.a_major);
+      const uint32_t b_lo0 = umma_desc_lo(smem_base + A_STAGE_BYTES, p.b_major);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      // one k-block: wait for its operands, issue k16 (1..4) instructions of K = 16, free the slot when they have read it
+      auto kblock = [&](uint32_t tmem_d, uint32_t accum, int k16) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
-          umma_bf16(tmem_d, adesc, bdesc, idesc, accum);
-          if (k16 > 1) umma_bf16(tmem_d, adesc + (uint64_t)a_kstep, bdesc + (uint64_t)b_kstep, idesc, 1u);
-          if (k16 > 2) umma_bf16(tmem_d, adesc + (uint64_t)(2 * a_kstep), bdesc + (uint64_t)(2 * b_kstep), idesc, 1u);
-          if (k16 > 3) umma_bf16(tmem_d, adesc + (uint64_t)(3 * a_kstep), bdesc + (uint64_t)(3 * b_kstep), idesc, 1u);
-          if (csize == 1) umma_commit(eb);                 // frees the smem slot once these MMAs have read it
-          else umma_commit_mc(eb, (uint16_t)3);            // ... in both CTAs of the pair (both producers write both)
+          const uint32_t so = (uint32_t)(stage * STAGE_BYTES) >> 4;
+          const uint32_t a = a_lo0 + so, b = b_lo0 + so;
+          umma_bf16<CG>(tmem_d, a, b, UMMA_DESC_HI, idesc, accum);
+          if (k16 > 1) umma_bf16<CG>(tmem_d, a + a_kstep, b + b_kstep, UMMA_DESC_HI, idesc, 1u);
+          if (k16 > 2) umma_bf16<CG>(tmem_d, a + 2 * a_kstep, b + 2 * b_kstep, UMMA_DESC_HI, idesc, 1u);
+          if (k16 > 3) umma_bf16<CG>(tmem_d, a + 3 * a_kstep, b + 3 * b_kstep, UMMA_DESC_HI, idesc, 1u);
+          umma_commit<CG>(empty_bar(stage));
         }
         __syncwarp();
-        accum = 1u;
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      };
+      for (int u = unit0; u < total_units; u += unit_stride) {
+        const int split = u / tile_units;
+        const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
+        int it = (int)(((int64_t)iters_total * split) / p.splits);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // every epilogue warp (of both CTAs) has drained this stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
+        uint32_t accum = 0u;
+        while (it < it_end) {
+          KRun run; run.init(it, it_end, p.kb[0], p.kb[1]);
+          it += run.n;
+          // all-zero k16 slices at the ragged end of a segment are skipped
+          int tail = 4;
+          if (run.ends_seg) {
+            tail = (p.klen[run.seg] - (p.kb[run.seg] - 1) * BK + 15) >> 4;
+            tail = tail > 4 ? 4 : (tail < 1 ? 1 : tail);
+          }
+          const int n_full = tail < 4 ? run.n - 1 : run.n;
+          for (int j = 0; j < n_full; ++j) { kblock(tmem_d, accum, 4); accum = 1u; }
+          if (tail < 4) { kblock(tmem_d, accum, tail); accum = 1u; }
+        }
+        if (elect_one()) umma_commit<CG>(tfull_bar(acc));    // accumulator complete -> epilogue (of both CTAs)
+        __syncwarp();
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
-      if (elect_one()) umma_commit(tfull_bar(acc));        // accumulator complete -> epilogue
-      __syncwarp();
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue ================================
+    // ================================ epilogue (16 warps) ================================
+    // Warp w owns the 32 rows of TMEM lane quarter w % 4 and the 32-column chunks c = (w - 4) / 4 + 4 j of the tile: four
+    // warps per scheduler hide each other's TMEM / shared-memory / fence latencies.
     const EpiParams& e = p.epi;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id % 4)
-    const int half = (warp - 4) >> 2;             // which 32-column half of a 64-column sub-tile / which chunk parity
+    const int cgrp = (warp - 4) >> 2;             // column group: chunks cgrp, cgrp + 4
     float* bias_s = bias_all + (warp - 4) * 32;
     const int m_valid = e.m_valid, n_valid = e.n_valid;
     const float* bias = (EPI == EPI_STORE || EPI == EPI_MSE) ? e.bias : nullptr;
     int acc = 0; uint32_t acc_phase = 0;
     double loss_local = 0.0;
     uint32_t aux_phase = 0;
+    const uint32_t tempty0 = (CG == 2) ? mapa_u32(tempty_bar(0), 0u) : tempty_bar(0);
     const uint32_t slab = smem_base + OFF_STAGING + (warp - 4) * SLAB_BYTES;      // this warp's private staging slab
     uint8_t* slab_gen = smem_gen + OFF_STAGING + (warp - 4) * SLAB_BYTES;
+    // 32 rows x 64 B, 64B swizzle: the 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
+    uint8_t* srow = slab_gen + lane * 64;
+    const int sw = (lane >> 1) & 3;
     for (int u = unit0; u < total_units; u += unit_stride) {
       const int tile = u % tile_units;
       const int n_tile = tile % p.n_tiles;
@@ -634,40 +705,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       const int row_in_tile = q * 32 + lane;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < m_valid;
-      // operands of this warp's (at most two) sub-tiles that do not depend on the accumulator: fetched while the main loop runs
-      float pre_bias[4] = {0.f, 0.f, 0.f, 0.f};
-      uint2 pre_mask[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+      // operands of this warp's (at most two) chunks that do not depend on the accumulator: fetched while the main loop runs
+      float pre_bias[2] = {0.f, 0.f};
+      uint32_t pre_mask[2] = {0u, 0u};
       if (TMAEPI) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int cs = n_tile * bn + (half + 2 * j) * 64;
-          if ((half + 2 * j) * 64 < bn && cs < n_valid) {
-            if (bias) {
-              pre_bias[2 * j] = (cs + lane < n_valid) ? __ldg(bias + cs + lane) : 0.f;
-              pre_bias[2 * j + 1] = (cs + lane + 32 < n_valid) ? __ldg(bias + cs + lane + 32) : 0.f;
-            }
-            if (USE_MASK && row_ok) pre_mask[j] = __ldg(reinterpret_cast<const uint2*>(e.mask + (int64_t)row * e.mask_ld + (cs >> 5)));
+          const int cs = n_tile * bn + (cgrp + 4 * j) * 32;
+          if ((cgrp + 4 * j) * 32 < bn && cs < n_valid) {
+            if (bias) pre_bias[j] = (cs + lane < n_valid) ? __ldg(bias + cs + lane) : 0.f;
+            if (USE_MASK && row_ok) pre_mask[j] = __ldg(e.mask + (int64_t)(cs >> 5) * e.mask_ld + row);
           }
         }
       }
       if (HAS_AUX) {
-        // fetch the aux slab of this warp's first sub-tile while the main loop of the tile is still running
-        const int col0s = n_tile * bn + half * 64;
-        if (col0s < n_valid && half * 64 < bn) {
+        // fetch the aux slab of this warp's first chunk while the main loop of the tile is still running
+        const int col0s = n_tile * bn + cgrp * 32;
+        if (col0s < n_valid && cgrp * 32 < bn) {
           tma_store_wait_read<0>();               // the slab's previous store has been read out (groups are per thread)
           __syncwarp();
           if (elect_one()) {
             mbar_expect_tx(auxfull_bar(warp - 4), SLAB_BYTES);
-            tma_load_3d(slab, &p.tmAux, auxfull_bar(warp - 4), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
+            tma_load_3d<1>(slab, &p.tmAux, auxfull_bar(warp - 4), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
           }
           __syncwarp();
         }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      const int nchunks = (bn + 31) >> 5;
       if (!TMAEPI) {
-        const int nchunks = (bn + 31) >> 5;
-        for (int c = half; c < nchunks; c += 2) {
+        for (int c = cgrp; c < nchunks; c += 4) {
           const int col0 = n_tile * bn + c * 32;
           if (col0 >= n_valid) break;             // warp-uniform
           int nv = n_valid - col0; nv = nv > 32 ? 32 : nv;
@@ -687,167 +755,161 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           epilogue_chunk<EPI, ACT>(e, v, bias_s, row, row_ok, col0, nv, row0, lane, loss_local);
         }
       } else {
-        // Each warp owns the 32 rows of its TMEM lane quarter and every other 64-column sub-tile; it stages its 32 x 64 bf16
-        // slab in private shared memory and stores it with one TMA instruction -- no cross-warp synchronisation.
-        const int nsub = (bn + 63) >> 6;
-        const int sw = lane & 7;
-        uint8_t* srow = slab_gen + lane * 128;
-        for (int s = half; s < nsub; s += 2) {
-          const int col0s = n_tile * bn + s * 64;
-          if (col0s >= n_valid) break;            // warp-uniform
-          int nv = n_valid - col0s; nv = nv > 64 ? 64 : nv;
-          const int tile_nv = bn - s * 64;        // columns of this sub-tile that belong to this tile
+        // Each warp stages its 32 x 32 bf16 chunk in a private 2 KiB slab and stores it with one TMA instruction -- no
+        // cross-warp synchronisation.
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          const int c = cgrp + 4 * j;
+          if (c >= nchunks) break;                // warp-uniform
+          const int col0 = n_tile * bn + c * 32;
+          if (col0 >= n_valid) break;             // warp-uniform
+          int nv = n_valid - col0; nv = nv > 32 ? 32 : nv;
+          const int tile_nv = bn - c * 32;        // columns of this chunk that belong to this tile
           if (tile_nv < nv) nv = tile_nv;
-          const int sj = (s - half) >> 1;         // 0 or 1: which of this warp's sub-tiles (bn <= 256)
-          const uint2 mbits = sj ? pre_mask[1] : pre_mask[0];
-          const float bias_lo = sj ? pre_bias[2] : pre_bias[0];   // lane -> bias of columns lane and lane + 32 of the sub-tile
-          const float bias_hi = sj ? pre_bias[3] : pre_bias[1];
-          if (HAS_AUX && s != half) {             // later sub-tiles of the tile: the aux load is exposed
+          const uint32_t mbits = j ? pre_mask[1] : pre_mask[0];
+          const float bias_l = j ? pre_bias[1] : pre_bias[0];     // lane -> bias of column lane of the chunk
+          if (HAS_AUX && j != 0) {                // second chunk of the tile: the aux load is exposed
             tma_store_wait_read<0>();
             __syncwarp();
             if (elect_one()) {
               mbar_expect_tx(auxfull_bar(warp - 4), SLAB_BYTES);
-              tma_load_3d(slab, &p.tmAux, auxfull_bar(warp - 4), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
+              tma_load_3d<1>(slab, &p.tmAux, auxfull_bar(warp - 4), col0, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
             }
             __syncwarp();
           }
-          uint32_t raw[64];
+          float v[32];
           {
-            uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[0]);
-            uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[32]);
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + s * 64);
-            tmem_ld32(taddr, r0);
-            tmem_ld32(taddr + 32, r1);
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + c * 32), raw);
             tmem_ld_wait();
-          }
-          float v[64];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(raw[i]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          }
           if (bias) {
+            __syncwarp();
+            bias_s[lane] = bias_l;
+            __syncwarp();
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-              __syncwarp();
-              bias_s[lane] = hb ? bias_hi : bias_lo;
-              __syncwarp();
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 b = *reinterpret_cast<const float4*>(bias_s + g * 4);
-                v[hb * 32 + g * 4 + 0] += b.x; v[hb * 32 + g * 4 + 1] += b.y; v[hb * 32 + g * 4 + 2] += b.z; v[hb * 32 + g * 4 + 3] += b.w;
-              }
+            for (int g = 0; g < 8; ++g) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + g * 4);
+              v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
             }
           }
+          uint32_t pk[16];                        // the chunk's row as packed bf16 pairs
           if (EPI == EPI_STORE) {
+            if (ACT != ACT_RELU || e.out_f32 != nullptr || nv < 32) {   // (warp-uniform) general path
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = act_fwd<ACT>(v[i]);
-            if (nv < 64) {                        // ragged last sub-tile: keep the padding columns of the mask / slab zero
+              for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
+              if (nv < 32) {                      // ragged last chunk: keep the padding columns of the mask / slab zero
 #pragma unroll
-              for (int i = 0; i < 64; ++i) v[i] = (i < nv) ? v[i] : 0.f;
-            }
-            if (row_ok) {
-              if (e.out_f32) store_f32_row64(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn, e.f32_sn, nv, v);
-              if (ACT == ACT_RELU && e.mask) {
-                uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { m0 |= (v[i] > 0.f ? 1u : 0u) << i; m1 |= (v[32 + i] > 0.f ? 1u : 0u) << i; }
-                *reinterpret_cast<uint2*>(e.mask + (int64_t)row * e.mask_ld + (col0s >> 5)) = make_uint2(m0, m1);
+                for (int i = 0; i < 32; ++i) v[i] = (i < nv) ? v[i] : 0.f;
               }
+              if (row_ok && e.out_f32) store_f32_row32(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn, e.f32_sn, nv, v);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = (ACT == ACT_RELU) ? pack_bf16x2_relu(v[2 * i], v[2 * i + 1]) : pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            if (ACT == ACT_RELU && e.mask && row_ok) {
+              // sign-bit mask from the packed non-negative results: a half is > 0 iff adding 0x7fff carries into its bit 15.
+              // Word layout: bit i = column 2 i, bit 16 + i = column 2 i + 1 (private to this kernel's dgrad epilogue).
+              uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                m0 |= ((pk[i] + 0x7FFF7FFFu) & 0x80008000u) >> (15 - i);
+                m1 |= ((pk[i + 1] + 0x7FFF7FFFu) & 0x80008000u) >> (14 - i);
+              }
+              e.mask[(int64_t)(col0 >> 5) * e.mask_ld + row] = m0 | m1;
             }
           } else {
-            float y[64];
+            // aux values (MSE target / forward activation) are consumed piece by piece to keep the register footprint small
+            auto aux_piece = [&](int g, float (&y)[8]) {
+              const uint4 qv = *reinterpret_cast<const uint4*>(srow + ((g ^ sw) << 4));
+              const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                y[2 * t]     = __uint_as_float(w[t] << 16);
+                y[2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u);
+              }
+            };
             if (HAS_AUX) {
               mbar_wait(auxfull_bar(warp - 4), aux_phase);
               aux_phase ^= 1u;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4 qv = *reinterpret_cast<const uint4*>(srow + ((j ^ sw) << 4));
-                const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  y[j * 8 + 2 * t]     = __uint_as_float(w[t] << 16);
-                  y[j * 8 + 2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u);
-                }
-              }
-              __syncwarp();                       // every lane has read the aux slab before it is overwritten below
             }
             if (EPI == EPI_MSE) {
               if (row_ok) {
-                if (e.out_f32) store_f32_row64(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn, e.f32_sn, nv, v);
-                if (e.out2) {
-                  float (&v0)[32] = *reinterpret_cast<float (*)[32]>(&v[0]);
-                  float (&v1)[32] = *reinterpret_cast<float (*)[32]>(&v[32]);
-                  store_row32(e.out2 + (int64_t)row * e.out2_ld + col0s, e.out2_ps, e.out2_planes, nv > 32 ? 32 : nv, v0);
-                  if (nv > 32) store_row32(e.out2 + (int64_t)row * e.out2_ld + col0s + 32, e.out2_ps, e.out2_planes, nv - 32, v1);
-                }
+                if (e.out_f32) store_f32_row32(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn, e.f32_sn, nv, v);
+                if (e.out2) store_row32(e.out2 + (int64_t)row * e.out2_ld + col0, e.out2_ps, e.out2_planes, nv, v);
               }
               float sq = 0.f;
               const float scale = e.scale;
 #pragma unroll
-              for (int i = 0; i < 64; ++i) {
-                const float di = (row_ok && i < nv) ? (v[i] - y[i]) : 0.f;
-                sq += di * di;
-                v[i] = scale * di;
+              for (int g = 0; g < 4; ++g) {
+                float y[8];
+                aux_piece(g, y);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  const int i = g * 8 + t;
+                  const float di = (row_ok && i < nv) ? (v[i] - y[t]) : 0.f;
+                  sq += di * di;
+                  v[i] = scale * di;
+                }
               }
               loss_local += (double)sq;
             } else {  // EPI_DGRAD
               if (e.add && row_ok) {
                 float a[32];
-                load_row32(e.add + (int64_t)row * e.add_ld + col0s, e.add_ps, e.add_planes, nv > 32 ? 32 : nv, a);
+                load_row32(e.add + (int64_t)row * e.add_ld + col0, e.add_ps, e.add_planes, nv, a);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += a[i];
-                if (nv > 32) {
-                  load_row32(e.add + (int64_t)row * e.add_ld + col0s + 32, e.add_ps, e.add_planes, nv - 32, a);
+              }
+              if (USE_MASK) {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) v[32 + i] += a[i];
+                for (int i = 0; i < 32; ++i) v[i] = ((mbits >> ((i >> 1) + 16 * (i & 1))) & 1u) ? v[i] : 0.f;   // mask is 0 for rows >= m_valid
+              } else if (ACT != ACT_LINEAR) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  float y[8];
+                  aux_piece(g, y);
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) v[g * 8 + t] *= act_bwd_from_out<ACT>(y[t]);
                 }
               }
+              if (nv < 32 || (!USE_MASK && !row_ok)) {   // keep what the bias-gradient column sums must not see at zero
 #pragma unroll
-              for (int i = 0; i < 64; ++i) {
-                float g = v[i];
-                if (USE_MASK) g = ((i < 32 ? mbits.x >> i : mbits.y >> (i - 32)) & 1u) ? g : 0.f;   // mask is 0 for rows >= m_valid
-                else if (ACT != ACT_LINEAR) g *= act_bwd_from_out<ACT>(y[i]);
-                v[i] = g;
+                for (int i = 0; i < 32; ++i) v[i] = (row_ok && i < nv) ? v[i] : 0.f;
               }
-              if (nv < 64 || (!USE_MASK && !row_ok)) {   // keep what the bias-gradient column sums must not see at zero
-#pragma unroll
-                for (int i = 0; i < 64; ++i) v[i] = (row_ok && i < nv) ? v[i] : 0.f;
-              }
-              if (row_ok && e.out_f32) store_f32_row64(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0s * e.f32_sn, e.f32_sn, nv, v);
+              if (row_ok && e.out_f32) store_f32_row32(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn, e.f32_sn, nv, v);
             }
+            if (HAS_AUX) __syncwarp();            // every lane has read the aux slab before it is overwritten below
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
           }
           if (!HAS_AUX) {                         // (with aux the slab was already claimed before the aux load)
             tma_store_wait_read<0>();             // bulk groups are per thread: only the electing lane ever has pending ones
             __syncwarp();
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 qv;
-            qv.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); qv.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-            qv.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); qv.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-            *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = qv;
-          }
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(srow + ((g ^ sw) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           fence_proxy_async();                    // generic-proxy writes -> visible to the TMA store
           __syncwarp();
           if (m_tile * BM + q * 32 < m_valid) {   // warp-uniform
             if (elect_one()) {
-              tma_store_3d(&p.tmOut, slab, col0s, m_tile * BM + q * 32, 0);
+              tma_store_3d(&p.tmOut, slab, col0, m_tile * BM + q * 32, 0);
               tma_store_commit();
             }
             __syncwarp();
           }
           if (EPI != EPI_STORE && e.colsum) {
-            // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> columns lane, lane + 32
-#pragma unroll
-            for (int hcol = 0; hcol < 2; ++hcol) {
-              const int col = lane + 32 * hcol;
-              if (col < nv) {
-                float sum = 0.f;
+            // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> column lane
+            if (lane < nv) {
+              float sum = 0.f;
+              const int piece = lane >> 3, within = (lane & 7) << 1;
 #pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                  const unsigned short hv = *reinterpret_cast<const unsigned short*>(slab_gen + r * 128 + ((((col >> 3) ^ (r & 7)) << 4) | ((col & 7) << 1)));
-                  sum += __uint_as_float((uint32_t)hv << 16);
-                }
-                atomicAdd(e.colsum + col0s + col, sum);
+              for (int r = 0; r < 32; ++r) {
+                const unsigned short hv = *reinterpret_cast<const unsigned short*>(slab_gen + r * 64 + (((piece ^ ((r >> 1) & 3)) << 4) | within));
+                sum += __uint_as_float((uint32_t)hv << 16);
               }
+              atomicAdd(e.colsum + col0 + lane, sum);
             }
             __syncwarp();
           }
@@ -855,7 +917,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {                            // the accumulator stage may be overwritten: tell the (leader's) MMA warp
+        if (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
     if (TMAEPI) tma_store_wait_read<0>();
@@ -868,31 +933,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();            // no CTA leaves while its peer may still multicast into it / signal its barriers
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (CG > 1) cluster_sync_all();               // no CTA leaves while its peer may still write its TMEM / signal its barriers
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<CG>(tmem_base, TMEM_COLS); }
 }
 
 typedef void (*GemmKernelFn)(const GemmParams);
-// host-side dispatch table: [epilogue type][activation][tma epilogue]
-template <int EPI, bool T> struct KernelRow {
+// host-side dispatch table: [epilogue type][activation][tma epilogue][CTAs per MMA]
+template <int EPI, bool T, int CG> struct KernelRow {
   static GemmKernelFn get(int act) {
     switch (act) {
-      case ACT_RELU:    return pvae_gemm_kernel<EPI, ACT_RELU, T>;
-      case ACT_TANH:    return pvae_gemm_kernel<EPI, ACT_TANH, T>;
-      case ACT_SIGMOID: return pvae_gemm_kernel<EPI, ACT_SIGMOID, T>;
-      case ACT_ELU:     return pvae_gemm_kernel<EPI, ACT_ELU, T>;
-      case ACT_SWISH:   return pvae_gemm_kernel<EPI, ACT_SWISH, T>;
-      default:          return pvae_gemm_kernel<EPI, ACT_LINEAR, T>;
+      case ACT_RELU:    return pvae_gemm_kernel<EPI, ACT_RELU, T, CG>;
+      case ACT_TANH:    return pvae_gemm_kernel<EPI, ACT_TANH, T, CG>;
+      case ACT_SIGMOID: return pvae_gemm_kernel<EPI, ACT_SIGMOID, T, CG>;
+      case ACT_ELU:     return pvae_gemm_kernel<EPI, ACT_ELU, T, CG>;
+      case ACT_SWISH:   return pvae_gemm_kernel<EPI, ACT_SWISH, T, CG>;
+      default:          return pvae_gemm_kernel<EPI, ACT_LINEAR, T, CG>;
     }
   }
 };
-static inline GemmKernelFn select_kernel(int epi, int act, bool tma) {
+template <int CG> static inline GemmKernelFn select_kernel_cg(int epi, int act, bool tma) {
   switch (epi) {
-    case EPI_STORE: return tma ? KernelRow<EPI_STORE, true>::get(act) : KernelRow<EPI_STORE, false>::get(act);
-    case EPI_DGRAD: return tma ? KernelRow<EPI_DGRAD, true>::get(act) : KernelRow<EPI_DGRAD, false>::get(act);
-    case EPI_MSE:   return tma ? pvae_gemm_kernel<EPI_MSE, ACT_LINEAR, true> : pvae_gemm_kernel<EPI_MSE, ACT_LINEAR, false>;
-    default:        return pvae_gemm_kernel<EPI_WGRAD, ACT_LINEAR, false>;
+    case EPI_STORE: return tma ? KernelRow<EPI_STORE, true, CG>::get(act) : KernelRow<EPI_STORE, false, CG>::get(act);
+    case EPI_DGRAD: return tma ? KernelRow<EPI_DGRAD, true, CG>::get(act) : KernelRow<EPI_DGRAD, false, CG>::get(act);
+    case EPI_MSE:   return tma ? pvae_gemm_kernel<EPI_MSE, ACT_LINEAR, true, CG> : pvae_gemm_kernel<EPI_MSE, ACT_LINEAR, false, CG>;
+    default:        return pvae_gemm_kernel<EPI_WGRAD, ACT_LINEAR, false, CG>;
   }
+}
+static inline GemmKernelFn select_kernel(int epi, int act, bool tma, int cg) {
+  return cg == 2 ? select_kernel_cg<2>(epi, act, tma) : select_kernel_cg<1>(epi, act, tma);
 }
 
 }  // namespace pvae
