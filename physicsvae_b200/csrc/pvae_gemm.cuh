@@ -41,7 +41,7 @@ static_assert(Geo<1>::STAGES * Geo<1>::STAGE_BYTES == PIPE_BYTES && Geo<2>::STAG
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 16;                 // four warps per TMEM lane quarter, interleaved over 32-column chunks
-constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warps 0..3: TMA / MMA / TMEM-alloc / idle, warps 4..11: epilogue
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM allocation, warps 2..17: epilogue (576 threads -> 112 registers each)
 constexpr int SLAB_BYTES = 32 * 64;           // per-epilogue-warp staging slab: 32 rows x 32 bf16 (TMA store / aux load box, 64B swizzle)
 constexpr int OFF_STAGING = PIPE_BYTES;
 constexpr int OFF_BARS = OFF_STAGING + EPI_WARPS * SLAB_BYTES;
@@ -123,7 +123,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.  The spinning part lives out of
 // line so that the pipeline loops (one iteration per 64-wide k-block) stay a few dozen instructions long.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+// SITE only separates the call sites (producer / MMA / epilogue) in profiles: stall samples land in the instance of the waiter.
+enum : int { W_EMPTY = 0, W_FULL = 1, W_TEMPTY = 2, W_TFULL = 3, W_AUX = 4 };
+template <int SITE> __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -132,14 +134,14 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
       else if (t - t0 > 4000000000ull) {   // 4 s
-        printf("pvae_gemm: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        printf("pvae_gemm: mbarrier wait %d timed out (block %d thread %d bar 0x%x parity %u)\n", SITE, (int)blockIdx.x, (int)threadIdx.x, bar, parity);
         __trap();
       }
     }
   }
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+template <int SITE> __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow<SITE>(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -185,8 +187,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of (possibly) the peer CTA.  Default semantics (release at CTA scope) on purpose: what the arrival
+// publishes is the completion of this warp's tcgen05.ld reads (ordered by tcgen05.wait::ld + fence::before_thread_sync), not
+// generic-proxy memory, and a cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR (40 % of a thin layer's epilogue).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(auxfull_bar(w), 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
+  if (warp == 1) { __syncwarp(); tmem_alloc<CG>(tmem_slot, TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();               // the peer's barriers are initialised before anything arrives on them
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         for (int j = 0; j < run.n; ++j) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait<W_EMPTY>(empty_bar(stage), phase ^ 1u);
           if (elect_one()) {
             if (leader) mbar_expect_tx(full_bar(stage), stage_tx);
             const uint32_t fb = full0 + 8u * stage;
@@ -639,7 +644,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       int acc = 0; uint32_t acc_phase = 0;
       // one k-block: wait for its operands, issue k16 (1..4) instructions of K = 16, free the slot when they have read it
       auto kblock = [&](uint32_t tmem_d, uint32_t accum, int k16) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait<W_FULL>(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t so = (uint32_t)(stage * STAGE_BYTES) >> 4;
@@ -657,7 +662,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         const int split = u / tile_units;
         const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
         int it = (int)(((int64_t)iters_total * split) / p.splits);
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // every epilogue warp (of both CTAs) has drained this stage
+        mbar_wait<W_TEMPTY>(tempty_bar(acc), acc_phase ^ 1u);          // every epilogue warp (of both CTAs) has drained this stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
         uint32_t accum = 0u;
@@ -679,22 +684,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ================================ epilogue (16 warps) ================================
-    // Warp w owns the 32 rows of TMEM lane quarter w % 4 and the 32-column chunks c = (w - 4) / 4 + 4 j of the tile: four
-    // warps per scheduler hide each other's TMEM / shared-memory / fence latencies.
+    // Warp w owns the 32 rows of TMEM lane quarter w % 4 (a hardware rule) and the 32-column chunks c = (w - 2) / 4 + 4 j of
+    // the tile: four warps per scheduler hide each other's TMEM / shared-memory / fence latencies.
     const EpiParams& e = p.epi;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id % 4)
-    const int cgrp = (warp - 4) >> 2;             // column group: chunks cgrp, cgrp + 4
-    float* bias_s = bias_all + (warp - 4) * 32;
+    const int ew = warp - 2;                      // epilogue warp index 0..15
+    const int cgrp = ew >> 2;                     // column group: chunks cgrp, cgrp + 4 (its four warps cover the four quarters)
+    float* bias_s = bias_all + ew * 32;
     const int m_valid = e.m_valid, n_valid = e.n_valid;
     const float* bias = (EPI == EPI_STORE || EPI == EPI_MSE) ? e.bias : nullptr;
     int acc = 0; uint32_t acc_phase = 0;
     double loss_local = 0.0;
     uint32_t aux_phase = 0;
+    constexpr int CS_TILES = 4;                   // N tiles whose bias-gradient column sums are kept in registers
+    float cs_acc[2 * CS_TILES];
+#pragma unroll
+    for (int k = 0; k < 2 * CS_TILES; ++k) cs_acc[k] = 0.f;
     const uint32_t tempty0 = (CG == 2) ? mapa_u32(tempty_bar(0), 0u) : tempty_bar(0);
-    const uint32_t slab = smem_base + OFF_STAGING + (warp - 4) * SLAB_BYTES;      // this warp's private staging slab
-    uint8_t* slab_gen = smem_gen + OFF_STAGING + (warp - 4) * SLAB_BYTES;
+    const uint32_t slab = smem_base + OFF_STAGING + ew * SLAB_BYTES;      // this warp's private staging slab
+    uint8_t* slab_gen = smem_gen + OFF_STAGING + ew * SLAB_BYTES;
     // 32 rows x 64 B, 64B swizzle: the 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
     uint8_t* srow = slab_gen + lane * 64;
     const int sw = (lane >> 1) & 3;
@@ -725,13 +735,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           tma_store_wait_read<0>();               // the slab's previous store has been read out (groups are per thread)
           __syncwarp();
           if (elect_one()) {
-            mbar_expect_tx(auxfull_bar(warp - 4), SLAB_BYTES);
-            tma_load_3d<1>(slab, &p.tmAux, auxfull_bar(warp - 4), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
+            mbar_expect_tx(auxfull_bar(ew), SLAB_BYTES);
+            tma_load_3d<1>(slab, &p.tmAux, auxfull_bar(ew), col0s, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
           }
           __syncwarp();
         }
       }
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait<W_TFULL>(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int nchunks = (bn + 31) >> 5;
       if (!TMAEPI) {
@@ -772,8 +782,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             tma_store_wait_read<0>();
             __syncwarp();
             if (elect_one()) {
-              mbar_expect_tx(auxfull_bar(warp - 4), SLAB_BYTES);
-              tma_load_3d<1>(slab, &p.tmAux, auxfull_bar(warp - 4), col0, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
+              mbar_expect_tx(auxfull_bar(ew), SLAB_BYTES);
+              tma_load_3d<1>(slab, &p.tmAux, auxfull_bar(ew), col0, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
             }
             __syncwarp();
           }
@@ -831,7 +841,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
               }
             };
             if (HAS_AUX) {
-              mbar_wait(auxfull_bar(warp - 4), aux_phase);
+              mbar_wait<W_AUX>(auxfull_bar(ew), aux_phase);
               aux_phase ^= 1u;
             }
             if (EPI == EPI_MSE) {
@@ -900,15 +910,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             __syncwarp();
           }
           if (EPI != EPI_STORE && e.colsum) {
-            // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> column lane
+            // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> column lane.  The sums stay in registers
+            // (one accumulator per (N tile, chunk) this warp can meet) until the end of the kernel: per-chunk red.global.add
+            // to the same few cache lines from every CTA serialises in L2 (65536 warp-wide reds onto 32 lines for a 1024-wide layer).
+            float sum = 0.f;
             if (lane < nv) {
-              float sum = 0.f;
               const int piece = lane >> 3, within = (lane & 7) << 1;
 #pragma unroll 8
               for (int r = 0; r < 32; ++r) {
                 const unsigned short hv = *reinterpret_cast<const unsigned short*>(slab_gen + r * 64 + (((piece ^ ((r >> 1) & 3)) << 4) | within));
                 sum += __uint_as_float((uint32_t)hv << 16);
               }
+            }
+            if (n_tile < CS_TILES) {
+              const int key = n_tile * 2 + j;
+#pragma unroll
+              for (int k = 0; k < 2 * CS_TILES; ++k) cs_acc[k] += (k == key) ? sum : 0.f;
+            } else if (lane < nv) {
               atomicAdd(e.colsum + col0 + lane, sum);
             }
             __syncwarp();
@@ -924,6 +942,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
     if (TMAEPI) tma_store_wait_read<0>();
+    if (TMAEPI && EPI != EPI_STORE && e.colsum) {
+      // flush the bias-gradient sums: the four lane-quarter warps of a column group combine through their (now idle)
+      // staging slabs, then one warp per column group issues the reds -- 32 warp-wide reds per CTA instead of 32 per tile.
+      __syncwarp();
+      float* mine = reinterpret_cast<float*>(slab_gen);
+#pragma unroll
+      for (int k = 0; k < 2 * CS_TILES; ++k) mine[k * 32 + lane] = cs_acc[k];
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      if ((ew & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < 2 * CS_TILES; ++k) {
+          float t = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            t += reinterpret_cast<const float*>(smem_gen + OFF_STAGING + (cgrp * 4 + qq) * SLAB_BYTES)[k * 32 + lane];
+          const int c = cgrp + 4 * (k & 1);
+          const int col = (k >> 1) * bn + c * 32 + lane;
+          if (c * 32 + lane < bn && (k >> 1) < p.n_tiles && col < n_valid) atomicAdd(e.colsum + col, t);
+        }
+      }
+    }
     if (EPI == EPI_MSE && e.loss) {
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, off);
@@ -934,7 +973,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();               // no CTA leaves while its peer may still write its TMEM / signal its barriers
-  if (warp == 2) { tc_fence_after(); tmem_dealloc<CG>(tmem_base, TMEM_COLS); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<CG>(tmem_base, TMEM_COLS); }
 }
 
 typedef void (*GemmKernelFn)(const GemmParams);
