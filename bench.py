@@ -264,6 +264,13 @@ def run_b200(args, cfg):
     clocks = sampler.stop(t0, t1) if sampler else None
     loss_after = float(eng.loss[0].item())
     value = B * world * args.steps / (ms * 1e-3)
+    if os.environ.get("PVAE_TRACE_IDX") and rank == 0:      # tools/gpu_trace.sh: role timeline of one GEMM launch
+        import ctypes
+        nwords = _abi.load().pvae_debug_trace(None, 0, 0)
+        buf = (ctypes.c_ulonglong * nwords)()
+        _abi.load().pvae_debug_trace(buf, nwords, 0)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.save(os.path.join(ROOT, "gpurun_out", "trace_%s.npy" % os.environ["PVAE_TRACE_IDX"]), np.frombuffer(buf, dtype=np.uint64))
 
     # ---- roofline leg: the tensor-core kernel sequence alone (forward + loss + backward launches of one step), CUDA events
     #      on the launching stream around pvae_{world,vae}_step only (no Adam / all-reduce / shadow refresh)

@@ -164,6 +164,11 @@ int pvae_gemm_bf16(const void* A_dev, int a_major, const void* B_dev, int b_majo
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t pvae_launch_count(void);
 
+/* profiling aid (no reference counterpart): with PVAE_DBG bit 5 set every GEMM launch records per-unit clock64 stamps of its
+ * producer / MMA / epilogue roles; this copies them to the host (out_host may be NULL) and optionally clears them.
+ * Returns the number of 64-bit words of the trace, or a negative status. */
+int pvae_debug_trace(unsigned long long* out_host, int max_words, int clear);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ SYMBOLS = [
     "pvae_last_error", "pvae_abi_version", "pvae_create", "pvae_destroy", "pvae_bind_net", "pvae_net_grad_elems",
     "pvae_sync_weights", "pvae_adam_step", "pvae_workspace_bytes", "pvae_bind_workspace", "pvae_transitions_bytes", "pvae_ingest",
     "pvae_bind_transitions", "pvae_set_cursor", "pvae_advance_cursor", "pvae_world_step", "pvae_vae_step",
-    "pvae_forward", "pvae_gemm_bf16", "pvae_launch_count",
+    "pvae_forward", "pvae_gemm_bf16", "pvae_launch_count", "pvae_debug_trace",
 ]
 
 
@@ -80,6 +80,7 @@ def load():
     lib.pvae_vae_step.argtypes = [vp, i32, vp, u64, u64, i32, f32, f32, f32, vp, vp]
     lib.pvae_forward.argtypes = [vp, u32, i32, vp, i64, vp, vp, i64, vp, i32, u64, u64, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.pvae_gemm_bf16.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.pvae_debug_trace.argtypes = [vp, i32, i32]
     lib.pvae_launch_count.restype = u64
     lib.pvae_launch_count.argtypes = []
     for name in SYMBOLS:

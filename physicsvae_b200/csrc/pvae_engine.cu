@@ -110,6 +110,7 @@ struct Device {
   int mn_bn_align = 64;   // UMMA N granularity used when B is MN-major (PVAE_MN_BN_ALIGN)
   int tma_epilogue = 1;   // bf16 outputs leave through shared memory + TMA stores (PVAE_TMA_EPILOGUE=0 disables)
   int cluster = 2;        // CTA pairs run tcgen05.mma.cta_group::2 on two adjacent M tiles (PVAE_CLUSTER=1 disables)
+  int dbg = 0;            // PVAE_DBG: epilogue timing experiments (see GemmParams::dbg)
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
@@ -126,6 +127,13 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   // CTA pairs (tcgen05.mma.cta_group::2, 256 x bn per instruction) whenever there are two M tiles to pair
   const int cluster = (dev.cluster == 2 && p.m_tiles >= 2) ? 2 : 1;
   p.cg = cluster;
+  p.dbg = dev.dbg;
+  {  // PVAE_TRACE_IDX=n: record the role timeline (GemmParams::dbg bit 5) of the n-th GEMM launch of this process only
+    static const char* sel = getenv("PVAE_TRACE_IDX");
+    static long gemm_idx = 0;
+    if (sel && atol(sel) == gemm_idx) p.dbg |= 32;
+    ++gemm_idx;
+  }
   int n_tiles = cdiv(d.N, MAX_BN);
   // bn: K-major B -- one N tile: any multiple of 16 (the TMA store clips at the tensor edge), several: whole 64-column
   // sub-tiles; MN-major B -- whole 64-column TMA boxes per CTA (each CTA of a pair stages bn / 2 columns)
@@ -245,7 +253,7 @@ struct pvae_engine {
   Net nets[PVAE_NUM_NETS];
   int planes = 1, passes = 1;
   int max_batch = 0;
-  int dsb = 0, dsbp = 0, da = 0, z = 0, te_out = 0;   // dsbp: 16-byte aligned column where s_{t+1} starts inside a transition row
+  int dsb = 0, dsbp = 0, da = 0, z = 0, te_out = 0;   // dsbp: 128-byte aligned column where s_{t+1} starts inside a transition row
   // workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -486,6 +494,8 @@ static int init_device(Device& dev, int device) {
   if (env) { int v = atoi(env); if (v == 16 || v == 32 || v == 64) dev.mn_bn_align = v; }
   env = getenv("PVAE_TMA_EPILOGUE");
   if (env) dev.tma_epilogue = atoi(env) != 0;
+  env = getenv("PVAE_DBG");
+  if (env) dev.dbg = atoi(env);
   env = getenv("PVAE_CLUSTER");
   if (env) dev.cluster = atoi(env) == 1 ? 1 : 2;
   CKR(resolve_driver());
@@ -509,9 +519,11 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
   h->max_batch = desc->max_batch;
   h->dsb = desc->dim_state_body; h->da = desc->dim_action; h->z = desc->latent_dim;
   h->te_out = desc->latent_prior ? 2 * h->z : h->z;
-  h->dsbp = rup(h->dsb, 8);
+  // s_t and s_{t+1} each start on a 128-byte boundary and rows are whole cache lines, so that every 64-column TMA box row
+  // of the resident buffer is exactly one L2 line (a 16-byte-aligned 800 B row stride made every box row straddle two)
+  h->dsbp = rup(h->dsb, 64);
   h->tx_ld = 2 * h->dsbp;
-  h->ty_ld = rup(h->da, 8);
+  h->ty_ld = rup(h->da, 64);
   for (int n = 0; n < PVAE_NUM_NETS; ++n) {
     Net& net = h->nets[n];
     const pvae_net_desc& nd = desc->nets[n];
@@ -918,6 +930,22 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
   }
   CK(cudaGetLastError());
   return PVAE_OK;
+}
+
+// Debug: copy the per-unit clock stamps of the most recent GEMM launches (PVAE_DBG bit 5) to the host; returns the number
+// of 64-bit words written (see g_trace in pvae_gemm.cuh).  Not part of the reference-facing interface.
+int pvae_debug_trace(unsigned long long* out_host, int max_words, int clear) {
+  const int n = TRACE_CTAS * TRACE_UNITS * 8;
+  if (out_host) {
+    if (max_words < n) return fail(PVAE_ERR_INVALID, "trace buffer needs %d words", n);
+    CK(cudaMemcpyFromSymbol(out_host, g_trace, sizeof(unsigned long long) * n));
+  }
+  if (clear) {
+    void* sym = nullptr;
+    CK(cudaGetSymbolAddress(&sym, g_trace));
+    CK(cudaMemset(sym, 0, sizeof(unsigned long long) * n));
+  }
+  return n;
 }
 
 // D = A . B^T on the tensor-core path, operands given as bf16 planes (unit tests / bench roofline).

@@ -91,6 +91,7 @@ struct GemmParams {
   int32_t b_dyn;                   // B: add *row_cursor to the k row coordinate (MN-major)
   int32_t passes;                  // 1 = bf16, 3 = bf16x3
   int32_t m_tiles, n_tiles, bn, splits;
+  int32_t dbg;                     // PVAE_DBG bit mask: skip parts of the TMA epilogue (timing experiments only, results are wrong)
   int32_t cg;                      // 1, or 2: CTA pairs on adjacent M tiles run one 256-row tcgen05.mma.cta_group::2 (kernel template CG)
   const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
   CUtensorMap tmOut;               // TMA-store epilogue: the primary bf16 output, box 64 cols x 32 rows (one warp's slab)
@@ -306,6 +307,37 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float a, float b) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// Column sums of a 32 x 32 bf16 slab (32 rows of 64 B, 64B swizzle) on the legacy tensor path: ones[16 x 32] . slab, i.e.
+// per 8-column group one ldmatrix.x4.trans (lane l supplies the address of its own row's 16-byte piece) feeding two
+// mma.sync m16n8k16.  Returns the sum of column `lane`.  `piece_addr(j)` = shared address of piece j of this lane's row.
+template <typename F> __device__ __forceinline__ float slab_colsum32(F piece_addr, int lane) {
+  float d[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t b0, b1, b2, b3;
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(piece_addr(j)));
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    const uint32_t one2 = 0x3F803F80u;            // bf16x2 (1, 1)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
+                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(one2), "r"(b0), "r"(b1));
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
+                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(one2), "r"(b2), "r"(b3));
+    d[j][0] = c0; d[j][1] = c1;                   // columns 8 j + 2 (lane % 4) + {0, 1}, the same in every row group
+  }
+  // lane l keeps column (l / 8) * 8 + (l % 4) * 2 + ((l / 4) & 1): with l % 4 = t and (l / 4) & 1 = e that is d[l / 8][e]
+  const int j = lane >> 3, e = (lane >> 2) & 1;
+  float r = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const float pick = e ? d[jj][1] : d[jj][0];
+    r = (jj == j) ? pick : r;
+  }
+  return r;
+}
+// which column of a chunk slab_colsum32 leaves in `lane`
+__device__ __forceinline__ int slab_colsum_col(int lane) { return ((lane >> 3) << 3) + ((lane & 3) << 1) + ((lane >> 2) & 1); }
+
 __device__ __forceinline__ float bf16_lo_part(float v) {  // v - bf16(v)
   return v - __bfloat162float(__float2bfloat16_rn(v));
 }
@@ -500,9 +532,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float (&v)[32
 struct KRun {
   int pass, seg, r0, n;        // r0: first k-block inside the segment; n: k-blocks in the run
   bool ends_seg;               // the run contains the segment's last (possibly ragged) k-block
-  __device__ __forceinline__ void init(int it, int it_end, int kb0, int kb1) {
+  __device__ __forceinline__ void init(int it, int it_end, int kb0, int kb1, int passes) {
     const int kb_total = kb0 + kb1;
-    pass = it / kb_total;
+    pass = passes == 1 ? 0 : it / kb_total;       // (no division in the single-pass bf16 mode)
     const int rem = it - pass * kb_total;
     seg = rem >= kb0 ? 1 : 0;
     r0 = seg ? rem - kb0 : rem;
@@ -510,6 +542,47 @@ struct KRun {
     n = left < it_end - it ? left : it_end - it;
     ends_seg = (n == left);
   }
+};
+
+// PVAE_DBG bit 5: per-unit clock64 stamps of the three roles of every CTA (first TRACE_UNITS units), read back through
+// pvae_debug_trace().  slots: 0 MMA loop top, 1 tempty acquired, 2 first operands landed, 3 last k-block issued,
+// 4 epilogue before tfull wait, 5 accumulator ready, 6 epilogue done, 7 producer issued the unit's last copy.
+constexpr int TRACE_UNITS = 16, TRACE_CTAS = 160;
+__device__ unsigned long long g_trace[TRACE_CTAS * TRACE_UNITS * 8];
+__device__ __forceinline__ void trace_stamp(int dbg, int k, int slot) {
+  if ((dbg & 32) && k < TRACE_UNITS && blockIdx.x < TRACE_CTAS) g_trace[((int)blockIdx.x * TRACE_UNITS + k) * 8 + slot] = clock64();
+}
+
+// The work units of one CTA (pair): u = unit0, unit0 + stride, ... numbered split-major / M-tile / N-tile-minor.  The
+// (split, m, n) triple is stepped as a mixed-radix counter: integer divisions (~150 dependent cycles each, 64-bit ones
+// several hundred) happen once per kernel instead of once per unit in every role -- for a 5-k-block tile they cost the
+// MMA-issuing warp more time than the tile's tensor work.
+struct UnitWalk {
+  int split, mp, nt;
+  int d_split, d_mp, d_nt, n_tiles, m_pairs, it_base, it_rem;
+  __device__ __forceinline__ void init(int u0, int stride, int n_tiles_, int m_pairs_, int iters_total, int splits) {
+    n_tiles = n_tiles_; m_pairs = m_pairs_;
+    const int tile_units = n_tiles * m_pairs;
+    split = u0 / tile_units;
+    int t = u0 - split * tile_units;
+    mp = t / n_tiles; nt = t - mp * n_tiles;
+    d_split = stride / tile_units;
+    t = stride - d_split * tile_units;
+    d_mp = t / n_tiles; d_nt = t - d_mp * n_tiles;
+    it_base = iters_total / splits; it_rem = iters_total - it_base * splits;
+  }
+  __device__ __forceinline__ void next() {
+    nt += d_nt;
+    int c = nt >= n_tiles ? 1 : 0;
+    nt -= c ? n_tiles : 0;
+    mp += d_mp + c;
+    c = mp >= m_pairs ? 1 : 0;
+    mp -= c ? m_pairs : 0;
+    split += d_split + c;
+  }
+  // k-blocks of the current split: the first it_rem splits get one more than the others
+  __device__ __forceinline__ int it_begin() const { return split * it_base + (split < it_rem ? split : it_rem); }
+  __device__ __forceinline__ int it_end() const { return it_begin() + it_base + (split < it_rem ? 1 : 0); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -576,7 +649,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   const int kb_total = p.kb[0] + p.kb[1];
   const int iters_total = p.passes * kb_total;
   // units of one CTA (pair): tile-minor / split-major, so that the CTAs running at the same time share K ranges through L2
-  const int tile_units = ((p.m_tiles + csize - 1) / csize) * p.n_tiles;
+  const int m_pairs = (p.m_tiles + csize - 1) / csize;
+  const int tile_units = m_pairs * p.n_tiles;
   const int total_units = tile_units * p.splits;
   const int bn = p.bn;
 
@@ -592,16 +666,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     const bool leader = (CG == 1) || crank == 0;
     const uint32_t full0 = (CG == 2) ? mapa_u32(full_bar(0), 0u) : full_bar(0);
     int stage = 0; uint32_t phase = 0;
-    for (int u = unit0; u < total_units; u += unit_stride) {
-      const int split = u / tile_units;
-      const int tile = u - split * tile_units;
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = (tile / p.n_tiles) * csize + crank;
-      const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
-      int it = (int)(((int64_t)iters_total * split) / p.splits);
+    UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits);
+    for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
+      const int n_tile = w.nt;
+      const int m_tile = w.mp * csize + crank;
+      const int it_end = w.it_end();
+      int it = w.it_begin();
       const int b_n = p.b_n0 + n_tile * bn + crank * bn_loc;
       while (it < it_end) {
-        KRun run; run.init(it, it_end, p.kb[0], p.kb[1]);
+        KRun run; run.init(it, it_end, p.kb[0], p.kb[1], p.passes);
         it += run.n;
         const int seg = run.seg;
         const int a_plane = (run.pass == 2) ? 1 : 0;
@@ -631,6 +704,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      if (lane == 0) trace_stamp(p.dbg, (u - unit0) / unit_stride, 7);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA of the pair only) ================================
@@ -658,16 +732,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       };
-      for (int u = unit0; u < total_units; u += unit_stride) {
-        const int split = u / tile_units;
-        const int it_end = (int)(((int64_t)iters_total * (split + 1)) / p.splits);
-        int it = (int)(((int64_t)iters_total * split) / p.splits);
+      UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits);
+      for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
+        const int it_end = w.it_end();
+        int it = w.it_begin();
+        const int tk = (p.dbg & 32) ? (u - unit0) / unit_stride : 0;
+        if (lane == 0) trace_stamp(p.dbg, tk, 0);
         mbar_wait<W_TEMPTY>(tempty_bar(acc), acc_phase ^ 1u);          // every epilogue warp (of both CTAs) has drained this stage
         tc_fence_after();
+        if (lane == 0) trace_stamp(p.dbg, tk, 1);
+        bool first_kb = true;
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
         uint32_t accum = 0u;
         while (it < it_end) {
-          KRun run; run.init(it, it_end, p.kb[0], p.kb[1]);
+          KRun run; run.init(it, it_end, p.kb[0], p.kb[1], p.passes);
           it += run.n;
           // all-zero k16 slices at the ragged end of a segment are skipped
           int tail = 4;
@@ -676,9 +754,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             tail = tail > 4 ? 4 : (tail < 1 ? 1 : tail);
           }
           const int n_full = tail < 4 ? run.n - 1 : run.n;
+          if ((p.dbg & 32) && first_kb) {          // (trace only) when did the unit's first operands land?
+            mbar_wait<W_FULL>(full_bar(stage), phase);
+            if (lane == 0) trace_stamp(p.dbg, tk, 2);
+            first_kb = false;
+          }
           for (int j = 0; j < n_full; ++j) { kblock(tmem_d, accum, 4); accum = 1u; }
           if (tail < 4) { kblock(tmem_d, accum, tail); accum = 1u; }
         }
+        if (lane == 0) trace_stamp(p.dbg, tk, 3);
         if (elect_one()) umma_commit<CG>(tfull_bar(acc));    // accumulator complete -> epilogue (of both CTAs)
         __syncwarp();
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
@@ -698,6 +782,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     int acc = 0; uint32_t acc_phase = 0;
     double loss_local = 0.0;
     uint32_t aux_phase = 0;
+    const bool cs_mma = kb_total <= 8;            // see the column-sum code below
     constexpr int CS_TILES = 4;                   // N tiles whose bias-gradient column sums are kept in registers
     float cs_acc[2 * CS_TILES];
 #pragma unroll
@@ -708,10 +793,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     // 32 rows x 64 B, 64B swizzle: the 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
     uint8_t* srow = slab_gen + lane * 64;
     const int sw = (lane >> 1) & 3;
-    for (int u = unit0; u < total_units; u += unit_stride) {
-      const int tile = u % tile_units;
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = (tile / p.n_tiles) * csize + crank;
+    UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits);
+    for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
+      const int n_tile = w.nt;
+      const int m_tile = w.mp * csize + crank;
       const int row_in_tile = q * 32 + lane;
       const int row = m_tile * BM + row_in_tile;
       const bool row_ok = row < m_valid;
@@ -741,8 +826,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           __syncwarp();
         }
       }
+      const int tk = (p.dbg & 32) ? (u - unit0) / unit_stride : 0;
+      if (ew == 0 && lane == 0) trace_stamp(p.dbg, tk, 4);
       mbar_wait<W_TFULL>(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (ew == 0 && lane == 0) trace_stamp(p.dbg, tk, 5);
       const int nchunks = (bn + 31) >> 5;
       if (!TMAEPI) {
         for (int c = cgrp; c < nchunks; c += 4) {
@@ -790,12 +878,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           float v[32];
           {
             uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + c * 32), raw);
-            tmem_ld_wait();
+            if (!(p.dbg & 16)) {
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + c * 32), raw);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) raw[i] = 0u;
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
           }
-          if (bias) {
+          if (bias && !(p.dbg & 1)) {
             __syncwarp();
             bias_s[lane] = bias_l;
             __syncwarp();
@@ -818,7 +911,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = (ACT == ACT_RELU) ? pack_bf16x2_relu(v[2 * i], v[2 * i + 1]) : pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            if (ACT == ACT_RELU && e.mask && row_ok) {
+            if (ACT == ACT_RELU && e.mask && row_ok && !(p.dbg & 2)) {
               // sign-bit mask from the packed non-negative results: a half is > 0 iff adding 0x7fff carries into its bit 15.
               // Word layout: bit i = column 2 i, bit 16 + i = column 2 i + 1 (private to this kernel's dgrad epilogue).
               uint32_t m0 = 0u, m1 = 0u;
@@ -871,10 +964,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += a[i];
               }
-              if (USE_MASK) {
+              if (USE_MASK && e.out_f32 != nullptr) {   // (an fp32 copy wants the masked values themselves)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = ((mbits >> ((i >> 1) + 16 * (i & 1))) & 1u) ? v[i] : 0.f;   // mask is 0 for rows >= m_valid
-              } else if (ACT != ACT_LINEAR) {
+              } else if (!USE_MASK && ACT != ACT_LINEAR) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                   float y[8];
@@ -892,7 +985,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             if (HAS_AUX) __syncwarp();            // every lane has read the aux slab before it is overwritten below
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            if (USE_MASK && !(p.dbg & 2)) {
+              // ReLU': bit i / bit 16 + i of the mask word gate the low / high half of pair i -- shift them onto the sign bits of
+              // bytes 1 / 3 and let prmt replicate the signs over the two halves
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                uint32_t m;
+                asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(mbits << (15 - i)));
+                pk[i] &= m;
+              }
+            }
           }
+          if (p.dbg & 4) continue;
           if (!HAS_AUX) {                         // (with aux the slab was already claimed before the aux load)
             tma_store_wait_read<0>();             // bulk groups are per thread: only the electing lane ever has pending ones
             __syncwarp();
@@ -909,30 +1013,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             }
             __syncwarp();
           }
-          if (EPI != EPI_STORE && e.colsum) {
+          if (EPI != EPI_STORE && e.colsum && !(p.dbg & 8)) {
             // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> column lane.  The sums stay in registers
             // (one accumulator per (N tile, chunk) this warp can meet) until the end of the kernel: per-chunk red.global.add
             // to the same few cache lines from every CTA serialises in L2 (65536 warp-wide reds onto 32 lines for a 1024-wide layer).
+            // (columns >= nv of the slab are zero, rows >= m_valid too)
+            // Short-K GEMMs leave the tensor pipe idle most of the time: there the sums ride on mma.sync (ones . slab); with a
+            // long K the legacy MMAs stall the tcgen05 stream (measured: 1024-deep dgrad 100 -> 123 us), so lanes add up columns.
             float sum = 0.f;
-            if (lane < nv) {
-              const int piece = lane >> 3, within = (lane & 7) << 1;
-#pragma unroll 8
+            if (cs_mma) {
+              sum = slab_colsum32([&](int jp) { return slab + (uint32_t)lane * 64u + (uint32_t)((jp ^ sw) << 4); }, lane);
+            } else {
+              const int col = slab_colsum_col(lane);
+              const int piece = col >> 3, within = (col & 7) << 1;
+              float part[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains instead of one 32-long dependent one
+#pragma unroll
               for (int r = 0; r < 32; ++r) {
                 const unsigned short hv = *reinterpret_cast<const unsigned short*>(slab_gen + r * 64 + (((piece ^ ((r >> 1) & 3)) << 4) | within));
-                sum += __uint_as_float((uint32_t)hv << 16);
+                part[r & 3] += __uint_as_float((uint32_t)hv << 16);
               }
+              sum = (part[0] + part[1]) + (part[2] + part[3]);
             }
             if (n_tile < CS_TILES) {
               const int key = n_tile * 2 + j;
 #pragma unroll
               for (int k = 0; k < 2 * CS_TILES; ++k) cs_acc[k] += (k == key) ? sum : 0.f;
-            } else if (lane < nv) {
-              atomicAdd(e.colsum + col0 + lane, sum);
+            } else if (slab_colsum_col(lane) < nv) {
+              atomicAdd(e.colsum + col0 + slab_colsum_col(lane), sum);
             }
             __syncwarp();
           }
         }
       }
+      if (ew == 0 && lane == 0) trace_stamp(p.dbg, tk, 6);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                            // the accumulator stage may be overwritten: tell the (leader's) MMA warp
@@ -958,8 +1071,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           for (int qq = 0; qq < 4; ++qq)
             t += reinterpret_cast<const float*>(smem_gen + OFF_STAGING + (cgrp * 4 + qq) * SLAB_BYTES)[k * 32 + lane];
           const int c = cgrp + 4 * (k & 1);
-          const int col = (k >> 1) * bn + c * 32 + lane;
-          if (c * 32 + lane < bn && (k >> 1) < p.n_tiles && col < n_valid) atomicAdd(e.colsum + col, t);
+          const int cl = c * 32 + slab_colsum_col(lane);
+          const int col = (k >> 1) * bn + cl;
+          if (cl < bn && (k >> 1) < p.n_tiles && col < n_valid) atomicAdd(e.colsum + col, t);
         }
       }
     }

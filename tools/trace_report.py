@@ -1,0 +1,24 @@
+"""Summarise gpurun_out/trace_<idx>.npy files (tools/gpu_trace.sh): per-unit role timeline of a GEMM launch."""
+import sys, numpy as np
+names = {27: "fwd L0", 28: "fwd L1", 29: "fwd L2 MSE", 30: "wgrad L2", 31: "dgrad L1", 32: "wgrad L1", 33: "dgrad L0", 34: "wgrad L0 s", 35: "wgrad L0 a"}
+for idx in sorted(names):
+    try:
+        t = np.load("gpurun_out/trace_%d.npy" % idx).reshape(160, 16, 8).astype(np.int64)
+    except Exception as e:
+        continue
+    t = np.where(t == 0, np.nan, t.astype(np.float64))
+    L = t[0:148:2]                       # leader CTAs (even rank)
+    nun = int(np.sum(~np.isnan(L[0, :, 0])))
+    print("== %d %s: units traced per CTA %d" % (idx, names[idx], nun))
+    def m(a): return np.nanmean(a)
+    U = L[:, 2:min(nun, 12)]
+    period = L[:, 3:min(nun, 12), 0] - L[:, 2:min(nun, 12) - 1, 0]
+    print("   MMA warp: period %.0f | wait tempty %.0f | wait first operands %.0f | issue k-blocks %.0f | rest %.0f" % (
+        m(period), m(U[..., 1] - U[..., 0]), m(U[..., 2] - U[..., 1]), m(U[..., 3] - U[..., 2]), m(period) - m(U[..., 3] - U[..., 0])))
+    print("   epilogue warp 0: wait acc %.0f | work %.0f | acc ready after MMA issue end %.0f | epi done -> next tempty seen %.0f" % (
+        m(U[..., 5] - U[..., 4]), m(U[..., 6] - U[..., 5]), m(U[..., 5] - U[..., 3]), m(L[:, 4:min(nun, 12), 1] - L[:, 2:min(nun, 12) - 2, 6])))
+    print("   producer: done with unit's copies relative to MMA issue end %.0f" % m(U[..., 7] - U[..., 3]))
+    c = 0
+    base = L[c, 0, 0]
+    for k in range(min(nun, 6)):
+        print("     cta0 unit %d: " % k + " ".join("%7.0f" % (x - base) for x in L[c, k]))
