@@ -277,21 +277,43 @@ def run_b200(args, cfg):
     fl_world, fl_vae = orc.flops_per_transition(cfg["dsb"], cfg["da"], cfg["z"], [cfg["te"][0]] * cfg["te"][1],
                                                 [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
     flops_step = (fl_world if phase == "world" else fl_vae) * B
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
-    n0 = _abi.launch_count()
-    for i in range(max(5, min(args.steps, 20))):
-        k0.record()
+    def kernel_seq():
         if phase == "world":
             eng.world_step(B, s_coeff=1.0)
         else:
             eng.vae_step(B, eps=None, seed=1234, offset=rank, noise=True, a_coeff=1.0, kl_coeff=1.0, cyc_coeff=1e-3)
-        k1.record()
-        k1.synchronize()
-        kms.append(k0.elapsed_time(k1))
         eng.advance_cursor(B, B, n_rows)
-    gemm_launches = (_abi.launch_count() - n0) // len(kms) - 2          # minus finalize_loss + cursor advance
-    kernel_ms = statistics.median(kms)
+    n0 = _abi.launch_count()
+    kernel_seq()
+    gemm_launches = (_abi.launch_count() - n0) - 2                     # minus finalize_loss + cursor advance
+    torch.cuda.synchronize()
+    kgraph = None
+    if not args.no_graph:                      # the same launch sequence as a graph: device time without host launch gaps
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    kernel_seq()
+            torch.cuda.current_stream().wait_stream(side)
+            kgraph = g
+        except Exception:
+            kgraph = None
+            torch.cuda.synchronize()
+    krun = (lambda: kgraph.replay()) if kgraph is not None else kernel_seq
+    for _ in range(3):
+        krun()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kiters = max(5, min(args.steps, 50))
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(kiters):
+        krun()
+    k1.record()
+    k1.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / kiters
+    kgraph = None
     pk, pk_src = peaks()
     achieved = flops_step / (kernel_ms * 1e-3) / 1e12
     traffic = None
@@ -313,24 +335,39 @@ def run_b200(args, cfg):
     # ---- end-to-end leg: the reference-facing call with HOST buffers.  Per step, exactly what torch_models.TrainModel.step
     #      does per mini-batch: x, y (pinned host fp32, as the DataLoader hands them over) -> device, compute_loss, backward,
     #      optimizer.step, loss.item()
-    xh = torch.from_numpy(synthetic_arrays(cfg, B, seed=77 + rank)[0]).float().pin_memory()
-    yh = torch.from_numpy(synthetic_arrays(cfg, B, seed=77 + rank)[1]).pin_memory()
+    xa, ya = synthetic_arrays(cfg, B, seed=77 + rank)
+    xh = torch.from_numpy(xa).float().pin_memory()
+    yh = torch.from_numpy(ya).pin_memory()
     h2d = xh.numel() * 4 + yh.numel() * 4
+    # double-buffered loader: the copy of mini-batch i + 1 (pinned host -> device, every step) runs on a copy stream while
+    # step i computes; loss.item() at the end of every step is the device -> host read
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(xh, device=dev), torch.empty_like(yh, device=dev)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        x = xh.to(dev, non_blocking=True)
-        y = yh.to(dev, non_blocking=True)
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2][0].copy_(xh, non_blocking=True)
+            bufs[i % 2][1].copy_(yh, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_step(i, last=False):
+        if not last:
+            prefetch(i + 1)                  # buffer (i + 1) % 2 was last read by step i - 1, which loss.item() has retired
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        x, y = bufs[i % 2]
         loss = tr.compute_loss(y, x)
         loss.backward()
         tr.optimizer.step()
         return loss.item()
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(3):
-        e2e_step()
+    prefetch(0)
+    for i in range(3):
+        e2e_step(i)
     barrier()
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for i in range(3, 3 + e2e_steps):
+        e2e_step(i, last=(i == 2 + e2e_steps))
     e1.record()
     barrier()
     ems = e0.elapsed_time(e1)
@@ -339,7 +376,7 @@ def run_b200(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ems = float(t.item())
     e2e = {"value": B * world * e2e_steps / (ems * 1e-3), "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-           "steps": e2e_steps, "ms_per_step": ems / e2e_steps, "api": "TrainModel.compute_loss(y, x) + backward + optimizer.step + loss.item()"}
+           "steps": e2e_steps, "ms_per_step": ems / e2e_steps, "api": "double-buffered pinned-host loader -> TrainModel.compute_loss(y, x) + backward + optimizer.step + loss.item()"}
 
     if rank == 0:
         line = {"metric": "transitions/sec (world-model+VAE step)", "value": value, "unit": "transitions/s", "n_gpus": world,

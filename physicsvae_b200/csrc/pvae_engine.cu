@@ -100,6 +100,7 @@ struct GemmDesc {
   int K[2] = {0, 0};      // valid k extent per segment
   int passes = 1;
   bool split = false;     // split K over CTAs (wgrad)
+  bool mseg = false;      // A[0] / A[1] are M segments (MN-major wgrad of a two-segment input) instead of K segments
   EpiParams epi;
   GemmDesc() { memset(&epi, 0, sizeof(epi)); }
 };
@@ -124,6 +125,13 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   p.b_major = d.b_major;
   p.passes = d.passes;
   p.m_tiles = cdiv(d.M, BM);
+  if (d.mseg) {
+    if (d.a_major != MAJOR_MN || d.nseg != 2) return fail(PVAE_ERR_INVALID, "M segments need an MN-major two-segment A operand");
+    p.m_seg_tiles = cdiv(d.A[0].width, BM);
+    p.m_seg_rows[0] = d.A[0].width; p.m_seg_rows[1] = d.A[1].width;
+    p.m_seg_out0 = d.A[0].width;
+    p.m_tiles = p.m_seg_tiles + cdiv(d.A[1].width, BM);
+  }
   // CTA pairs (tcgen05.mma.cta_group::2, 256 x bn per instruction) whenever there are two M tiles to pair
   const int cluster = (dev.cluster == 2 && p.m_tiles >= 2) ? 2 : 1;
   p.cg = cluster;
@@ -146,7 +154,7 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   p.bn = bn;
   for (int s = 0; s < 2; ++s) {
     if (s < d.nseg) {
-      p.kb[s] = cdiv(d.K[s], BK);
+      p.kb[s] = (d.mseg && s == 1) ? 0 : cdiv(d.K[s], BK);
       p.klen[s] = d.K[s];
       p.a_c0[s] = 0;
       p.a_r0[s] = 0;
@@ -389,28 +397,29 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
   for (int l = L - 1; l >= 0; --l) {
     const View gl = ws_view(h, net.g[l], net.act_ld[l], net.out_dims[l], batch);
     if (train) {
-      // dW[l]^T [in][out] = input^T . g[l]; one launch per input segment
-      const int nseg = (l == 0) ? in.nseg : 1;
-      int col0 = 0;
-      for (int s = 0; s < nseg; ++s) {
-        GemmDesc d;
-        d.a_major = MAJOR_MN; d.b_major = MAJOR_MN;
+      // dW[l]^T [in][out] = input^T . g[l]; the two input segments of layer 0 are M segments of one launch (g[0] is read once)
+      GemmDesc d;
+      d.a_major = MAJOR_MN; d.b_major = MAJOR_MN;
+      d.K[0] = batch; d.K[1] = batch;
+      d.passes = h->passes;
+      d.split = true;
+      d.epi.type = EPI_WGRAD;
+      d.epi.out_f32 = net.grad + net.gW[l];
+      d.epi.f32_atomic = 1;
+      d.epi.f32_sm = 1; d.epi.f32_sn = net.in_dims[l];
+      d.B = gl;
+      d.N = net.out_dims[l];
+      if (l == 0 && in.nseg == 2) {
+        d.nseg = 2; d.mseg = true;
+        d.A[0] = in.seg[0]; d.A[1] = in.seg[1];
+        d.M = in.seg[0].width + in.seg[1].width;
+      } else {
         d.nseg = 1;
-        const View xin = (l == 0) ? in.seg[s] : ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
-        const int m_in = xin.width;
-        d.K[0] = batch;
-        d.passes = h->passes;
-        d.split = true;
-        d.epi.type = EPI_WGRAD;
-        d.epi.out_f32 = net.grad + net.gW[l] + col0;
-        d.epi.f32_atomic = 1;
-        d.A[0] = xin; d.B = gl;
-        d.M = m_in; d.N = net.out_dims[l];
-        d.epi.f32_sm = 1; d.epi.f32_sn = net.in_dims[l];
         // the operand that comes from the resident buffer walks the batch along k: the dynamic cursor applies to its rows
-        CKR(launch_gemm(h->dev, d, st));
-        col0 += m_in;
+        d.A[0] = (l == 0) ? in.seg[0] : ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
+        d.M = d.A[0].width;
       }
+      CKR(launch_gemm(h->dev, d, st));
     }
     if (l > 0) {
       GemmDesc d;

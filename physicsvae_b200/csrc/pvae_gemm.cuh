@@ -89,6 +89,9 @@ struct GemmParams {
   int32_t b_k0[2];                 // B: k offset at the start of the segment (K-major: inner coord, MN-major: row coord)
   int32_t b_n0;                    // B: n offset
   int32_t b_dyn;                   // B: add *row_cursor to the k row coordinate (MN-major)
+  // M segments (MN-major A only, wgrad of a layer whose input is a virtual concat): M tiles [0, m_seg_tiles) come from
+  // tmA[0], the rest from tmA[1]; a segment-1 tile's rows land in the output at row m_seg_out0 + local row.  0 = off.
+  int32_t m_seg_tiles, m_seg_rows[2], m_seg_out0;
   int32_t passes;                  // 1 = bf16, 3 = bf16x3
   int32_t m_tiles, n_tiles, bn, splits;
   int32_t dbg;                     // PVAE_DBG bit mask: skip parts of the TMA epilogue (timing experiments only, results are wrong)
@@ -679,11 +682,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         const int seg = run.seg;
         const int a_plane = (run.pass == 2) ? 1 : 0;
         const int b_plane = (run.pass == 1) ? 1 : 0;
-        const CUtensorMap* tmA = &p.tmA[seg];
-        const int a_row = p.a_r0[seg] + (p.a_dyn[seg] ? row0 : 0);
+        const int aseg = (p.m_seg_tiles && m_tile >= p.m_seg_tiles) ? 1 : seg;     // M segment (wgrad) or K segment
+        const int m_loc = (p.m_seg_tiles && m_tile >= p.m_seg_tiles) ? m_tile - p.m_seg_tiles : m_tile;
+        const CUtensorMap* tmA = &p.tmA[aseg];
+        const int a_row = p.a_r0[aseg] + (p.a_dyn[aseg] ? row0 : 0);
         // coordinates of the run's first k-block; a k-block further on moves the K coordinate by BK
-        int ac0 = a_mn ? p.a_c0[seg] + m_tile * BM : p.a_c0[seg] + run.r0 * BK;
-        int ac1 = a_mn ? a_row + run.r0 * BK : a_row + m_tile * BM;
+        int ac0 = a_mn ? p.a_c0[aseg] + m_loc * BM : p.a_c0[aseg] + run.r0 * BK;
+        int ac1 = a_mn ? a_row + run.r0 * BK : a_row + m_loc * BM;
         int bc0 = b_mn ? b_n : p.b_k0[seg] + run.r0 * BK;
         int bc1 = b_mn ? p.b_k0[seg] + run.r0 * BK + (p.b_dyn ? row0 : 0) : b_n;
         for (int j = 0; j < run.n; ++j) {
@@ -798,8 +803,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       const int n_tile = w.nt;
       const int m_tile = w.mp * csize + crank;
       const int row_in_tile = q * 32 + lane;
-      const int row = m_tile * BM + row_in_tile;
-      const bool row_ok = row < m_valid;
+      int row = m_tile * BM + row_in_tile;
+      bool row_ok = row < m_valid;
+      if (p.m_seg_tiles) {                         // output row of an M-segmented (virtual concat) operand
+        const int s1 = m_tile >= p.m_seg_tiles ? 1 : 0;
+        const int local = row - (s1 ? p.m_seg_tiles * BM : 0);
+        row_ok = local < p.m_seg_rows[s1];
+        row = (s1 ? p.m_seg_out0 : 0) + local;
+      }
       // operands of this warp's (at most two) chunks that do not depend on the accumulator: fetched while the main loop runs
       float pre_bias[2] = {0.f, 0.f};
       uint32_t pre_mask[2] = {0u, 0u};
