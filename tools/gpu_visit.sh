@@ -23,6 +23,6 @@ except Exception as e: print('bench parse failed', e)
 timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:pvae -s 40 -c 30 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
 python tools/launch_table.py gpurun_out/launches_$TAG.csv 2>&1 | tail -n 24
 if [ "$F" = "full" ]; then
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:pvae_gemm -s 27 -c 9 -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:pvae_gemm -s 24 -c 8 -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out/prof_$TAG.ncu-rep
 fi
