@@ -20,7 +20,8 @@ PART_ENCODER, PART_DECODER, PART_WORLD, PART_VALUE = 1, 2, 4, 8
 ACT_IDS = {None: 0, "linear": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "elu": 4, "swish": 5, "silu": 5}
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libpvae_sm100.so")
+# PVAE_LIB selects another build of the same library (e.g. one compiled with -DPVAE_DEBUG_HOOKS for the role-timeline tools)
+LIB_PATH = os.environ.get("PVAE_LIB") or os.path.join(LIB_DIR, "libpvae_sm100.so")
 
 # every symbol include/pvae_sm100.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = [

@@ -22,8 +22,10 @@ __device__ __forceinline__ int split_src_col(int c, int w0, int p0, int width) {
   const int j = w0 + (c - p0);
   return j < width ? j : -1;
 }
+// src2 (optional): a second fp32 array whose w2 columns land at destination columns [c2, c2 + w2) (a_t behind s_t)
 template <typename SrcT>
-__global__ void ingest_kernel(const SrcT* __restrict__ src, int64_t src_ld, int width, int w0, int p0, __nv_bfloat16* __restrict__ dst,
+__global__ void ingest_kernel(const SrcT* __restrict__ src, int64_t src_ld, int width, int w0, int p0,
+                              const float* __restrict__ src2, int64_t src2_ld, int w2, int c2, __nv_bfloat16* __restrict__ dst,
                               int64_t dst_ld, int64_t dst_ps, int planes, int64_t n_rows) {
   const int64_t pairs_per_row = dst_ld >> 1;   // dst_ld is a multiple of 8
   const int64_t total = n_rows * pairs_per_row;
@@ -31,8 +33,12 @@ __global__ void ingest_kernel(const SrcT* __restrict__ src, int64_t src_ld, int 
     const int64_t r = i / pairs_per_row;
     const int c = (int)(i - r * pairs_per_row) * 2;
     const int s0 = split_src_col(c, w0, p0, width), s1 = split_src_col(c + 1, w0, p0, width);
-    const float v0 = (s0 >= 0) ? (float)src[r * src_ld + s0] : 0.f;
-    const float v1 = (s1 >= 0) ? (float)src[r * src_ld + s1] : 0.f;
+    float v0 = (s0 >= 0) ? (float)src[r * src_ld + s0] : 0.f;
+    float v1 = (s1 >= 0) ? (float)src[r * src_ld + s1] : 0.f;
+    if (src2) {
+      if (c >= c2 && c < c2 + w2) v0 = src2[r * src2_ld + (c - c2)];
+      if (c + 1 >= c2 && c + 1 < c2 + w2) v1 = src2[r * src2_ld + (c + 1 - c2)];
+    }
     __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
     *reinterpret_cast<__nv_bfloat162*>(dst + r * dst_ld + c) = h;
     if (planes > 1) {

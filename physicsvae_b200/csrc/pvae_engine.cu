@@ -101,6 +101,7 @@ struct GemmDesc {
   int passes = 1;
   bool split = false;     // split K over CTAs (wgrad)
   bool mseg = false;      // A[0] / A[1] are M segments (MN-major wgrad of a two-segment input) instead of K segments
+  int m_gap0 = 0, m_gap = 0;   // rows [m_gap0, m_gap0 + m_gap) of D do not exist in the output (alignment gap of a fused input), later rows move up
   EpiParams epi;
   GemmDesc() { memset(&epi, 0, sizeof(epi)); }
 };
@@ -166,6 +167,7 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   if (d.nseg == 1) p.tmA[1] = p.tmA[0];
   p.b_n0 = d.b_n0;
   p.b_dyn = d.B.dyn;
+  p.m_gap0 = d.m_gap0; p.m_gap = d.m_gap;
   CKR(encode_map(&p.tmB, d.B, 64, d.b_major == MAJOR_K ? bn / cluster : BK));
   const int kb_total = p.kb[0] + p.kb[1];
   const int iters = kb_total * d.passes;
@@ -218,9 +220,15 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static const int log_level = getenv("PVAE_LOG_GEMM") ? atoi(getenv("PVAE_LOG_GEMM")) : 0;   // 1: print every launch, 2: and synchronise after it
+  if (log_level)
+    fprintf(stderr, "[pvae_gemm] epi %d act %d tma %d cg %d | M %d N %d K %d+%d majors %d%d passes %d | m_tiles %d n_tiles %d bn %d splits %d grid %d | b_k0 %d,%d b_n0 %d mseg %d\n",
+            p.epi.type, p.epi.act, (int)tma, cluster, d.M, d.N, d.K[0], d.nseg > 1 ? d.K[1] : 0, d.a_major, d.b_major, d.passes, p.m_tiles, n_tiles, bn,
+            splits, grid, p.b_k0[0], p.b_k0[1], p.b_n0, p.m_seg_tiles);
   CK(cudaLaunchKernelEx(&cfg, fn, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
+  if (log_level >= 2) CK(cudaStreamSynchronize(st));
   return PVAE_OK;
 }
 
@@ -261,7 +269,7 @@ struct pvae_engine {
   Net nets[PVAE_NUM_NETS];
   int planes = 1, passes = 1;
   int max_batch = 0;
-  int dsb = 0, dsbp = 0, da = 0, z = 0, te_out = 0;   // dsbp: 128-byte aligned column where s_{t+1} starts inside a transition row
+  int dsb = 0, dsb8 = 0, dsbp = 0, da = 0, z = 0, te_out = 0;   // dsbp: 128-byte aligned column where s_{t+1} starts inside a transition row
   // workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -418,6 +426,7 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
         // the operand that comes from the resident buffer walks the batch along k: the dynamic cursor applies to its rows
         d.A[0] = (l == 0) ? in.seg[0] : ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
         d.M = d.A[0].width;
+        if (l == 0 && net.k1 && d.M > net.k0) { d.m_gap0 = net.k0; d.m_gap = net.K0pad - net.k0; }   // fused (first | gap | second) input row
       }
       CKR(launch_gemm(h->dev, d, st));
     }
@@ -528,10 +537,15 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
   h->max_batch = desc->max_batch;
   h->dsb = desc->dim_state_body; h->da = desc->dim_action; h->z = desc->latent_dim;
   h->te_out = desc->latent_prior ? 2 * h->z : h->z;
-  // s_t and s_{t+1} each start on a 128-byte boundary and rows are whole cache lines, so that every 64-column TMA box row
-  // of the resident buffer is exactly one L2 line (a 16-byte-aligned 800 B row stride made every box row straddle two)
-  h->dsbp = rup(h->dsb, 64);
-  h->tx_ld = 2 * h->dsbp;
+  // A resident transition row is (s_t | 0.. | a_t | 0.. | s_{t+1} | 0..): s_t and s_{t+1} each start on a 128-byte boundary and rows
+  // are whole cache lines, so that every 64-column TMA box row is exactly one L2 line (a 16-byte-aligned 800 B row stride made every
+  // box row straddle two).  a_t sits behind s_t at the next 16-byte boundary (TMA box coordinates must be 16-byte aligned, and the
+  // layer-0 shadow weights use the same column numbering), which makes the world model's input cat[s_t, a_t] ONE K segment of
+  // the row (200 + 45 = 245 columns = 4 k-blocks instead of 4 + 1, and two instead of three M tiles in the layer-0 weight
+  // gradient); GEMMs that want s_t alone describe the row with a 197-column tensor map and the hardware zero-fills the rest.
+  h->dsb8 = rup(h->dsb, 8);
+  h->dsbp = rup(h->dsb8 + h->da, 64);
+  h->tx_ld = h->dsbp + rup(h->dsb, 64);
   h->ty_ld = rup(h->da, 64);
   for (int n = 0; n < PVAE_NUM_NETS; ++n) {
     Net& net = h->nets[n];
@@ -546,14 +560,17 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
       default: net.k0 = h->dsb; net.k1 = h->dsb; break;
     }
     net.in_dim = net.k0 + net.k1;
-    net.K0pad = rup(net.k0, 64);
+    // layer-0 shadow columns: the second input segment's weights start at the next 16-byte boundary behind the first one's (a TMA
+    // box coordinate must be a multiple of 16 bytes: an odd start raises an illegal-instruction fault) -- a two-segment A operand
+    // addresses them at k offset K0pad, a one-segment A operand that keeps the same gap (resident rows) sees one K range
+    net.K0pad = rup(net.k0, 8);
     int64_t goff = 0;
     for (int l = 0; l < nd.n_layers; ++l) {
       if (nd.out_dims[l] <= 0 || nd.acts[l] < 0 || nd.acts[l] > PVAE_ACT_SWISH) { delete h; return fail(PVAE_ERR_INVALID, "net %d layer %d: bad size/activation", n, l); }
       net.in_dims[l] = l == 0 ? net.in_dim : nd.out_dims[l - 1];
       net.out_dims[l] = nd.out_dims[l];
       net.acts[l] = nd.acts[l];
-      net.kpad[l] = l == 0 ? net.K0pad + (net.k1 ? rup(net.k1, 64) : 0) : rup(net.in_dims[l], 64);
+      net.kpad[l] = l == 0 ? rup(net.K0pad + net.k1, 64) : rup(net.in_dims[l], 64);
       net.gW[l] = goff; goff += (int64_t)net.in_dims[l] * net.out_dims[l];
       net.gb[l] = goff; goff += net.out_dims[l];
       net.wsh_ps[l] = (int64_t)net.out_dims[l] * net.kpad[l];
@@ -698,11 +715,13 @@ int pvae_ingest(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t dst_row,
   const int64_t xt = n_rows * (h->tx_ld / 2), yt = n_rows * (h->ty_ld / 2);
   if (x_is_f64)
     ingest_kernel<double><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const double*>(x_raw_dev), 2 * h->dsb, 2 * h->dsb, h->dsb, h->dsbp,
+                                                                         y_raw_dev, h->da, h->da, h->dsb8,
                                                                          xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
   else
     ingest_kernel<float><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const float*>(x_raw_dev), 2 * h->dsb, 2 * h->dsb, h->dsb, h->dsbp,
+                                                                        y_raw_dev, h->da, h->da, h->dsb8,
                                                                         xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
-  ingest_kernel<float><<<grid_for(yt, 256, h->dev.sms), 256, 0, st>>>(y_raw_dev, h->da, h->da, h->da, 1 << 30, yb + dst_row * h->ty_ld, h->ty_ld,
+  ingest_kernel<float><<<grid_for(yt, 256, h->dev.sms), 256, 0, st>>>(y_raw_dev, h->da, h->da, h->da, 1 << 30, nullptr, 0, 0, 0, yb + dst_row * h->ty_ld, h->ty_ld,
                                                                       buf_rows * h->ty_ld, h->planes, n_rows);
   g_launches.fetch_add(2, std::memory_order_relaxed);
   CK(cudaGetLastError());
@@ -751,10 +770,9 @@ int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pv
   if (!wm.grad) return fail(PVAE_ERR_STATE, "world model has no gradient buffer bound");
   CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
   CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));
-  NetIO in;
-  in.nseg = 2;
-  in.seg[0] = tx_view(h, 0, h->dsb);
-  in.seg[1] = ty_view(h, h->da);
+  NetIO in;                       // cat[s_t, a_t] (train_physics_vae.py:412-413) = the first dsb8 + da columns of a resident row
+  in.nseg = 1;
+  in.seg[0] = tx_view(h, 0, h->dsb8 + h->da);
   const int L = wm.n_layers;
   EpiParams last;
   memset(&last, 0, sizeof(last));

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <type_traits>
 
 namespace pvae {
 
@@ -92,6 +93,7 @@ struct GemmParams {
   // M segments (MN-major A only, wgrad of a layer whose input is a virtual concat): M tiles [0, m_seg_tiles) come from
   // tmA[0], the rest from tmA[1]; a segment-1 tile's rows land in the output at row m_seg_out0 + local row.  0 = off.
   int32_t m_seg_tiles, m_seg_rows[2], m_seg_out0;
+  int32_t m_gap0, m_gap;           // rows [m_gap0, m_gap0 + m_gap) of D are an alignment gap of the A operand: not stored, later rows move up
   int32_t passes;                  // 1 = bf16, 3 = bf16x3
   int32_t m_tiles, n_tiles, bn, splits;
   int32_t dbg;                     // PVAE_DBG bit mask: skip parts of the TMA epilogue (timing experiments only, results are wrong)
@@ -310,6 +312,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float a, float b) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// two fp32 additions in one instruction (FADD2 on sm_100): (a0, a1) += (b0, b1)
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tadd.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+// per 16-bit half: 0xffff if the bf16 value is > 0, else 0
+__device__ __forceinline__ uint32_t bf16x2_gt0(uint32_t a) {
+  uint32_t d;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(0u));
+  return d;
+}
+// ReLU sign-bit mask word of one 32-column chunk of one row.  Column c = 4 s + 2 h + e (s = 0..7, h, e = 0 / 1) lives in bit
+// 8 (2 e + h) + 7 - s: the word shifted left by s has the bits of columns 4 s .. 4 s + 3 in the sign positions of bytes
+// 0 (h=0,e=0), 1 (h=1,e=0), 2 (h=0,e=1), 3 (h=1,e=1), from where one prmt (sign-replicating mode) per bf16 pair makes the AND mask.
+__device__ __forceinline__ constexpr uint32_t relu_mask_bit(int c) { return 1u << (8 * (2 * (c & 1) + ((c >> 1) & 1)) + 7 - (c >> 2)); }
 // Column sums of a 32 x 32 bf16 slab (32 rows of 64 B, 64B swizzle) on the legacy tensor path: ones[16 x 32] . slab, i.e.
 // per 8-column group one ldmatrix.x4.trans (lane l supplies the address of its own row's 16-byte piece) feeding two
 // mma.sync m16n8k16.  Returns the sum of column `lane`.  `piece_addr(j)` = shared address of piece j of this lane's row.
@@ -550,10 +567,17 @@ struct KRun {
 // PVAE_DBG bit 5: per-unit clock64 stamps of the three roles of every CTA (first TRACE_UNITS units), read back through
 // pvae_debug_trace().  slots: 0 MMA loop top, 1 tempty acquired, 2 first operands landed, 3 last k-block issued,
 // 4 epilogue before tfull wait, 5 accumulator ready, 6 epilogue done, 7 producer issued the unit's last copy.
+// The hooks (role timeline + the epilogue-skipping PVAE_DBG switches) are compiled in only with -DPVAE_DEBUG_HOOKS: their tests,
+// the trace index division and the stamps cost the hot epilogue loop ~15 % of its instructions.
+#ifdef PVAE_DEBUG_HOOKS
+constexpr bool DEBUG_HOOKS = true;
+#else
+constexpr bool DEBUG_HOOKS = false;
+#endif
 constexpr int TRACE_UNITS = 16, TRACE_CTAS = 160;
 __device__ unsigned long long g_trace[TRACE_CTAS * TRACE_UNITS * 8];
 __device__ __forceinline__ void trace_stamp(int dbg, int k, int slot) {
-  if ((dbg & 32) && k < TRACE_UNITS && blockIdx.x < TRACE_CTAS) g_trace[((int)blockIdx.x * TRACE_UNITS + k) * 8 + slot] = clock64();
+  if (DEBUG_HOOKS && (dbg & 32) && k < TRACE_UNITS && blockIdx.x < TRACE_CTAS) g_trace[((int)blockIdx.x * TRACE_UNITS + k) * 8 + slot] = clock64();
 }
 
 // The work units of one CTA (pair): u = unit0, unit0 + stride, ... numbered split-major / M-tile / N-tile-minor.  The
@@ -709,7 +733,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
-      if (lane == 0) trace_stamp(p.dbg, (u - unit0) / unit_stride, 7);
+      if (DEBUG_HOOKS && lane == 0) trace_stamp(p.dbg, (u - unit0) / unit_stride, 7);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA of the pair only) ================================
@@ -741,7 +765,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
         const int it_end = w.it_end();
         int it = w.it_begin();
-        const int tk = (p.dbg & 32) ? (u - unit0) / unit_stride : 0;
+        const int tk = (DEBUG_HOOKS && (p.dbg & 32)) ? (u - unit0) / unit_stride : 0;
         if (lane == 0) trace_stamp(p.dbg, tk, 0);
         mbar_wait<W_TEMPTY>(tempty_bar(acc), acc_phase ^ 1u);          // every epilogue warp (of both CTAs) has drained this stage
         tc_fence_after();
@@ -759,7 +783,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             tail = tail > 4 ? 4 : (tail < 1 ? 1 : tail);
           }
           const int n_full = tail < 4 ? run.n - 1 : run.n;
-          if ((p.dbg & 32) && first_kb) {          // (trace only) when did the unit's first operands land?
+          if (DEBUG_HOOKS && (p.dbg & 32) && first_kb) {          // (trace only) when did the unit's first operands land?
             mbar_wait<W_FULL>(full_bar(stage), phase);
             if (lane == 0) trace_stamp(p.dbg, tk, 2);
             first_kb = false;
@@ -811,6 +835,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         row_ok = local < p.m_seg_rows[s1];
         row = (s1 ? p.m_seg_out0 : 0) + local;
       }
+      if (p.m_gap && row >= p.m_gap0) {            // (s_t | gap | a_t) input rows of the world model's layer-0 weight gradient
+        row_ok = row_ok && row >= p.m_gap0 + p.m_gap;
+        row -= p.m_gap;
+      }
       // operands of this warp's (at most two) chunks that do not depend on the accumulator: fetched while the main loop runs
       float pre_bias[2] = {0.f, 0.f};
       uint32_t pre_mask[2] = {0u, 0u};
@@ -837,7 +865,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           __syncwarp();
         }
       }
-      const int tk = (p.dbg & 32) ? (u - unit0) / unit_stride : 0;
+      const int tk = (DEBUG_HOOKS && (p.dbg & 32)) ? (u - unit0) / unit_stride : 0;
       if (ew == 0 && lane == 0) trace_stamp(p.dbg, tk, 4);
       mbar_wait<W_TFULL>(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -865,32 +893,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         }
       } else {
         // Each warp stages its 32 x 32 bf16 chunk in a private 2 KiB slab and stores it with one TMA instruction -- no
-        // cross-warp synchronisation.
-#pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
-          const int c = cgrp + 4 * j;
-          if (c >= nchunks) break;                // warp-uniform
-          const int col0 = n_tile * bn + c * 32;
-          if (col0 >= n_valid) break;             // warp-uniform
+        // cross-warp synchronisation.  The (at most two) chunks of a warp are two compile-time instances of one body, so that
+        // their prefetched operands and bias-gradient accumulators are plain registers.
+        const uint32_t tmem_unit = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + cgrp * 32);
+        const int col_unit = n_tile * bn + cgrp * 32;
+        const int arow0 = (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32;      // first row of this warp's slab in the aux / output tensor
+        auto chunk = [&](auto jc) {
+          constexpr int J = decltype(jc)::value;
+          const int c = cgrp + 4 * J;
+          const int col0 = col_unit + 128 * J;
+          if (c >= nchunks || col0 >= n_valid) return;              // warp-uniform
           int nv = n_valid - col0; nv = nv > 32 ? 32 : nv;
           const int tile_nv = bn - c * 32;        // columns of this chunk that belong to this tile
           if (tile_nv < nv) nv = tile_nv;
-          const uint32_t mbits = j ? pre_mask[1] : pre_mask[0];
-          const float bias_l = j ? pre_bias[1] : pre_bias[0];     // lane -> bias of column lane of the chunk
-          if (HAS_AUX && j != 0) {                // second chunk of the tile: the aux load is exposed
+          const uint32_t mbits = pre_mask[J];
+          if (HAS_AUX && J != 0) {                // second chunk of the tile: the aux load is exposed
             tma_store_wait_read<0>();
             __syncwarp();
             if (elect_one()) {
               mbar_expect_tx(auxfull_bar(ew), SLAB_BYTES);
-              tma_load_3d<1>(slab, &p.tmAux, auxfull_bar(ew), col0, (e.aux_dyn ? row0 : 0) + m_tile * BM + q * 32, 0);
+              tma_load_3d<1>(slab, &p.tmAux, auxfull_bar(ew), col0, arow0, 0);
             }
             __syncwarp();
           }
           float v[32];
           {
             uint32_t raw[32];
-            if (!(p.dbg & 16)) {
-              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + c * 32), raw);
+            if (!(DEBUG_HOOKS && (p.dbg & 16))) {
+              tmem_ld32(tmem_unit + 128u * J, raw);
               tmem_ld_wait();
             } else {
 #pragma unroll
@@ -899,14 +929,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
           }
-          if (bias && !(p.dbg & 1)) {
+          if (bias && !(DEBUG_HOOKS && (p.dbg & 1))) {
             __syncwarp();
-            bias_s[lane] = bias_l;
+            bias_s[lane] = pre_bias[J];           // lane -> bias of column lane of the chunk
             __syncwarp();
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + g * 4);
-              v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
+              fadd2(v[g * 4 + 0], v[g * 4 + 1], b4.x, b4.y);
+              fadd2(v[g * 4 + 2], v[g * 4 + 3], b4.z, b4.w);
             }
           }
           uint32_t pk[16];                        // the chunk's row as packed bf16 pairs
@@ -922,26 +953,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = (ACT == ACT_RELU) ? pack_bf16x2_relu(v[2 * i], v[2 * i + 1]) : pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            if (ACT == ACT_RELU && e.mask && row_ok && !(p.dbg & 2)) {
-              // sign-bit mask from the packed non-negative results: a half is > 0 iff adding 0x7fff carries into its bit 15.
-              // Word layout: bit i = column 2 i, bit 16 + i = column 2 i + 1 (private to this kernel's dgrad epilogue).
-              uint32_t m0 = 0u, m1 = 0u;
+            if (ACT == ACT_RELU && e.mask && row_ok && !(DEBUG_HOOKS && (p.dbg & 2))) {
+              // sign-bit mask from the packed results: one packed compare + one (a & imm) | m per pair; layout: relu_mask_bit()
+              uint32_t m = 0u;
 #pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                m0 |= ((pk[i] + 0x7FFF7FFFu) & 0x80008000u) >> (15 - i);
-                m1 |= ((pk[i + 1] + 0x7FFF7FFFu) & 0x80008000u) >> (14 - i);
-              }
-              e.mask[(int64_t)(col0 >> 5) * e.mask_ld + row] = m0 | m1;
+              for (int i = 0; i < 16; ++i) m |= bf16x2_gt0(pk[i]) & (relu_mask_bit(2 * i) | relu_mask_bit(2 * i + 1));
+              e.mask[(int64_t)(col0 >> 5) * e.mask_ld + row] = m;
             }
           } else {
             // aux values (MSE target / forward activation) are consumed piece by piece to keep the register footprint small
             auto aux_piece = [&](int g, float (&y)[8]) {
               const uint4 qv = *reinterpret_cast<const uint4*>(srow + ((g ^ sw) << 4));
-              const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+              const uint32_t w4[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                y[2 * t]     = __uint_as_float(w[t] << 16);
-                y[2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u);
+                y[2 * t]     = __uint_as_float(w4[t] << 16);
+                y[2 * t + 1] = __uint_as_float(w4[t] & 0xFFFF0000u);
               }
             };
             if (HAS_AUX) {
@@ -977,7 +1004,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
               }
               if (USE_MASK && e.out_f32 != nullptr) {   // (an fp32 copy wants the masked values themselves)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = ((mbits >> ((i >> 1) + 16 * (i & 1))) & 1u) ? v[i] : 0.f;   // mask is 0 for rows >= m_valid
+                for (int i = 0; i < 32; ++i) v[i] = (mbits & relu_mask_bit(i)) ? v[i] : 0.f;   // mask is 0 for rows >= m_valid
               } else if (!USE_MASK && ACT != ACT_LINEAR) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -996,18 +1023,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             if (HAS_AUX) __syncwarp();            // every lane has read the aux slab before it is overwritten below
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            if (USE_MASK && !(p.dbg & 2)) {
-              // ReLU': bit i / bit 16 + i of the mask word gate the low / high half of pair i -- shift them onto the sign bits of
-              // bytes 1 / 3 and let prmt replicate the signs over the two halves
+            if (USE_MASK && !(DEBUG_HOOKS && (p.dbg & 2))) {
+              // ReLU': the mask word shifted left by s carries the bits of pairs 2 s / 2 s + 1 in the byte sign positions
+              // (relu_mask_bit()); prmt in sign-replicating mode turns two of them into the AND mask of a bf16 pair
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                uint32_t m;
-                asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(mbits << (15 - i)));
-                pk[i] &= m;
+              for (int s = 0; s < 8; ++s) {
+                const uint32_t t = mbits << s;
+                uint32_t m0, m1;
+                asm("prmt.b32 %0, %1, %1, 0xAA88;" : "=r"(m0) : "r"(t));
+                asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m1) : "r"(t));
+                pk[2 * s] &= m0;
+                pk[2 * s + 1] &= m1;
               }
             }
           }
-          if (p.dbg & 4) continue;
+          if (DEBUG_HOOKS && (p.dbg & 4)) return;
           if (!HAS_AUX) {                         // (with aux the slab was already claimed before the aux load)
             tma_store_wait_read<0>();             // bulk groups are per thread: only the electing lane ever has pending ones
             __syncwarp();
@@ -1024,11 +1054,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             }
             __syncwarp();
           }
-          if (EPI != EPI_STORE && e.colsum && !(p.dbg & 8)) {
-            // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> column lane.  The sums stay in registers
-            // (one accumulator per (N tile, chunk) this warp can meet) until the end of the kernel: per-chunk red.global.add
-            // to the same few cache lines from every CTA serialises in L2 (65536 warp-wide reds onto 32 lines for a 1024-wide layer).
-            // (columns >= nv of the slab are zero, rows >= m_valid too)
+          if (EPI != EPI_STORE && e.colsum && !(DEBUG_HOOKS && (p.dbg & 8))) {
+            // bias gradient: column sums of the staged (bf16-rounded) slab; lane -> column slab_colsum_col(lane).  The sums stay
+            // in registers (one accumulator per (N tile, chunk) this warp can meet) until the end of the kernel: per-chunk
+            // red.global.add to the same few cache lines from every CTA serialises in L2 (65536 warp-wide reds onto 32 lines for a
+            // 1024-wide layer).  (columns >= nv of the slab are zero, rows >= m_valid too)
             // Short-K GEMMs leave the tensor pipe idle most of the time: there the sums ride on mma.sync (ones . slab); with a
             // long K the legacy MMAs stall the tcgen05 stream (measured: 1024-deep dgrad 100 -> 123 us), so lanes add up columns.
             float sum = 0.f;
@@ -1046,15 +1076,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
               sum = (part[0] + part[1]) + (part[2] + part[3]);
             }
             if (n_tile < CS_TILES) {
-              const int key = n_tile * 2 + j;
 #pragma unroll
-              for (int k = 0; k < 2 * CS_TILES; ++k) cs_acc[k] += (k == key) ? sum : 0.f;
+              for (int t = 0; t < CS_TILES; ++t) cs_acc[2 * t + J] += (n_tile == t) ? sum : 0.f;
             } else if (slab_colsum_col(lane) < nv) {
               atomicAdd(e.colsum + col0 + slab_colsum_col(lane), sum);
             }
             __syncwarp();
           }
-        }
+        };
+        chunk(std::integral_constant<int, 0>{});
+        chunk(std::integral_constant<int, 1>{});
       }
       if (ew == 0 && lane == 0) trace_stamp(p.dbg, tk, 6);
       tc_fence_before();

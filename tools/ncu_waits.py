@@ -6,7 +6,7 @@ ks = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)
 seen = set()
 for which in range(len(ks) - 1):
     s, e = ks[which], ks[which + 1]
-    if which % 2: continue
+    pass
     H = rows[s + 1]; data = [r for r in rows[s + 2:e] if len(r) > 5]
     if not data: continue
     iaddr, isamp, isrc, iex = H.index("Address"), H.index("# Samples"), H.index("Source"), H.index("Instructions Executed")

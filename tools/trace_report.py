@@ -1,6 +1,6 @@
 """Summarise gpurun_out/trace_<idx>.npy files (tools/gpu_trace.sh): per-unit role timeline of a GEMM launch."""
 import sys, numpy as np
-names = {27: "fwd L0", 28: "fwd L1", 29: "fwd L2 MSE", 30: "wgrad L2", 31: "dgrad L1", 32: "wgrad L1", 33: "dgrad L0", 34: "wgrad L0 s", 35: "wgrad L0 a"}
+names = {24: "fwd L0", 25: "fwd L1", 26: "fwd L2 MSE", 27: "wgrad L2", 28: "dgrad L1", 29: "wgrad L1", 30: "dgrad L0", 31: "wgrad L0"}
 for idx in sorted(names):
     try:
         t = np.load("gpurun_out/trace_%d.npy" % idx).reshape(160, 16, 8).astype(np.int64)
