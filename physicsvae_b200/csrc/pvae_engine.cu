@@ -113,6 +113,8 @@ struct Device {
   int tma_epilogue = 1;   // bf16 outputs leave through shared memory + TMA stores (PVAE_TMA_EPILOGUE=0 disables)
   int cluster = 2;        // CTA pairs run tcgen05.mma.cta_group::2 on two adjacent M tiles (PVAE_CLUSTER=1 disables)
   int dbg = 0;            // PVAE_DBG: epilogue timing experiments (see GemmParams::dbg)
+  int bn_cap = MAX_BN;    // PVAE_BN_CAP: widest N tile (experiments)
+  int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
@@ -143,13 +145,14 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
     if (sel && atol(sel) == gemm_idx) p.dbg |= 32;
     ++gemm_idx;
   }
-  int n_tiles = cdiv(d.N, MAX_BN);
+  int n_tiles = cdiv(d.N, dev.bn_cap);
   // bn: K-major B -- one N tile: any multiple of 16 (the TMA store clips at the tensor edge), several: whole 64-column
   // sub-tiles; MN-major B -- whole 64-column TMA boxes per CTA (each CTA of a pair stages bn / 2 columns)
   int bn;
   if (d.b_major == MAJOR_MN) bn = rup(cdiv(d.N, n_tiles), (n_tiles > 1 ? 64 : dev.mn_bn_align) * cluster);
   else bn = rup(cdiv(d.N, n_tiles), n_tiles > 1 ? 64 : 16);
   if (bn > MAX_BN) bn = MAX_BN;
+  p.cs_mma = dev.cs_mma;
   n_tiles = cdiv(d.N, bn);
   p.n_tiles = n_tiles;
   p.bn = bn;
@@ -514,6 +517,10 @@ static int init_device(Device& dev, int device) {
   if (env) dev.tma_epilogue = atoi(env) != 0;
   env = getenv("PVAE_DBG");
   if (env) dev.dbg = atoi(env);
+  env = getenv("PVAE_BN_CAP");
+  if (env) { int v = atoi(env); if (v >= 64 && v <= MAX_BN && v % 64 == 0) dev.bn_cap = v; }
+  env = getenv("PVAE_CS_MMA");
+  if (env) dev.cs_mma = atoi(env) != 0;
   env = getenv("PVAE_CLUSTER");
   if (env) dev.cluster = atoi(env) == 1 ? 1 : 2;
   CKR(resolve_driver());

@@ -97,6 +97,7 @@ struct GemmParams {
   int32_t passes;                  // 1 = bf16, 3 = bf16x3
   int32_t m_tiles, n_tiles, bn, splits;
   int32_t dbg;                     // PVAE_DBG bit mask: skip parts of the TMA epilogue (timing experiments only, results are wrong)
+  int32_t cs_mma;                  // bias-gradient column sums: 1 = mma.sync (ones . slab), 0 = lanes add columns, -1 = by K depth
   int32_t cg;                      // 1, or 2: CTA pairs on adjacent M tiles run one 256-row tcgen05.mma.cta_group::2 (kernel template CG)
   const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
   CUtensorMap tmOut;               // TMA-store epilogue: the primary bf16 output, box 64 cols x 32 rows (one warp's slab)
@@ -811,7 +812,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     int acc = 0; uint32_t acc_phase = 0;
     double loss_local = 0.0;
     uint32_t aux_phase = 0;
-    const bool cs_mma = kb_total <= 8;            // see the column-sum code below
+    const bool cs_mma = p.cs_mma > 0;              // see the column-sum code below
     constexpr int CS_TILES = 4;                   // N tiles whose bias-gradient column sums are kept in registers
     float cs_acc[2 * CS_TILES];
 #pragma unroll
@@ -1059,8 +1060,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             // in registers (one accumulator per (N tile, chunk) this warp can meet) until the end of the kernel: per-chunk
             // red.global.add to the same few cache lines from every CTA serialises in L2 (65536 warp-wide reds onto 32 lines for a
             // 1024-wide layer).  (columns >= nv of the slab are zero, rows >= m_valid too)
-            // Short-K GEMMs leave the tensor pipe idle most of the time: there the sums ride on mma.sync (ones . slab); with a
-            // long K the legacy MMAs stall the tcgen05 stream (measured: 1024-deep dgrad 100 -> 123 us), so lanes add up columns.
+            // Lanes add up columns.  The alternative (PVAE_CS_MMA=1: ones . slab on mma.sync) stalls the tcgen05 stream that shares
+            // the tensor pipe: measured 1024-deep dgrad 98 -> 118 us, 197-deep dgrad 54 -> 57 us.
             float sum = 0.f;
             if (cs_mma) {
               sum = slab_colsum32([&](int jp) { return slab + (uint32_t)lane * 64u + (uint32_t)((jp ^ sw) << 4); }, lane);
