@@ -69,66 +69,119 @@ def synthetic_arrays(cfg, n, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled in-process every ~2 ms (the
+    timed region of a short run lasts only tens of milliseconds, `nvidia-smi -lms` cannot resolve that); if NVML is not
+    importable the recipe's `nvidia-smi --query-gpu` loop is used instead."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.halt, self.source = index, [], None, threading.Event(), None
+
+    def _nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        self.source = "nvml"
+        while not self.halt.is_set():
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            try:
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            self.rows.append((time.time(), sm, mx, pw, mask))
+            time.sleep(0.002)
+
+    def _smi(self):
+        self.source = "nvidia-smi"
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                      "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        f = lambda v: float(v) if v.replace(".", "", 1).isdigit() else 0.0
+        for line in self.proc.stdout:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 7:
+                mask = sum(bit for (name, bit), v in zip(self.REASONS.items(), c[3:7]) if v.lower().startswith("active"))
+                self.rows.append((time.time(), f(c[0]), f(c[1]), f(c[2]), mask))
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+            self._nvml()
         except Exception:
-            pass
+            try:
+                self._smi()
+            except Exception:
+                pass
 
     def stop(self, t0, t1):
+        self.halt.set()
         if self.proc:
             self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 - 0.02 <= t <= t1 + 0.02 and len(r) >= 7] or [r for t, r in self.rows if len(r) >= 7]
+        self.join(timeout=1.0)
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        rows = inside or [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05] or self.rows
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
-        f = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
-        sm = [f(r[0]) for r in rows if f(r[0]) is not None]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": f(rows[0][1]), "samples": len(rows),
-                "power_w_max": max([f(r[2]) or 0 for r in rows]), "reasons": reasons}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        mask = 0
+        for r in rows:
+            mask |= r[4]
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_min_mhz": min(r[1] for r in rows), "sm_max_mhz": rows[0][2],
+                "samples": len(rows), "samples_inside_timed_region": len(inside), "power_w_max": max(r[3] for r in rows),
+                "reasons": [n for n, bit in self.REASONS.items() if mask & bit], "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port of train_physics_vae.TrainModel.compute_loss + backward + Adam)
 # --------------------------------------------------------------------------------------------------------------------
-def cpu_arm(cfg, phase, rows, steps, warmup, seed=0):
+def cpu_arm(cfg, phase, rows, steps, warmup, seed=0, min_seconds=0.0, max_seconds=150.0):
+    """`steps` timed mini-batch steps of `rows` transitions each through the oracle port on all host cores.  `min_seconds`:
+    keep stepping until that much time was measured (the cpu_baseline leg wants 10-30 s of CPU work); `max_seconds`: if the
+    requested run would take longer, the per-step sample shrinks (reported) so that the run still ends within minutes."""
     from oracle import pvae_oracle as orc
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(seed)
     m = orc.OracleModel(cfg["dsb"], cfg["da"], cfg["z"], orc.gen_layers(*cfg["te"]), orc.gen_layers(*cfg["md"]), orc.gen_layers(*cfg["wm"]))
-    X, Y = synthetic_arrays(cfg, rows, seed + 1)
-    tr = orc.OracleTrainer(m, X, Y, batch_size=rows, max_iter_world_model=0 if phase == "vae" else 10 ** 9)
-    for _ in range(warmup):
-        tr.step()
+
+    def trainer(n):
+        X, Y = synthetic_arrays(cfg, n, seed + 1)
+        return orc.OracleTrainer(m, X, Y, batch_size=n, max_iter_world_model=0 if phase == "vae" else 10 ** 9)
+    tr = trainer(rows)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    tr.step()
+    t1 = time.perf_counter() - t0
+    while rows > 256 and t1 * (steps + warmup) > max_seconds:
+        rows //= 2
+        tr = trainer(rows)
+        t0 = time.perf_counter()
         tr.step()
+        t1 = time.perf_counter() - t0
+    for _ in range(max(warmup - 1, 0)):
+        tr.step()
+    done, t0 = 0, time.perf_counter()
+    while done < steps or (time.perf_counter() - t0) < min_seconds:
+        tr.step()
+        done += 1
     dt = time.perf_counter() - t0
-    return rows * steps / dt, dt / steps * 1e3, cores
+    return rows * done / dt, dt / done * 1e3, cores, rows, done
 
 
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-    value, ms, cores = cpu_arm(cfg, args.phase, args.cpu_sample, steps, warmup)
-    from oracle import pvae_oracle as orc
-    sample = "%d steps of %d transitions (%s phase, %s dims), fp32 torch-CPU, compute_loss+backward+Adam+item" % (
-        steps, args.cpu_sample, args.phase, args.config)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    value, ms, cores, rows, steps = cpu_arm(cfg, args.phase, args.cpu_sample, steps, warmup)
+    sample = "%d steps of %d transitions (%s phase, %s dims), fp32 torch-CPU on %d threads, compute_loss+backward+Adam+item" % (
+        steps, rows, args.phase, args.config, cores)
     line = {"impl": "reference", "metric": "transitions/sec (world-model+VAE step)", "value": value, "unit": "transitions/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -386,10 +439,10 @@ def run_b200(args, cfg):
                 "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
                 "cuda_graph": graph is not None, "roofline": roofline, "loss_after": loss_after}
         if not args.no_cpu_baseline:
-            rows = args.cpu_sample
-            v, cms, cores = cpu_arm(cfg, phase, rows, 3, 1)
-            line["cpu_baseline"] = {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port",
-                                    "sample": "3 steps of %d transitions (%s phase), oracle port of compute_loss+backward+Adam, fp32 torch-CPU" % (rows, phase)}
+            v, cms, cores, rows, nsteps = cpu_arm(cfg, phase, args.cpu_sample, 3, 1, min_seconds=10.0)
+            line["cpu_baseline"] = {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port", "ms_per_step": cms,
+                                    "sample": "%d steps of %d transitions (%s phase, ~10 s), oracle port of compute_loss+backward+Adam+item, "
+                                              "fp32 torch-CPU on %d threads" % (nsteps, rows, phase, cores)}
         print(json.dumps(line), flush=True)
     # Teardown: a CUDA graph that captured NCCL work keeps the communicator busy and destroy_process_group() can block on
     # it forever; every rank is done with collectives here, so drop the graph and leave without the collective teardown.
