@@ -56,3 +56,17 @@ class PvaeAdam(torch.optim.Optimizer):
                                          "exp_avg_sq": exp_avg_sq[off:off + k].view_as(p)}
                     off += k
         return loss
+
+    # ---- resume support (the reference saves no optimizer state: a resumed run restarts the moments) ----
+    def flat_state_dict(self):
+        """{net name: {"exp_avg", "exp_avg_sq", "step"}} on the CPU + the learning rate the schedulers drive."""
+        return {"nets": {n: {"exp_avg": a.detach().cpu().clone(), "exp_avg_sq": b.detach().cpu().clone(), "step": c.detach().cpu().clone()}
+                         for n, (a, b, c) in self._flat_state.items()},
+                "lr": [float(g["lr"]) for g in self.param_groups]}
+
+    def load_flat_state_dict(self, sd):
+        for n, st in sd["nets"].items():
+            a, b, c = self._net_state(n)
+            a.copy_(st["exp_avg"]); b.copy_(st["exp_avg_sq"]); c.copy_(st["step"])
+        for g, lr in zip(self.param_groups, sd["lr"]):
+            g["lr"] = lr

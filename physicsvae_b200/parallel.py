@@ -7,12 +7,36 @@ import torch
 import torch.distributed as dist
 
 
-def world_size():
+_replicas = False      # sweep mode: the ranks of the job are independent trainers, no gradient exchange
+
+
+def set_replica_mode(flag):
+    """Sweep over grid points with one independent trainer per GPU (the role of Ray Tune's parallel trials,
+    train_physics_vae.py:264-285, 484-502): data-parallel sharding and the all-reduce are switched off."""
+    global _replicas
+    _replicas = bool(flag)
+
+
+def job_world_size():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
-def rank():
+def job_rank():
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def world_size():
+    """Ranks that share one trainer's mini-batches (1 in replica mode)."""
+    return 1 if _replicas else job_world_size()
+
+
+def rank():
+    return 0 if _replicas else job_rank()
+
+
+def sweep_points(n_points, r, world):
+    """Grid points trainer r of `world` replicas runs: round-robin, so that every point runs exactly once."""
+    return [i for i in range(n_points) if i % world == r]
 
 
 def shard_rows(lo, hi, r, world):

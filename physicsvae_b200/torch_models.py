@@ -46,11 +46,15 @@ except Exception:  # noqa
 
         def restore(self, checkpoint_path):
             self.load_checkpoint(checkpoint_path)
+            it = getattr(self, "_restored_iteration", None)
+            if it is not None:
+                self._iteration = it
 
         def stop(self):
             pass
 
 EPSILON = np.finfo(np.float32).eps
+TRAINER_STATE_FILE = "trainer_state.pt"
 
 
 def get_lr_scheduler(optimizer, name, params):
@@ -271,10 +275,36 @@ class TrainModel(_TrainableBase):
         os.makedirs(checkpoint_dir, exist_ok=True)
         checkpoint_path = os.path.join(checkpoint_dir, "model.pth")
         torch.save({k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}, checkpoint_path)
+        if self.config.get("save_trainer_state", False):
+            # beyond the reference (which restarts Adam's moments and the StepLR counter on resume):
+            # what a bit-faithful continuation needs, in a file the reference's loaders never look at
+            torch.save(self.trainer_state(), os.path.join(checkpoint_dir, TRAINER_STATE_FILE))
         return checkpoint_path
 
     def load_checkpoint(self, checkpoint_path):
         self.model.load_state_dict(torch.load(checkpoint_path, map_location="cpu"))
+        state_path = os.path.join(os.path.dirname(checkpoint_path), TRAINER_STATE_FILE)
+        if os.path.exists(state_path):
+            self.load_trainer_state(torch.load(state_path, map_location="cpu"))
+
+    def trainer_state(self):
+        opt = self.optimizer
+        return {"iter": self.iter, "training_iteration": getattr(self, "_iteration", self.iter),
+                "optimizer_kind": type(opt).__name__,
+                "optimizer": opt.flat_state_dict() if isinstance(opt, PvaeAdam) else opt.state_dict(),
+                "lr_scheduler": self.lr_scheduler.state_dict() if self.lr_scheduler else None}
+
+    def load_trainer_state(self, st):
+        self.iter = int(st["iter"])
+        self._restored_iteration = int(st.get("training_iteration", st["iter"]))
+        if st["optimizer_kind"] != type(self.optimizer).__name__:
+            raise ValueError("checkpoint was written with optimizer %s, this trainer uses %s" % (st["optimizer_kind"], type(self.optimizer).__name__))
+        if isinstance(self.optimizer, PvaeAdam):
+            self.optimizer.load_flat_state_dict(st["optimizer"])
+        else:
+            self.optimizer.load_state_dict(st["optimizer"])
+        if self.lr_scheduler and st.get("lr_scheduler") is not None:
+            self.lr_scheduler.load_state_dict(st["lr_scheduler"])
 
 
 class WorldModel(object):

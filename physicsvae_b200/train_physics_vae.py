@@ -65,6 +65,9 @@ def arg_parser():
     parser.add_argument("--latent_prior_type", type=str, action="append", default=["normal_zero_mean_one_std"])
     # engine knob (not in the reference): "bf16x3" reproduces fp32 results, "bf16" is the fast path
     parser.add_argument("--precision", type=str, default="bf16x3", choices=["bf16", "bf16x3"])
+    # multi-GPU launch (torchrun): "dp" = every trial is data-parallel over all ranks; "replicas" = the grid points of the
+    # sweep are spread over the ranks, one independent trainer per GPU (what Ray Tune's parallel trials do upstream)
+    parser.add_argument("--sweep_mode", type=str, default="dp", choices=["dp", "replicas"])
     return parser
 
 
@@ -282,11 +285,28 @@ class TrainModel(torch_models.TrainModel):
     def step(self):
         if self.iter == self.max_iter_world_model:
             # end-to-end learning of the VAE starts (train_physics_vae.py:342-350)
-            self.model.set_learnable_task_encoder(True)
-            self.model.set_learnable_motor_decoder(True)
-            self.model.set_learnable_world_model(False)
-            self.read_loss_fn_coeff(world=False)
+            self._enter_vae_phase()
         return super().step()
+
+    def _enter_vae_phase(self):
+        self.model.set_learnable_task_encoder(True)
+        self.model.set_learnable_motor_decoder(True)
+        self.model.set_learnable_world_model(False)
+        self.read_loss_fn_coeff(world=False)
+
+    def load_trainer_state(self, st):
+        """Resume: the phase is a function of the iteration counter (the switch fires when iter == max_iter_world_model)."""
+        super().load_trainer_state(st)
+        self._noise_step = int(st.get("noise_step", 0))
+        if self.iter > self.max_iter_world_model:
+            self._enter_vae_phase()
+            for p_ in self.model._world_model.parameters():      # a frozen net's stale gradient must not reach Adam
+                p_.grad = None
+
+    def trainer_state(self):
+        st = super().trainer_state()
+        st["noise_step"] = self._noise_step
+        return st
 
     def create_model(self, config):
         return create_model(config)
@@ -377,16 +397,28 @@ class TrainModel(torch_models.TrainModel):
         return checkpoint_path
 
 
+def latest_checkpoint(trial_dir):
+    """model.pth of the newest checkpoint_NNNNNN directory of a trial, or None."""
+    if not os.path.isdir(trial_dir):
+        return None
+    ck = sorted(d for d in os.listdir(trial_dir) if d.startswith("checkpoint_") and os.path.exists(os.path.join(trial_dir, d, "model.pth")))
+    return os.path.join(trial_dir, ck[-1], "model.pth") if ck else None
+
+
 def run_trial(config, max_iter, checkpoint_freq, trial_dir, restore=None):
     """What one Ray Tune trial does (train_physics_vae.py:484-502): train() until training_iteration == max_iter,
-    checkpoint every `checkpoint_freq` iterations and at the end; results go to result.json like Tune's JSON logger."""
+    checkpoint every `checkpoint_freq` iterations and at the end; results go to result.json like Tune's JSON logger.
+    `restore`: continue from that checkpoint (weights; with its trainer_state.pt also Adam moments, LR schedule, phase and
+    iteration counter -- upstream a resumed trial restarts those)."""
     os.makedirs(trial_dir, exist_ok=True)
+    config = dict(config)
+    config["save_trainer_state"] = True
     trainer = TrainModel(config)
     if restore:
         trainer.restore(restore)
-    last = None
+    last = restore
     with open(os.path.join(trial_dir, "result.json"), "a") as log:
-        for it in range(1, max_iter + 1):
+        for it in range(trainer.training_iteration + 1, max_iter + 1):
             result = trainer.train()
             log.write(json.dumps(result) + "\n")
             log.flush()
@@ -395,17 +427,37 @@ def run_trial(config, max_iter, checkpoint_freq, trial_dir, restore=None):
     return trainer, last
 
 
+def init_distributed(sweep_mode="dp"):
+    """Under torchrun (WORLD_SIZE > 1): one process per GPU, NCCL process group; "replicas" keeps the ranks independent."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    parallel.set_replica_mode(sweep_mode == "replicas")
+
+
 def main(argv=None):
     global args
     args = arg_parser().parse_args(argv)
     trainer_config = get_trainer_config(args)
     checkpoint = args.checkpoint
+    init_distributed(args.sweep_mode)
     if args.checkpoint is None:
         local_dir = os.path.expanduser(args.local_dir)
         name = args.name or "TrainModel"
-        for i, point in enumerate(resolve_grid(trainer_config)):
+        points = resolve_grid(trainer_config)
+        mine = parallel.sweep_points(len(points), parallel.job_rank(), parallel.job_world_size()) if args.sweep_mode == "replicas" \
+            else list(range(len(points)))
+        for i in mine:
             trial_dir = os.path.join(local_dir, name, "trial_%05d" % i)
-            _, checkpoint = run_trial(point, args.max_iter, args.checkpoint_freq, trial_dir)
+            restore = latest_checkpoint(trial_dir) if args.resume else None
+            _, checkpoint = run_trial(points[i], args.max_iter, args.checkpoint_freq, trial_dir, restore=restore)
     if args.output is not None:
         # the reference's --output branch instantiates the abstract base trainer and always fails (SURVEY.md F9);
         # here it exports the full state dict of the checkpoint

@@ -1,6 +1,7 @@
 """Parity tests proper (-m gpu): the sm_100a path, called through the C ABI, against the CPU oracle on the same seeded
 inputs, against the reference-generated golden fixtures, and -- at BASELINE.json's full sizes -- through size-independent
 properties.  Tolerance: north_star's rtol=1e-3 / atol=1e-5 for the fp32-accurate mode (bf16x3)."""
+import json
 import os
 import pickle
 
@@ -281,6 +282,33 @@ def test_trainer_trajectory_phase_switch_and_checkpoints(tmp_path):
     tr2.model.latent_prior_noise = False
     om2.latent_prior_noise = False
     P.assert_close("restored forward", tr2.compute_model(x.cuda()), om2.forward(x)[:, :5])
+
+
+def test_resume_continues_the_trajectory(tmp_path):
+    """run_trial with --resume semantics: 2 iterations + checkpoint + a NEW trainer restored from it + 3 more iterations ==
+    5 iterations straight (weights, Adam moments, StepLR counter, phase switch at iteration 3 and the iteration counter all
+    travel in trainer_state.pt; upstream a resumed trial restarts the optimizer)."""
+    from physicsvae_b200 import train_physics_vae as tp
+    f, data = _pickle(tmp_path)
+    tp.args = tp.arg_parser().parse_args(["--data_train", f, "--max_iter_world_model", "3", "--max_iter", "5", "--batch_size", "32",
+                                          "--latent_dim", "4"])
+    cfg = tp.resolve_grid(tp.get_trainer_config(tp.args))[0]
+    cfg.update(TE_width=16, MD_width=24, world_model_width=32, noise_seed=1, lr_schedule_params={"step_size": 2, "gamma": 0.5})
+    torch.manual_seed(5)
+    straight, _ = tp.run_trial(cfg, 5, 0, str(tmp_path / "straight"))
+    torch.manual_seed(5)
+    first, ck = tp.run_trial(cfg, 2, 2, str(tmp_path / "resumed"))
+    assert ck == tp.latest_checkpoint(str(tmp_path / "resumed")) and ck.endswith(os.path.join("checkpoint_000002", "model.pth"))
+    assert "trainer_state.pt" in os.listdir(os.path.dirname(ck))
+    torch.manual_seed(99)                                   # a different init: everything must come from the checkpoint
+    second, _ = tp.run_trial(cfg, 5, 0, str(tmp_path / "resumed"), restore=ck)
+    assert second.training_iteration == 5 and second.iter == 5 and not second.world_phase
+    assert abs(second.optimizer.param_groups[0]["lr"] - straight.optimizer.param_groups[0]["lr"]) < 1e-12
+    a, b = straight.model.state_dict(), second.model.state_dict()
+    for k in a:
+        P.assert_close("resumed " + k, b[k], a[k], rtol=1e-4, atol=1e-6)
+    lines = open(tmp_path / "resumed" / "result.json").read().strip().splitlines()
+    assert [json.loads(l)["training_iteration"] for l in lines] == [1, 2, 3, 4, 5]
 
 
 @pytest.mark.parametrize("weight_decay", [0.0, 0.01])

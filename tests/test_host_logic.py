@@ -227,3 +227,27 @@ def test_shard_rows_partition_and_weights():
         assert max(sizes) - min(sizes) <= 1 and max(sizes) <= parallel.max_shard_rows(hi - lo, world)
         w = [parallel.shard_weight(lo, hi, r, world) for r in range(world)]
         assert abs(sum(w) / world - 1.0) < 1e-12
+
+
+def test_sweep_replicas_partition_and_latest_checkpoint(tmp_path):
+    """`--sweep_mode replicas`: every grid point runs on exactly one rank; in that mode a trainer sees a world of one."""
+    from physicsvae_b200 import parallel
+    from physicsvae_b200 import train_physics_vae as tp
+    for n, world in [(1, 8), (5, 2), (8, 8), (9, 4)]:
+        parts = [parallel.sweep_points(n, r, world) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    parallel.set_replica_mode(True)
+    try:
+        assert parallel.world_size() == 1 and parallel.rank() == 0
+    finally:
+        parallel.set_replica_mode(False)
+    a = tp.arg_parser().parse_args(["--data_train", "x.pkl"])
+    assert a.sweep_mode == "dp" and a.resume is False
+    assert tp.latest_checkpoint(str(tmp_path / "missing")) is None
+    for it in (2, 10):
+        d = tmp_path / "trial" / ("checkpoint_%06d" % it)
+        d.mkdir(parents=True)
+        (d / "model.pth").write_bytes(b"")
+    (tmp_path / "trial" / "checkpoint_000011").mkdir()            # incomplete checkpoint directory: ignored
+    assert tp.latest_checkpoint(str(tmp_path / "trial")).endswith(os.path.join("checkpoint_000010", "model.pth"))
