@@ -290,6 +290,7 @@ struct pvae_engine {
   int tx_ld = 0, ty_ld = 0;
   // scalars
   double* acc = nullptr;    // [4] loss accumulators
+  unsigned int* adam_counter = nullptr;   // finished-blocks counter of adam_net_kernel
 };
 
 namespace pvae {
@@ -606,6 +607,8 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
     pvae_destroy(h);
     return fail(PVAE_ERR_CUDA, "cudaMalloc(scalars) failed");
   }
+  if (cudaMalloc(&h->adam_counter, sizeof(unsigned int)) == cudaSuccess) cudaMemset(h->adam_counter, 0, sizeof(unsigned int));
+  else h->adam_counter = nullptr;
   cudaMemset(h->dev.cursor, 0, sizeof(int32_t));
   cudaMemset(h->acc, 0, 4 * sizeof(double));
   h->ws_bytes = carve(h, nullptr);
@@ -619,6 +622,7 @@ int pvae_destroy(pvae_handle h) {
     for (int l = 0; l < h->nets[n].n_layers; ++l)
       if (h->nets[n].Wsh[l]) cudaFree(h->nets[n].Wsh[l]);
   if (h->acc) cudaFree(h->acc);
+  if (h->adam_counter) cudaFree(h->adam_counter);
   if (h->dev.cursor) cudaFree(h->dev.cursor);
   delete h;
   return PVAE_OK;
@@ -671,6 +675,36 @@ int pvae_adam_step(pvae_handle h, int net_id, uint32_t layer_mask, float* exp_av
   Net& net = h->nets[net_id];
   if (!net.bound || !net.grad) return fail(PVAE_ERR_STATE, "net %d has no parameters / gradient buffer bound", net_id);
   cudaStream_t st = (cudaStream_t)s;
+  {
+    // one launch over the whole flat buffer when the layers are laid out back to back ([W0 | b0 | W1 | b1 | ...], which is what
+    // physicsvae_b200 hands out) and 16-byte aligned; otherwise one launch per layer below
+    bool flat = net.n_layers <= 8 && h->adam_counter != nullptr;
+    for (int l = 0; l < net.n_layers && flat; ++l) {
+      if (net.b[l] != net.W[l] + (int64_t)net.in_dims[l] * net.out_dims[l]) flat = false;
+      if (l + 1 < net.n_layers && net.W[l + 1] != net.b[l] + net.out_dims[l]) flat = false;
+    }
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (flat && al16(net.W[0]) && al16(net.grad) && al16(exp_avg_dev) && al16(exp_avg_sq_dev)) {
+      AdamNet an;
+      memset(&an, 0, sizeof(an));
+      an.n_layers = net.n_layers;
+      an.total = net.grad_elems;
+      for (int l = 0; l < net.n_layers; ++l) {
+        AdamLayer& L = an.L[l];
+        L.off = net.gW[l]; L.out = net.out_dims[l]; L.in = net.in_dims[l];
+        L.k0 = l == 0 ? net.k0 : net.in_dims[l];
+        L.K0pad = l == 0 && net.k1 ? net.K0pad : net.kpad[l];
+        L.Kpad = net.kpad[l]; L.active = (layer_mask >> l) & 1u;
+        L.Wsh = net.Wsh[l]; L.ps = net.wsh_ps[l];
+      }
+      adam_net_kernel<<<grid_for((an.total + 3) / 4, 256, h->dev.sms), 256, 0, st>>>(
+          const_cast<float*>(net.W[0]), net.grad, exp_avg_dev, exp_avg_sq_dev, step_dev, h->adam_counter, lr, beta1, beta2, eps,
+          weight_decay, an, h->planes);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      CK(cudaGetLastError());
+      return PVAE_OK;
+    }
+  }
   add_scalar_kernel<<<1, 32, 0, st>>>(step_dev, 1.f);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   for (int l = 0; l < net.n_layers; ++l) {
