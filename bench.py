@@ -25,6 +25,7 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
+CPU_THREADS = 0
 CONFIGS = {
     "default": dict(dsb=197, da=45, z=32, te=(256, 2), md=(512, 3), wm=(1024, 2)),
     "wide": dict(dsb=512, da=128, z=32, te=(1024, 3), md=(1024, 3), wm=(1024, 3)),
@@ -37,7 +38,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch"],
+                    help="b200: this repo; reference: the reference algorithm on the host cores; torch: stock PyTorch-CUDA "
+                         "(cuBLAS bf16 nn.Linear autocast + autograd + fused Adam, graph-captured) as the library baseline")
     ap.add_argument("--phase", default="world", choices=["world", "vae"])
     ap.add_argument("--config", default="default", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=65536, help="mini-batch rows PER GPU")
@@ -45,6 +48,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="rows per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all cores; 1 with --cpu-sample 256 = configs[0])")
     return ap.parse_args()
 
 
@@ -146,7 +150,7 @@ def cpu_arm(cfg, phase, rows, steps, warmup, seed=0, min_seconds=0.0, max_second
     keep stepping until that much time was measured (the cpu_baseline leg wants 10-30 s of CPU work); `max_seconds`: if the
     requested run would take longer, the per-step sample shrinks (reported) so that the run still ends within minutes."""
     from oracle import pvae_oracle as orc
-    cores = os.cpu_count() or 1
+    cores = CPU_THREADS or os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(seed)
     m = orc.OracleModel(cfg["dsb"], cfg["da"], cfg["z"], orc.gen_layers(*cfg["te"]), orc.gen_layers(*cfg["md"]), orc.gen_layers(*cfg["wm"]))
@@ -493,10 +497,92 @@ def run_b200(args, cfg):
         os._exit(0)
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# library baseline: the same training step written with stock PyTorch on the same GPU (not part of the driver contract)
+# --------------------------------------------------------------------------------------------------------------------
+def run_torch(args, cfg):
+    """World / VAE step with nn.Linear under bf16 autocast (cuBLASLt), autograd, torch.optim.Adam(fused, capturable), the whole
+    step captured in one CUDA graph; inputs pre-concatenated and resident in bf16 (the friendliest setting for the library)."""
+    import torch.nn as nn
+    from oracle import pvae_oracle as orc
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, phase = args.batch, args.phase
+    dsb, da, z = cfg["dsb"], cfg["da"], cfg["z"]
+
+    def mlp(i, w, d, o):
+        layers, k = [], i
+        for _ in range(d):
+            layers += [nn.Linear(k, w), nn.ReLU()]
+            k = w
+        return nn.Sequential(*layers, nn.Linear(k, o)).to(dev)
+    torch.manual_seed(0)
+    te, md, wm = mlp(2 * dsb, *cfg["te"], 2 * z), mlp(dsb + z, *cfg["md"], da), mlp(dsb + da, *cfg["wm"], dsb)
+    s1 = torch.randn(B, dsb, device=dev, dtype=torch.bfloat16)
+    s2 = (s1.float() + 0.05 * torch.randn(B, dsb, device=dev)).bfloat16()
+    a = (torch.rand(B, da, device=dev) * 2 - 1).bfloat16()
+    s1a, s12 = torch.cat([s1, a], 1), torch.cat([s1, s2], 1)
+    train = list(wm.parameters()) if phase == "world" else list(te.parameters()) + list(md.parameters())
+    if phase == "vae":
+        for p_ in wm.parameters():
+            p_.requires_grad_(False)
+    opt = torch.optim.Adam(train, lr=torch.tensor(5e-4, device=dev), fused=True, capturable=True)
+    mse = nn.functional.mse_loss
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if phase == "world":
+                loss = mse(wm(s1a).float(), s2.float())
+            else:
+                h = te(s12).float()
+                mu, lv = h[:, :z], h[:, z:]
+                zz = mu + torch.randn_like(mu) * torch.exp(0.5 * lv)
+                act = md(torch.cat([s1, zz.bfloat16()], 1))
+                fut = wm(torch.cat([s1, act], 1))
+                kl = torch.mean(-0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp(), dim=1))
+                loss = mse(act.float(), a.float()) + kl + 1e-3 * mse(fut.float(), s2.float())
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(max(args.warmup, 3)):
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    fl = orc.flops_per_transition(dsb, da, z, [cfg["te"][0]] * cfg["te"][1], [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
+    flops = (fl[0] if phase == "world" else fl[1]) * B
+    pk, _ = peaks()
+    print(json.dumps({"impl": "torch", "metric": "transitions/sec (world-model+VAE step)", "value": B / (ms * 1e-3), "unit": "transitions/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "bf16 autocast (cuBLASLt) + fp32 masters", "data": "synthetic", "config": workload(args, cfg), "cuda_graph": True,
+                      "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
+                                   "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                                   "note": "whole step (library kernels are not separable by event inside the graph)"}}), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     c = CONFIGS[a.config]
-    if a.impl == "reference":
+    CPU_THREADS = a.cpu_threads
+    if a.impl == "torch":
+        run_torch(a, c)
+    elif a.impl == "reference":
         run_reference(a, c)
     else:
         run_b200(a, c)
