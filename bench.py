@@ -248,7 +248,27 @@ def run_b200(args, cfg):
               "motor_decoder_a_rec_coeff": 1.0, "world_model_s_rec_coeff": 0.0, "vae_cycle_coeff": 1e-3,
               "engine_precision": args.precision, "optimizer_capturable": True}
     torch.manual_seed(0)                      # same init on every rank (replicated parameters)
-    tr = BenchTrainer(config)
+    # N > 1: allocate the trainer's device memory (flat gradient buffers included) from NCCL's allocator and register the pool
+    # with the communicator, so that the all-reduce runs zero-copy on the user buffers (NVLS / symmetric memory on NVSwitch)
+    # instead of staging through NCCL's internal buffers.  Opt-in (PVAE_NCCL_POOL=1): measured at N = 2 it changes nothing
+    # (0.567 ms per step either way), and it has not been run at N = 8.
+    import contextlib
+    pool, backend, nccl_pool = None, None, "off"
+    if world > 1 and os.environ.get("PVAE_NCCL_POOL", "0") == "1":
+        try:
+            backend = dist.distributed_c10d._get_default_group()._get_backend(dev)
+            pool = torch.cuda.MemPool(backend.mem_allocator)
+        except Exception as e:  # noqa
+            pool, nccl_pool = None, "unavailable: %s" % repr(e)[:120]
+    with (torch.cuda.use_mem_pool(pool) if pool is not None else contextlib.nullcontext()):
+        tr = BenchTrainer(config)
+        torch.cuda.synchronize()
+    if pool is not None:
+        try:
+            backend.register_mem_pool(pool)
+            nccl_pool = "registered"
+        except Exception as e:  # noqa
+            nccl_pool = "allocated, not registered: %s" % repr(e)[:120]
     if phase == "vae":
         tr.model.set_learnable_task_encoder(True); tr.model.set_learnable_motor_decoder(True); tr.model.set_learnable_world_model(False)
         tr.read_loss_fn_coeff(world=False)
@@ -480,7 +500,7 @@ def run_b200(args, cfg):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3(fp32-accurate)",
                 "data": "synthetic", "config": workload(args, cfg), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
-                "cuda_graph": graph is not None, "roofline": roofline, "loss_after": loss_after}
+                "cuda_graph": graph is not None, "nccl_user_buffers": nccl_pool, "roofline": roofline, "loss_after": loss_after}
         if not args.no_cpu_baseline:
             v, cms, cores, rows, nsteps = cpu_arm(cfg, phase, args.cpu_sample, 3, 1, min_seconds=10.0)
             line["cpu_baseline"] = {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port", "ms_per_step": cms,

@@ -114,10 +114,49 @@ struct Device {
   int cluster = 2;        // CTA pairs run tcgen05.mma.cta_group::2 on two adjacent M tiles (PVAE_CLUSTER=1 disables)
   int dbg = 0;            // PVAE_DBG: epilogue timing experiments (see GemmParams::dbg)
   int bn_cap = MAX_BN;    // PVAE_BN_CAP: widest N tile (experiments)
+  int snake = 1;          // PVAE_SNAKE=0: every GEMM walks the batch front to back (see batch_direction)
   int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
+
+// L2-aware traversal: the big batch-indexed tensors of a step (134 MB each at batch 65536) do not fit the 126 MB L2, but
+// most of one does.  A GEMM that walks the batch in the direction OPPOSITE to the last kernel that touched its main
+// batch-indexed operand starts on the rows that kernel touched last, i.e. the ones still resident.  The table remembers, per
+// buffer, the direction of the last walk; the launch sequence of a step is static, so a captured graph freezes a
+// consistent zig-zag.  (Order never changes results: tiles are independent, weight gradients accumulate with atomics.)
+struct WalkTable {
+  static constexpr int N = 64;
+  const void* ptr[N];
+  int dir[N];
+  int n = 0;
+  int last(const void* p) const { for (int i = 0; i < n; ++i) if (ptr[i] == p) return dir[i]; return -1; }
+  void set(const void* p, int d) {
+    if (!p) return;
+    for (int i = 0; i < n; ++i) if (ptr[i] == p) { dir[i] = d; return; }
+    if (n < N) { ptr[n] = p; dir[n] = d; ++n; }
+  }
+};
+static WalkTable g_walk;
+
+static int batch_direction(const Device& dev, const GemmDesc& d) {
+  if (!dev.snake) return 0;
+  // main batch-indexed input: A (row-streaming GEMMs: A is [batch x K]); weight gradients stream A and B along K = batch,
+  // the wider one decides
+  const void* main_in = d.A[0].base;
+  if (d.split && d.B.width >= d.A[0].width + (d.nseg > 1 ? d.A[1].width : 0)) main_in = d.B.base;   // (tie: the gradient is the fresher one)
+  const int prev = g_walk.last(main_in);
+  const int dir = prev < 0 ? 0 : 1 - prev;
+  g_walk.set(d.A[0].base, dir);
+  if (d.nseg > 1) g_walk.set(d.A[1].base, dir);
+  if (d.split) g_walk.set(d.B.base, dir);
+  g_walk.set(d.epi.out, dir);
+  g_walk.set(d.epi.out2, dir);
+  if (d.epi.type != EPI_WGRAD) g_walk.set(d.epi.out_f32, dir);
+  g_walk.set(d.epi.aux, dir);
+  g_walk.set(d.epi.add, dir);
+  return dir;
+}
 
 static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   CKR(resolve_driver());
@@ -153,6 +192,7 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   else bn = rup(cdiv(d.N, n_tiles), n_tiles > 1 ? 64 : 16);
   if (bn > MAX_BN) bn = MAX_BN;
   p.cs_mma = dev.cs_mma;
+  p.reverse = batch_direction(dev, d);
   n_tiles = cdiv(d.N, bn);
   p.n_tiles = n_tiles;
   p.bn = bn;
@@ -225,9 +265,9 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   cfg.numAttrs = 1;
   static const int log_level = getenv("PVAE_LOG_GEMM") ? atoi(getenv("PVAE_LOG_GEMM")) : 0;   // 1: print every launch, 2: and synchronise after it
   if (log_level)
-    fprintf(stderr, "[pvae_gemm] epi %d act %d tma %d cg %d | M %d N %d K %d+%d majors %d%d passes %d | m_tiles %d n_tiles %d bn %d splits %d grid %d | b_k0 %d,%d b_n0 %d mseg %d\n",
+    fprintf(stderr, "[pvae_gemm] epi %d act %d tma %d cg %d | M %d N %d K %d+%d majors %d%d passes %d | m_tiles %d n_tiles %d bn %d splits %d grid %d | b_k0 %d,%d b_n0 %d mseg %d rev %d\n",
             p.epi.type, p.epi.act, (int)tma, cluster, d.M, d.N, d.K[0], d.nseg > 1 ? d.K[1] : 0, d.a_major, d.b_major, d.passes, p.m_tiles, n_tiles, bn,
-            splits, grid, p.b_k0[0], p.b_k0[1], p.b_n0, p.m_seg_tiles);
+            splits, grid, p.b_k0[0], p.b_k0[1], p.b_n0, p.m_seg_tiles, p.reverse);
   CK(cudaLaunchKernelEx(&cfg, fn, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
@@ -520,6 +560,8 @@ static int init_device(Device& dev, int device) {
   if (env) dev.dbg = atoi(env);
   env = getenv("PVAE_BN_CAP");
   if (env) { int v = atoi(env); if (v >= 64 && v <= MAX_BN && v % 64 == 0) dev.bn_cap = v; }
+  env = getenv("PVAE_SNAKE");
+  if (env) dev.snake = atoi(env) != 0;
   env = getenv("PVAE_CS_MMA");
   if (env) dev.cs_mma = atoi(env) != 0;
   env = getenv("PVAE_CLUSTER");

@@ -97,6 +97,7 @@ struct GemmParams {
   int32_t passes;                  // 1 = bf16, 3 = bf16x3
   int32_t m_tiles, n_tiles, bn, splits;
   int32_t dbg;                     // PVAE_DBG bit mask: skip parts of the TMA epilogue (timing experiments only, results are wrong)
+  int32_t reverse;                 // walk the batch dimension from its far end (see UnitWalk)
   int32_t cs_mma;                  // bias-gradient column sums: 1 = mma.sync (ones . slab), 0 = lanes add columns, -1 = by K depth
   int32_t cg;                      // 1, or 2: CTA pairs on adjacent M tiles run one 256-row tcgen05.mma.cta_group::2 (kernel template CG)
   const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
@@ -585,11 +586,13 @@ __device__ __forceinline__ void trace_stamp(int dbg, int k, int slot) {
 // (split, m, n) triple is stepped as a mixed-radix counter: integer divisions (~150 dependent cycles each, 64-bit ones
 // several hundred) happen once per kernel instead of once per unit in every role -- for a 5-k-block tile they cost the
 // MMA-issuing warp more time than the tile's tensor work.
+// `reverse` walks the batch dimension (M pairs of a row-streaming GEMM, K splits of a weight gradient) from the far end: a kernel
+// that starts where its producer / the previous reader of the same activation stopped finds that end still in the 126 MB L2.
 struct UnitWalk {
   int split, mp, nt;
-  int d_split, d_mp, d_nt, n_tiles, m_pairs, it_base, it_rem;
-  __device__ __forceinline__ void init(int u0, int stride, int n_tiles_, int m_pairs_, int iters_total, int splits) {
-    n_tiles = n_tiles_; m_pairs = m_pairs_;
+  int d_split, d_mp, d_nt, n_tiles, m_pairs, it_base, it_rem, n_splits, rev;
+  __device__ __forceinline__ void init(int u0, int stride, int n_tiles_, int m_pairs_, int iters_total, int splits, int reverse) {
+    n_tiles = n_tiles_; m_pairs = m_pairs_; n_splits = splits; rev = reverse;
     const int tile_units = n_tiles * m_pairs;
     split = u0 / tile_units;
     int t = u0 - split * tile_units;
@@ -608,9 +611,11 @@ struct UnitWalk {
     mp -= c ? m_pairs : 0;
     split += d_split + c;
   }
+  __device__ __forceinline__ int m_pair() const { return (rev && n_splits == 1) ? m_pairs - 1 - mp : mp; }
+  __device__ __forceinline__ int k_split() const { return (rev && n_splits > 1) ? n_splits - 1 - split : split; }
   // k-blocks of the current split: the first it_rem splits get one more than the others
-  __device__ __forceinline__ int it_begin() const { return split * it_base + (split < it_rem ? split : it_rem); }
-  __device__ __forceinline__ int it_end() const { return it_begin() + it_base + (split < it_rem ? 1 : 0); }
+  __device__ __forceinline__ int it_begin() const { const int sp = k_split(); return sp * it_base + (sp < it_rem ? sp : it_rem); }
+  __device__ __forceinline__ int it_end() const { const int sp = k_split(); return it_begin() + it_base + (sp < it_rem ? 1 : 0); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -694,10 +699,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     const bool leader = (CG == 1) || crank == 0;
     const uint32_t full0 = (CG == 2) ? mapa_u32(full_bar(0), 0u) : full_bar(0);
     int stage = 0; uint32_t phase = 0;
-    UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits);
+    UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits, p.reverse);
     for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
       const int n_tile = w.nt;
-      const int m_tile = w.mp * csize + crank;
+      const int m_tile = w.m_pair() * csize + crank;
       const int it_end = w.it_end();
       int it = w.it_begin();
       const int b_n = p.b_n0 + n_tile * bn + crank * bn_loc;
@@ -762,7 +767,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       };
-      UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits);
+      UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits, p.reverse);
       for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
         const int it_end = w.it_end();
         int it = w.it_begin();
@@ -823,10 +828,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     // 32 rows x 64 B, 64B swizzle: the 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
     uint8_t* srow = slab_gen + lane * 64;
     const int sw = (lane >> 1) & 3;
-    UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits);
+    UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits, p.reverse);
     for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
       const int n_tile = w.nt;
-      const int m_tile = w.mp * csize + crank;
+      const int m_tile = w.m_pair() * csize + crank;
       const int row_in_tile = q * 32 + lane;
       int row = m_tile * BM + row_in_tile;
       bool row_ok = row < m_valid;

@@ -63,9 +63,13 @@ def allreduce_avg_(tensors, group=None):
     w = world_size()
     if w == 1:
         return
+    native_avg = dist.get_backend(group) == "nccl"      # NCCL averages inside the collective; gloo has no AVG
     for t in tensors:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        t.div_(w)
+        if native_avg:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            t.div_(w)
 
 
 def broadcast_(tensors, src=0):
