@@ -52,6 +52,24 @@ def parse():
     return ap.parse_args()
 
 
+def flops_per_transition(dsb, da, z, te, md, wm):
+    """Algorithmic FLOPs per transition (2*MAC on unpadded dims; bias / activation / loss elementwise work, the value branch and
+    the reference's dead forward excluded), SURVEY.md section 8d.  te / md / wm: hidden widths of the three trained MLPs.
+    world step = fwd + wgrad of every layer + dgrad of all but the first; VAE step = fwd of all three nets, wgrad + dgrad of
+    encoder and decoder (the decoder's first layer also w.r.t. its z columns), dgrad through the frozen world model (its first
+    layer w.r.t. the action columns only)."""
+    def M(i, hidden, o):
+        dims = [i] + list(hidden) + [o]
+        return sum(dims[k] * dims[k + 1] for k in range(len(dims) - 1)), dims
+    mte, dte = M(2 * dsb, te, 2 * z)
+    mmd, dmd = M(dsb + z, md, da)
+    mwm, dwm = M(dsb + da, wm, dsb)
+    m1 = lambda m, d: m - d[0] * d[1]
+    world = 2 * (2 * mwm + m1(mwm, dwm))
+    vae = 2 * (mte + mmd + mwm) + 2 * (mte + m1(mte, dte)) + 2 * (mmd + m1(mmd, dmd) + z * dmd[1]) + 2 * (m1(mwm, dwm) + da * dwm[1])
+    return world, vae
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -212,7 +230,6 @@ def run_b200(args, cfg):
     from physicsvae_b200 import _abi, parallel
     from physicsvae_b200 import train_physics_vae as tp
     from physicsvae_b200 import torch_models as tm
-    from oracle import pvae_oracle as orc     # FLOP model + (rank 0) the cpu_baseline leg only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -374,7 +391,7 @@ def run_b200(args, cfg):
 
     # ---- roofline leg: the tensor-core kernel sequence alone (forward + loss + backward launches of one step), CUDA events
     #      on the launching stream around pvae_{world,vae}_step only (no Adam / all-reduce / shadow refresh)
-    fl_world, fl_vae = orc.flops_per_transition(cfg["dsb"], cfg["da"], cfg["z"], [cfg["te"][0]] * cfg["te"][1],
+    fl_world, fl_vae = flops_per_transition(cfg["dsb"], cfg["da"], cfg["z"], [cfg["te"][0]] * cfg["te"][1],
                                                 [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
     flops_step = (fl_world if phase == "world" else fl_vae) * B
     def kernel_seq():
@@ -524,7 +541,6 @@ def run_torch(args, cfg):
     """World / VAE step with nn.Linear under bf16 autocast (cuBLASLt), autograd, torch.optim.Adam(fused, capturable), the whole
     step captured in one CUDA graph; inputs pre-concatenated and resident in bf16 (the friendliest setting for the library)."""
     import torch.nn as nn
-    from oracle import pvae_oracle as orc
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, phase = args.batch, args.phase
@@ -585,7 +601,7 @@ def run_torch(args, cfg):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    fl = orc.flops_per_transition(dsb, da, z, [cfg["te"][0]] * cfg["te"][1], [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
+    fl = flops_per_transition(dsb, da, z, [cfg["te"][0]] * cfg["te"][1], [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
     flops = (fl[0] if phase == "world" else fl[1]) * B
     pk, _ = peaks()
     print(json.dumps({"impl": "torch", "metric": "transitions/sec (world-model+VAE step)", "value": B / (ms * 1e-3), "unit": "transitions/s",

@@ -95,8 +95,9 @@ int pvae_sync_weights(pvae_handle h, uint32_t net_mask, pvae_stream s);
 /* One Adam step for the layers of `net` selected by layer_mask (bit l), on the bound fp32 masters and the bound gradient
  * buffer, followed -- in the same kernels -- by the refresh of the bf16 shadow operands.  exp_avg_dev / exp_avg_sq_dev: fp32
  * state in the flat layout of the gradient buffer ([W0|b0|W1|b1|...]), owned by the caller.  step_dev: device fp32 scalar
- * holding the number of steps taken so far by these parameters; it is incremented on the stream before the update (so the
- * call is CUDA-graph replayable).  Arithmetic follows torch.optim.Adam(amsgrad=False, maximize=False).
+ * holding the number of steps taken so far by these parameters; the call increments it on the device (the update uses
+ * step + 1 and the last thread block to finish writes it back), so the call is CUDA-graph replayable.  One launch covers
+ * the whole net when its layers are laid out back to back and 16-byte aligned, otherwise one launch per layer.  Arithmetic follows torch.optim.Adam(amsgrad=False, maximize=False).
  * replaces: optimizer.step() (torch_models.py:143) + pvae_sync_weights for the stepped layers. */
 int pvae_adam_step(pvae_handle h, int net, uint32_t layer_mask, float* exp_avg_dev, float* exp_avg_sq_dev, float* step_dev,
                    float lr, float beta1, float beta2, float eps, float weight_decay, pvae_stream s);
@@ -108,7 +109,10 @@ int pvae_bind_workspace(pvae_handle h, void* ws_dev, size_t bytes);
 /* --- transition buffers -------------------------------------------------------------------------------------- */
 /* Resident transition buffer = the reference's DatasetBase.X / .Y (torch_models.py:39-58; built by
  * load_dataset_for_PhysicsVAE, train_physics_vae.py:117-164) converted once to bf16 hi(/lo) planes:
- *   x: [n_rows][2*dsb]  (s_t | s_{t+1}),  y: [n_rows][da].
+ *   x: one row per transition (s_t | 0.. | a_t | 0.. | s_{t+1} | 0..), a_t at column roundup(dsb, 8), s_{t+1} at column
+ *      roundup(roundup(dsb, 8) + da, 64), row length a multiple of 64 columns (cat[s_t, a_t] is then one
+ *      K segment of the row);  y: [n_rows][roundup(da, 64)], a_t once more as the 16-byte aligned MSE target.
+ * The layout is private to the library: callers size the buffer with pvae_transitions_bytes and fill it with pvae_ingest.
  * pvae_ingest converts rows [0, n_rows) of the raw arrays (x_raw_dev: float64 if x_is_f64 else float32, row stride
  * 2*dsb; y_raw_dev: float32, row stride da) into rows [dst_row, dst_row + n_rows) of buf_dev.
  * replaces: DatasetBase.__getitem__ + default collate (torch.Tensor(x) per item, torch_models.py:52-68). */
