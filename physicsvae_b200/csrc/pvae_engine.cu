@@ -114,6 +114,7 @@ struct Device {
   int cluster = 2;        // CTA pairs run tcgen05.mma.cta_group::2 on two adjacent M tiles (PVAE_CLUSTER=1 disables)
   int dbg = 0;            // PVAE_DBG: epilogue timing experiments (see GemmParams::dbg)
   int bn_cap = MAX_BN;    // PVAE_BN_CAP: widest N tile (experiments)
+  int pdl = 1;            // PVAE_PDL=0: plain stream-ordered GEMM launches
   int snake = 1;          // PVAE_SNAKE=0: every GEMM walks the batch front to back (see batch_direction)
   int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
@@ -258,11 +259,16 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (dev.pdl) {      // programmatic dependent launch: this grid's prologue overlaps the previous kernel's tail (see the kernel)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   static const int log_level = getenv("PVAE_LOG_GEMM") ? atoi(getenv("PVAE_LOG_GEMM")) : 0;   // 1: print every launch, 2: and synchronise after it
   if (log_level)
     fprintf(stderr, "[pvae_gemm] epi %d act %d tma %d cg %d | M %d N %d K %d+%d majors %d%d passes %d | m_tiles %d n_tiles %d bn %d splits %d grid %d | b_k0 %d,%d b_n0 %d mseg %d rev %d\n",
@@ -560,6 +566,8 @@ static int init_device(Device& dev, int device) {
   if (env) dev.dbg = atoi(env);
   env = getenv("PVAE_BN_CAP");
   if (env) { int v = atoi(env); if (v >= 64 && v <= MAX_BN && v % 64 == 0) dev.bn_cap = v; }
+  env = getenv("PVAE_PDL");
+  if (env) dev.pdl = atoi(env) != 0;
   env = getenv("PVAE_SNAKE");
   if (env) dev.snake = atoi(env) != 0;
   env = getenv("PVAE_CS_MMA");

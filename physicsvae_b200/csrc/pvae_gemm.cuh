@@ -678,6 +678,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
   const int crank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int unit0 = blockIdx.x / csize, unit_stride = gridDim.x / csize;
 
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, cluster sync) touched
+  // no global memory, so it may run while the previous kernel of the stream is still draining -- a CTA of this grid becomes
+  // resident the moment the CTA of the previous grid on its SM exits.  launch_dependents lets the NEXT grid do the same with
+  // us; wait blocks until the previous grid has completed and its writes are visible.  Nothing below this line may move up.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int row0 = p.row_cursor ? *p.row_cursor : 0;
   const int kb_total = p.kb[0] + p.kb[1];
   const int iters_total = p.passes * kb_total;

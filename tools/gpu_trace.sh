@@ -4,6 +4,6 @@
 mkdir -p gpurun_out
 export PVAE_LIB=$PWD/physicsvae_b200/lib/libpvae_sm100_dbg.so
 for i in ${@:-24 25 26 27 28 29 30 31}; do
-PVAE_TRACE_IDX=$i timeout 300 python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/trace_$i.log 2>&1; echo "trace $i rc=$?"
+PVAE_TRACE_IDX=$i timeout 300 python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline ${BENCH_ARGS} > gpurun_out/trace_$i.log 2>&1; echo "trace $i rc=$?"
 done
 python tools/trace_report.py > gpurun_out/trace_report.log 2>&1

@@ -1,6 +1,10 @@
 """Summarise gpurun_out/trace_<idx>.npy files (tools/gpu_trace.sh): per-unit role timeline of a GEMM launch."""
 import sys, numpy as np
 names = {24: "fwd L0", 25: "fwd L1", 26: "fwd L2 MSE", 27: "wgrad L2", 28: "dgrad L1", 29: "wgrad L1", 30: "dgrad L0", 31: "wgrad L0"}
+import glob, os, re
+for f in glob.glob("gpurun_out/trace_*.npy"):
+    i = int(re.search(r"trace_(\d+)", f).group(1))
+    names.setdefault(i, "launch %d" % i)
 for idx in sorted(names):
     try:
         t = np.load("gpurun_out/trace_%d.npy" % idx).reshape(160, 16, 8).astype(np.int64)
