@@ -19,14 +19,14 @@ B, DSB, DA, H = 65536, 197, 45, 1024
 
 # (label, algorithmic FLOPs) of the eight GEMM launches of one world step, in launch order
 STEP = [
-    ("fwd L0   [s_t|a_t].W0^T (K=197+45, N=1024) +bias+ReLU+mask", 2.0 * B * (DSB + DA) * H),
+    ("fwd L0   [s_t|a_t].W0^T (K=245: one segment of the resident row, N=1024) +bias+ReLU+mask", 2.0 * B * (DSB + DA) * H),
     ("fwd L1   h0.W1^T (K=1024, N=1024) +bias+ReLU+mask", 2.0 * B * H * H),
     ("fwd L2   h1.W2^T (K=1024, N=197) +bias, MSE, dLoss, db2", 2.0 * B * H * DSB),
     ("wgrad L2 h1^T.g2 (M=1024, N=197, K=65536)", 2.0 * B * H * DSB),
     ("dgrad L1 g2.W2 (K=197, N=1024) * ReLU mask, db1", 2.0 * B * H * DSB),
     ("wgrad L1 h0^T.g1 (1024x1024, K=65536)", 2.0 * B * H * H),
     ("dgrad L0 g1.W1 (K=1024, N=1024) * ReLU mask, db0", 2.0 * B * H * H),
-    ("wgrad L0 [s_t|a_t]^T.g0 (M=197+45 as two M segments, N=1024, K=65536)", 2.0 * B * (DSB + DA) * H),
+    ("wgrad L0 [s_t|a_t]^T.g0 (M=245, N=1024, K=65536)", 2.0 * B * (DSB + DA) * H),
 ]
 
 
