@@ -26,7 +26,7 @@ LIB_PATH = os.environ.get("PVAE_LIB") or os.path.join(LIB_DIR, "libpvae_sm100.so
 # every symbol include/pvae_sm100.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = [
     "pvae_last_error", "pvae_abi_version", "pvae_create", "pvae_destroy", "pvae_bind_net", "pvae_net_grad_elems",
-    "pvae_sync_weights", "pvae_adam_step", "pvae_workspace_bytes", "pvae_bind_workspace", "pvae_transitions_bytes", "pvae_ingest",
+    "pvae_sync_weights", "pvae_adam_step", "pvae_workspace_bytes", "pvae_bind_workspace", "pvae_transitions_bytes", "pvae_ingest", "pvae_ingest_episodes",
     "pvae_bind_transitions", "pvae_set_cursor", "pvae_advance_cursor", "pvae_world_step", "pvae_vae_step",
     "pvae_forward", "pvae_gemm_bf16", "pvae_launch_count", "pvae_debug_trace",
 ]
@@ -74,6 +74,7 @@ def load():
     lib.pvae_bind_workspace.argtypes = [vp, vp, sz]
     lib.pvae_transitions_bytes.argtypes = [vp, i64, C.POINTER(sz)]
     lib.pvae_ingest.argtypes = [vp, vp, i64, i64, vp, i32, vp, i64, vp]
+    lib.pvae_ingest_episodes.argtypes = [vp, vp, i64, i64, vp, i32, i64, vp, vp, i64, vp]
     lib.pvae_bind_transitions.argtypes = [vp, vp, i64]
     lib.pvae_set_cursor.argtypes = [vp, i64, vp]
     lib.pvae_advance_cursor.argtypes = [vp, i64, i64, i64, vp]

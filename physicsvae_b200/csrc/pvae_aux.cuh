@@ -48,6 +48,42 @@ __global__ void ingest_kernel(const SrcT* __restrict__ src, int64_t src_ld, int 
   }
 }
 
+// ---- dataset build on the device (load_dataset_for_PhysicsVAE, train_physics_vae.py:133-156): every state of every episode is
+// uploaded ONCE ([n_states][dsb]); transition r is (s = states[first[r]], a = actions[first[r]], s' = states[first[r] + 1]).
+// One thread per (row, 2 destination columns) of the resident x rows (s | 0.. | a | 0.. | s' | 0..) / y rows (a | 0..).
+template <typename SrcT>
+__global__ void ingest_episodes_kernel(const SrcT* __restrict__ states, const float* __restrict__ actions,
+                                       const int64_t* __restrict__ first, int dsb, int da, int a_col, int s2_col,
+                                       __nv_bfloat16* __restrict__ dst, int64_t dst_ld, int64_t dst_ps, int planes, int64_t n_rows) {
+  const int64_t pairs_per_row = dst_ld >> 1;
+  const int64_t total = n_rows * pairs_per_row;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / pairs_per_row;
+    const int c0 = (int)(i - r * pairs_per_row) * 2;
+    const int64_t st = first[r];
+    float v[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = c0 + k;
+      float x = 0.f;
+      if (s2_col >= 0) {                       // x row
+        if (c < dsb) x = (float)states[st * dsb + c];
+        else if (c >= a_col && c < a_col + da) x = actions[st * da + (c - a_col)];
+        else if (c >= s2_col && c < s2_col + dsb) x = (float)states[(st + 1) * dsb + (c - s2_col)];
+      } else if (c < da) {                     // y row
+        x = actions[st * da + c];
+      }
+      v[k] = x;
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+    *reinterpret_cast<__nv_bfloat162*>(dst + r * dst_ld + c0) = h;
+    if (planes > 1) {
+      __nv_bfloat162 l = __floats2bfloat162_rn(v[0] - __low2float(h), v[1] - __high2float(h));
+      *reinterpret_cast<__nv_bfloat162*>(dst + dst_ps + r * dst_ld + c0) = l;
+    }
+  }
+}
+
 // ---- shadow weights: Wsh[plane][out][Kpad]; columns [0,K0pad) <- W[:, 0:k0], [K0pad, K0pad+K1pad) <- W[:, k0:k0+k1]
 __global__ void sync_weights_kernel(const float* __restrict__ W, int out, int in, int k0, int k1, int K0pad, int Kpad,
                                     __nv_bfloat16* __restrict__ Wsh, int64_t ps, int planes) {

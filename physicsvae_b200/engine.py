@@ -137,6 +137,25 @@ class Engine:
             _abi.check(self.lib.pvae_ingest(self._h, _ptr(self.transitions), self.n_rows, int(dst_row), _ptr(x_raw),
                                             1 if x_raw.dtype == torch.float64 else 0, _ptr(y_raw), x_raw.shape[0], _stream()))
 
+    def ingest_episodes(self, states, actions, first_state, dst_row=0):
+        """Dataset build on the device: states CUDA [S, dsb] float64 / float32 (all episodes back to back, every state once),
+        actions CUDA [S, da] float32, first_state CUDA [n] int64 (state row of s_t per transition; s_{t+1} is the next row)."""
+        if self.transitions is None:
+            raise _abi.PvaeError("alloc_transitions() first")
+        if states.dim() != 2 or states.shape[1] != self.dsb or actions.shape != (states.shape[0], self.da):
+            raise ValueError("episode arrays must be [S, %d] and [S, %d]" % (self.dsb, self.da))
+        if states.dtype not in (torch.float64, torch.float32):
+            raise ValueError("states must be float64 or float32")
+        states = states.to(self.device).contiguous()
+        actions = actions.to(self.device, torch.float32).contiguous()
+        first_state = first_state.to(self.device, torch.int64).contiguous()
+        if first_state.numel() and (int(first_state.min()) < 0 or int(first_state.max()) + 1 >= states.shape[0]):
+            raise ValueError("first_state index out of range")
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_ingest_episodes(self._h, _ptr(self.transitions), self.n_rows, int(dst_row), _ptr(states),
+                                                     1 if states.dtype == torch.float64 else 0, states.shape[0], _ptr(actions),
+                                                     _ptr(first_state), first_state.numel(), _stream()))
+
     def set_cursor(self, row):
         with torch.cuda.device(self.device):
             _abi.check(self.lib.pvae_set_cursor(self._h, int(row), _stream()))

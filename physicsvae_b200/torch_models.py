@@ -209,6 +209,18 @@ class TrainModel(_TrainableBase):
 
     def _upload(self, loader, which):
         """DatasetBase -> resident bf16 transition buffer (replaces per-item torch.Tensor + collate, torch_models.py:52-68)."""
+        src = getattr(loader.dataset, "episode_source", None)
+        if src is not None and not loader.dataset.normalize_x and not loader.dataset.normalize_y and len(src[2]) == len(loader.dataset):
+            # dataset build on the device: upload every state once, the ingest kernel pairs (s_t, a_t, s_{t+1}) by index
+            states, actions, first = src
+            eng = self.engine
+            eng.alloc_transitions(len(first))
+            st, ac = torch.from_numpy(states).to(self.device), torch.from_numpy(actions).to(self.device)
+            chunk = 1 << 20
+            for lo in range(0, len(first), chunk):
+                eng.ingest_episodes(st, ac, torch.from_numpy(first[lo:lo + chunk]).to(self.device), dst_row=lo)
+            self._resident = which
+            return
         X, Y = loader.dataset.arrays()
         if X.ndim == 3 and X.shape[1] != 1:
             raise NotImplementedError("lookahead > 1 is not on the hot path (train_physics_vae.py:277 hard-wires 1)")

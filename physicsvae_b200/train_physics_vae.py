@@ -120,6 +120,28 @@ def episodes_to_transitions(episodes, num_samples=None, lookahead=1, cond="abs",
     return np.concatenate(Xs, axis=0), np.concatenate(Ys, axis=0)
 
 
+def episodes_to_index(episodes, num_samples=None, use_a_gt=False):
+    """The compact form of the same dataset (lookahead 1, cond "abs") for the device-side builder (`pvae_ingest_episodes`):
+    all state_body rows back to back (every state once), the action rows, and per transition the row of s_t -- in exactly the
+    order `episodes_to_transitions` emits X / Y rows.  Returns (states float64 [S, dsb], actions float32 [S, da], first int64 [N])."""
+    S, A, first = [], [], []
+    count, base = 0, 0
+    for ep in episodes:
+        sb = np.asarray(ep["state_body"], dtype=np.float64)
+        act = np.asarray(ep["action_gt"] if use_a_gt else ep["action"], dtype=np.float32)
+        T = len(ep["time"])
+        n = T - 1
+        if num_samples is not None:
+            n = min(n, num_samples - count)
+        if n > 0:
+            first.append(base + np.arange(n, dtype=np.int64))
+            count += n
+        S.append(sb[:T]); A.append(act[:T])
+        base += T
+    return (np.concatenate(S, axis=0), np.concatenate(A, axis=0),
+            np.concatenate(first) if first else np.zeros((0,), dtype=np.int64))
+
+
 def load_dataset_for_PhysicsVAE(files, num_samples=None, lookahead=1, cond="abs", use_a_gt=False):
     """train_physics_vae.py:117-164."""
     assert files
@@ -127,12 +149,15 @@ def load_dataset_for_PhysicsVAE(files, num_samples=None, lookahead=1, cond="abs"
     data = merge_dataset(files)
     episodes = data["episodes"]
     X, Y = episodes_to_transitions(episodes, num_samples, lookahead, cond, use_a_gt)
+    source = episodes_to_index(episodes, num_samples, use_a_gt) if (lookahead == 1 and cond == "abs" and len(X)) else None
     print("------------------Data Loaded------------------")
     print("File:", files)
     print("Num Episodes:", len(episodes))
     print("Num Transitions (Tuples):", len(X))
     print("-----------------------------------------------")
-    return torch_models.DatasetBase(X, Y, normalize_x=False, normalize_y=False)
+    dataset = torch_models.DatasetBase(X, Y, normalize_x=False, normalize_y=False)
+    dataset.episode_source = source          # lets the trainer build the resident buffer on the device from the unique states
+    return dataset
 
 
 def create_model(config):

@@ -284,6 +284,35 @@ def test_trainer_trajectory_phase_switch_and_checkpoints(tmp_path):
     P.assert_close("restored forward", tr2.compute_model(x.cuda()), om2.forward(x)[:, :5])
 
 
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_device_side_dataset_build_equals_array_ingest(precision, tmp_path):
+    """pvae_ingest_episodes (unique states + index) must fill the resident buffer bit-identically to pvae_ingest
+    on the reference-format X / Y arrays, and the trainer must take that path for a pickled dataset."""
+    from physicsvae_b200 import train_physics_vae as tp
+    from physicsvae_b200.engine import Engine
+    f, data = _pickle(tmp_path, n_ep=5, T=23, dsb=13, da=5, seed=4)
+    X, Y = tp.episodes_to_transitions(data["episodes"])
+    states, actions, first = tp.episodes_to_index(data["episodes"])
+    nets = {"task_encoder": [(8, "relu"), (8, "linear")], "motor_decoder": [(8, "relu"), (5, "linear")],
+            "world_model": [(8, "relu"), (13, "linear")], "value_branch": [(8, "relu"), (1, "linear")]}
+    eng = Engine(13, 5, 4, nets, precision=precision, max_batch=64)
+    n = len(X)
+    buf = eng.alloc_transitions(n)
+    eng.ingest(torch.from_numpy(X[:, 0, :]).cuda(), torch.from_numpy(Y[:, 0, :]).cuda())
+    torch.cuda.synchronize()
+    a = buf.clone()
+    buf.zero_()
+    half = n // 2 + 3                                       # two calls with a destination offset, like the chunked upload
+    eng.ingest_episodes(torch.from_numpy(states).cuda(), torch.from_numpy(actions).cuda(), torch.from_numpy(first[:half]).cuda())
+    eng.ingest_episodes(torch.from_numpy(states).cuda(), torch.from_numpy(actions).cuda(), torch.from_numpy(first[half:]).cuda(), dst_row=half)
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.uint8).flatten(), buf.view(torch.uint8).flatten())
+    with pytest.raises(ValueError):
+        eng.ingest_episodes(torch.from_numpy(states).cuda(), torch.from_numpy(actions).cuda(), torch.tensor([len(states) - 1]).cuda())
+    ds = tp.load_dataset_for_PhysicsVAE([f])
+    assert ds.episode_source is not None and len(ds.episode_source[2]) == len(ds) == n
+
+
 def test_resume_continues_the_trajectory(tmp_path):
     """run_trial with --resume semantics: 2 iterations + checkpoint + a NEW trainer restored from it + 3 more iterations ==
     5 iterations straight (weights, Adam moments, StepLR counter, phase switch at iteration 3 and the iteration counter all

@@ -251,3 +251,21 @@ def test_sweep_replicas_partition_and_latest_checkpoint(tmp_path):
         (d / "model.pth").write_bytes(b"")
     (tmp_path / "trial" / "checkpoint_000011").mkdir()            # incomplete checkpoint directory: ignored
     assert tp.latest_checkpoint(str(tmp_path / "trial")).endswith(os.path.join("checkpoint_000010", "model.pth"))
+
+
+def test_episode_index_matches_transition_arrays():
+    """The compact dataset form of the device-side builder (unique states + per-transition index) describes exactly the X / Y
+    rows the reference's loop produces (train_physics_vae.py:133-156), including the --num_data cap and episode boundaries."""
+    from physicsvae_b200 import train_physics_vae as tp
+    data = orc.synthetic_episodes(4, 17, 7, 3, seed=11)
+    data["episodes"][2] = {k: (v[:5] if hasattr(v, "__len__") else v) for k, v in data["episodes"][2].items()}   # a short episode
+    for cap in (None, 1, 16, 23, 40, 10 ** 6):
+        X, Y = tp.episodes_to_transitions(data["episodes"], num_samples=cap)
+        states, actions, first = tp.episodes_to_index(data["episodes"], num_samples=cap)
+        assert states.dtype == np.float64 and actions.dtype == np.float32 and first.dtype == np.int64
+        assert len(first) == len(X) and states.shape[0] == actions.shape[0] == sum(len(e["time"]) for e in data["episodes"])
+        assert np.array_equal(X[:, 0, :7], states[first]) and np.array_equal(X[:, 0, 7:], states[first + 1])
+        assert np.array_equal(np.asarray(Y[:, 0, :], dtype=np.float32), actions[first])
+    Xg, Yg = tp.episodes_to_transitions(data["episodes"], use_a_gt=True)
+    _, ag, fg = tp.episodes_to_index(data["episodes"], use_a_gt=True)
+    assert np.array_equal(np.asarray(Yg[:, 0, :], dtype=np.float32), ag[fg])
