@@ -337,7 +337,8 @@ __global__ void f32_to_planes_kernel(const float* __restrict__ src, int64_t src_
 
 // ---- loss bookkeeping ---------------------------------------------------------------------------------------------
 // acc: [0] sum sq a, [1] sum kl, [2] sum sq s (world), [3] sum sq cyc
-__global__ void finalize_loss_kernel(const double* __restrict__ acc, float* __restrict__ loss, int B, int da, int dsb,
+// (the accumulators are cleared here, for the next step: one memset node less per step)
+__global__ void finalize_loss_kernel(double* __restrict__ acc, float* __restrict__ loss, int B, int da, int dsb,
                                      float a_c, float kl_c, float s_c, float cyc_c) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const float la = (float)(acc[0] / ((double)B * da));
@@ -346,6 +347,7 @@ __global__ void finalize_loss_kernel(const double* __restrict__ acc, float* __re
     const float lc = (float)(acc[3] / ((double)B * dsb));
     loss[1] = la; loss[2] = lk; loss[3] = ls; loss[4] = lc;
     loss[0] = a_c * la + kl_c * lk + s_c * ls + cyc_c * lc;
+    acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; acc[3] = 0.0;
   }
 }
 

@@ -336,6 +336,7 @@ struct pvae_engine {
   int tx_ld = 0, ty_ld = 0;
   // scalars
   double* acc = nullptr;    // [4] loss accumulators
+  bool acc_dirty = false;   // a step was entered but its finalize kernel (which clears acc) was not enqueued
   unsigned int* adam_counter = nullptr;   // finished-blocks counter of adam_net_kernel
 };
 
@@ -883,7 +884,8 @@ int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pv
   CKR(check_trainable_acts(wm));
   if (!wm.grad) return fail(PVAE_ERR_STATE, "world model has no gradient buffer bound");
   CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
-  CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));
+  if (h->acc_dirty) CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));   // only after a step that failed half-way: finalize clears them
+  h->acc_dirty = true;
   NetIO in;                       // cat[s_t, a_t] (train_physics_vae.py:412-413) = the first dsb8 + da columns of a resident row
   in.nseg = 1;
   in.seg[0] = tx_view(h, 0, h->dsb8 + h->da);
@@ -901,6 +903,7 @@ int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pv
   finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, 0.f, 0.f, s_coeff, 0.f);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
+  h->acc_dirty = false;
   return PVAE_OK;
 }
 
@@ -922,7 +925,8 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
   const int prior = h->desc.latent_prior;
   CK(cudaMemsetAsync(te.grad, 0, te.grad_elems * sizeof(float), st));
   CK(cudaMemsetAsync(md.grad, 0, md.grad_elems * sizeof(float), st));
-  CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));
+  if (h->acc_dirty) CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));   // only after a step that failed half-way: finalize clears them
+  h->acc_dirty = true;
   const int z = h->z, Lte = te.n_layers, Lmd = md.n_layers, Lwm = wm.n_layers;
 
   // encoder: h = TE(cat[s1, s2]) -> (mu | logvar)                      rllib_model_torch.py:773-800
@@ -993,6 +997,7 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
   }
   CKR(net_backward(h, te, te_in, batch, true, nullptr, st));
   finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, a_coeff, prior ? kl_coeff : 0.f, 0.f, cyc ? cyc_coeff : 0.f);
+  h->acc_dirty = false;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return PVAE_OK;
