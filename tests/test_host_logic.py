@@ -269,3 +269,29 @@ def test_episode_index_matches_transition_arrays():
     Xg, Yg = tp.episodes_to_transitions(data["episodes"], use_a_gt=True)
     _, ag, fg = tp.episodes_to_index(data["episodes"], use_a_gt=True)
     assert np.array_equal(np.asarray(Yg[:, 0, :], dtype=np.float32), ag[fg])
+
+
+def test_bench_reference_arm_and_flop_model():
+    """`bench.py --impl reference` needs no GPU: it must print one JSON line with the contract's keys; the FLOP model of the roofline
+    leg must give SURVEY.md 8d's numbers."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-sample", "256",
+                          "--cpu-threads", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "transitions/s" and d["higher_is_better"] is True and d["steps"] == 2
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pvae_bench", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.flops_per_transition(197, 45, 32, [256] * 2, [512] * 3, [1024] * 2) == (8493056, 10269696)
+    assert b.flops_per_transition(512, 128, 32, [1024] * 3, [1024] * 3, [1024] * 3) == (18350080, 44892160)
+    assert b.flops_per_transition(197, 45, 32, [256] * 2, [512] * 3, [1024] * 2) == orc.flops_per_transition(197, 45, 32, [256] * 2, [512] * 3, [1024] * 2)

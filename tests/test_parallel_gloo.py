@@ -83,3 +83,34 @@ def test_dp2_equals_single_rank_even_batch(tmp_path):
 
 def test_dp2_equals_single_rank_ragged_batch(tmp_path):
     _run(37, tmp_path)      # shards of 19 and 18 rows: the n_r * R / n weights make the average exact
+
+
+def _replica_worker(rank, world, port, out):
+    """`train_physics_vae.py --sweep_mode replicas` under torchrun: the CLI's own init (gloo here: no GPU) + point assignment."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank))
+    from physicsvae_b200 import train_physics_vae as tp
+    try:
+        tp.init_distributed("replicas")
+        assert dist.is_initialized() and parallel.job_world_size() == world and parallel.job_rank() == rank
+        assert parallel.world_size() == 1 and parallel.rank() == 0          # a replica trains alone: no sharding, no all-reduce
+        t = torch.ones(3)
+        parallel.allreduce_avg_([t])                                        # must be a no-op in replica mode
+        assert torch.equal(t, torch.ones(3))
+        mine = parallel.sweep_points(5, parallel.job_rank(), parallel.job_world_size())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            torch.save(gathered, out)
+        tp.init_distributed("dp")
+        assert parallel.world_size() == world and parallel.rank() == rank
+    finally:
+        parallel.set_replica_mode(False)
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_sweep_replica_mode_under_two_ranks(tmp_path):
+    out = str(tmp_path / "points.pt")
+    mp.spawn(_replica_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    parts = torch.load(out)
+    assert parts == [[0, 2, 4], [1, 3]]
