@@ -1,8 +1,9 @@
 #!/bin/bash
 # epilogue timing experiments: kernel durations of one world step with parts of the TMA epilogue skipped (PVAE_DBG bits)
+# needs the debug build (-DPVAE_DEBUG_HOOKS -> physicsvae_b200/lib/libpvae_sm100_dbg.so), see tools/README.md
 mkdir -p gpurun_out
 for d in 0 1 2 4 8 16 31; do
-PVAE_DBG=$d timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pvae_gemm -s 27 -c 9 --csv --log-file gpurun_out/dbg_$d.csv python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline > gpurun_out/dbg_$d.log 2>&1
+PVAE_LIB=$PWD/physicsvae_b200/lib/libpvae_sm100_dbg.so PVAE_DBG=$d timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pvae_gemm -s 24 -c 8 --csv --log-file gpurun_out/dbg_$d.csv python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline > gpurun_out/dbg_$d.log 2>&1
 echo "dbg=$d: $(python - <<P
 import csv
 rows=list(csv.reader(open('gpurun_out/dbg_$d.csv')))
