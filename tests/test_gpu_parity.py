@@ -340,6 +340,38 @@ def test_resume_continues_the_trajectory(tmp_path):
     assert [json.loads(l)["training_iteration"] for l in lines] == [1, 2, 3, 4, 5]
 
 
+def test_cli_main_grid_checkpoints_output_and_resume(tmp_path):
+    """The CLI end to end with the reference's flags (train_physics_vae.py:30-55, 469-521): a two-point grid (list flags append
+    to their defaults), per-trial result.json + checkpoint directories with the reference's five files, a working --output
+    export (it always fails upstream), and --resume continuing every trial from its newest checkpoint."""
+    from physicsvae_b200 import train_physics_vae as tp
+    f, data = _pickle(tmp_path)
+    out = str(tmp_path / "exported.pt")
+    base = ["--data_train", f, "--max_iter_world_model", "1", "--batch_size", "32", "--latent_dim", "4", "--vae_kl_coeff", "0.5",
+            "--local_dir", str(tmp_path / "results"), "--name", "cli", "--checkpoint_freq", "1"]
+    ck = tp.main(base + ["--max_iter", "2", "--output", out])
+    root = tmp_path / "results" / "cli"
+    assert sorted(os.listdir(root)) == ["trial_00000", "trial_00001"]          # vae_kl_coeff grid [1.0, 0.5]
+    assert ck == str(root / "trial_00001" / "checkpoint_000002" / "model.pth")
+    for t in ("trial_00000", "trial_00001"):
+        res = [json.loads(l) for l in open(root / t / "result.json").read().strip().splitlines()]
+        assert [r["training_iteration"] for r in res] == [1, 2] and all(np.isfinite(r["mean_train_loss"]) for r in res)
+        for c in ("checkpoint_000001", "checkpoint_000002"):
+            assert sorted(os.listdir(root / t / c)) == ["model.pt", "model.pth", "motor_decoder.pt", "task_encoder.pt", "trainer_state.pt",
+                                                        "world_model.pt"]
+    sd = torch.load(out)
+    assert len(sd) == 26 and all(k.split(".")[0] in ("_task_encoder", "_motor_decoder", "_world_model", "_value_branch") for k in sd)
+    ref = torch.load(ck)
+    assert all(torch.equal(sd[k], ref[k]) for k in ref)
+    ck3 = tp.main(base + ["--max_iter", "3", "--resume"])
+    assert ck3 == str(root / "trial_00001" / "checkpoint_000003" / "model.pth")
+    for t in ("trial_00000", "trial_00001"):
+        res = [json.loads(l) for l in open(root / t / "result.json").read().strip().splitlines()]
+        assert [r["training_iteration"] for r in res] == [1, 2, 3]
+    moved = [k for k in ref if k.startswith("_motor_decoder") and not torch.equal(torch.load(ck3)[k], ref[k])]
+    assert moved, "the resumed VAE-phase iteration must have trained the decoder"
+
+
 @pytest.mark.parametrize("weight_decay", [0.0, 0.01])
 def test_fused_adam_matches_torch_adam_and_refreshes_shadow(weight_decay):
     """physicsvae_b200.optim.PvaeAdam (one kernel per layer: Adam update + bf16 shadow refresh) vs torch.optim.Adam on the same
