@@ -7,6 +7,9 @@ Fixtures
   ref_loco_ckpt.npz    outputs of the shipped checkpoint data/pretrained/loco_modelV1.pt on a seeded input
                         -- weights are NOT copied (12.5 MB), only sha256 + outputs.
   ref_dataset.npz      load_dataset_for_PhysicsVAE on a synthetic README-format pickle: X / Y arrays and batch sizes.
+  ref_trajectory.npz   four epochs of the reference's own TrainModel.step() (two world-model epochs, phase switch, two VAE epochs;
+                       Adam lr 5e-4, StepLR, batch 32 with a short last batch, latent_prior_noise False so that no RNG is involved):
+                       the pickle, the seeded initial state dict, the per-epoch mean_train_loss and the final state dict.
 """
 import hashlib
 import os
@@ -105,9 +108,50 @@ def dataset():
     print("ref_dataset.npz: X %s %s Y %s %s batches %s" % (ds.X.shape, ds.X.dtype, ds.Y.shape, ds.Y.dtype, sizes))
 
 
+def trajectory():
+    import argparse
+    tpv, tm, rmt = refload.load()
+    dsb, da, z = 13, 5, 4
+    data = orc.synthetic_episodes(3, 41, dsb, da, seed=2)
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "demo.pkl")
+        with open(f, "wb") as fh:
+            pickle.dump(data, fh)
+        args = argparse.Namespace(max_iter_world_model=2, max_iter=4, data_train=[f], data_test=None, world_model=None, lr=5e-4,
+                                  lr_schedule="step", batch_size=32, latent_dim=z, latent_prior_type=["normal_zero_mean_one_std"],
+                                  vae_kl_coeff=[1.0], vae_cycle_coeff=[1e-3], num_data=None)
+        tpv.args = args
+        cfg = tpv.get_trainer_config(args)
+        for k, v in list(cfg.items()):
+            if isinstance(v, dict) and set(v) == {"grid_search"}:
+                cfg[k] = v["grid_search"][0]
+        cfg.update(TE_width=16, MD_width=24, world_model_width=32)
+        torch.manual_seed(5)
+        ref = tpv.TrainModel(cfg)
+    ref.model.latent_prior_noise = False
+    out = {"pickle_bytes": np.frombuffer(pickle.dumps(data), dtype=np.uint8), "dsb": dsb, "da": da, "z": z, "batch_size": 32, "lr": 5e-4,
+           "max_iter_world_model": 2, "TE_width": 16, "MD_width": 24, "world_model_width": 32,
+           "lr_step_size": cfg["lr_schedule_params"]["step_size"], "lr_gamma": cfg["lr_schedule_params"]["gamma"]}
+    for k, v in ref.model.state_dict().items():
+        out["init/" + k] = v.detach().numpy().copy()
+    losses = []
+    for it in range(4):
+        r = ref.step()
+        losses.append(r["mean_train_loss"])
+    out["losses"] = np.array(losses, dtype=np.float64)
+    for k, v in ref.model.state_dict().items():
+        if k.startswith("_value_branch"):                  # never trained (no loss term): identical to init, checked here, not stored
+            assert np.array_equal(v.detach().numpy(), out["init/" + k]), k
+            continue
+        out["final/" + k] = v.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "ref_trajectory.npz"), **out)
+    print("ref_trajectory.npz: losses %s" % losses)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     small_step()
     loco_ckpt()
     dataset()
+    trajectory()

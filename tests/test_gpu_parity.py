@@ -313,6 +313,33 @@ def test_device_side_dataset_build_equals_array_ingest(precision, tmp_path):
     assert ds.episode_source is not None and len(ds.episode_source[2]) == len(ds) == n
 
 
+def test_trainer_trajectory_matches_reference_fixture(tmp_path):
+    """tests/golden/ref_trajectory.npz holds four epochs of the REFERENCE's own TrainModel.step (oracle/make_golden.py): two
+    world-model epochs, the phase switch, two VAE epochs, Adam + StepLR, batches 32 / 32 / 32 / 24.  The CUDA trainer, started
+    from the fixture's initial weights, must reproduce the per-epoch losses and the final parameters."""
+    from physicsvae_b200 import train_physics_vae as tp
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_trajectory.npz"))
+    f = str(tmp_path / "demo.pkl")
+    with open(f, "wb") as fh:
+        fh.write(g["pickle_bytes"].tobytes())
+    tp.args = tp.arg_parser().parse_args(["--data_train", f, "--max_iter_world_model", str(int(g["max_iter_world_model"])), "--max_iter", "4",
+                                          "--batch_size", str(int(g["batch_size"])), "--latent_dim", str(int(g["z"])), "--lr", str(float(g["lr"]))])
+    cfg = tp.resolve_grid(tp.get_trainer_config(tp.args))[0]
+    cfg.update(TE_width=int(g["TE_width"]), MD_width=int(g["MD_width"]), world_model_width=int(g["world_model_width"]), noise_seed=1)
+    assert cfg["lr_schedule_params"] == {"step_size": int(g["lr_step_size"]), "gamma": float(g["lr_gamma"])}
+    tr = tp.TrainModel(cfg)
+    tr.model.load_state_dict({k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init/")})
+    tr.model.latent_prior_noise = False
+    assert len(tr.train_loader) == 4
+    for it, want in enumerate(g["losses"]):
+        r = tr.train()
+        assert abs(r["mean_train_loss"] - want) <= P.ATOL + P.RTOL * abs(want), (it, r, float(want))
+    sd = tr.model.state_dict()
+    for k in g.files:
+        if k.startswith("final/"):
+            P.assert_close("param " + k[6:], sd[k[6:]], torch.from_numpy(g[k]), rtol=2e-3, atol=2e-5)
+
+
 def test_resume_continues_the_trajectory(tmp_path):
     """run_trial with --resume semantics: 2 iterations + checkpoint + a NEW trainer restored from it + 3 more iterations ==
     5 iterations straight (weights, Adam moments, StepLR counter, phase switch at iteration 3 and the iteration counter all
