@@ -189,6 +189,41 @@ def test_reference_fixture_forward_losses_gradients():
             assert P.rel_l2(got[k], torch.from_numpy(ref[k])) < 5e-3, k
 
 
+@pytest.mark.parametrize("tag,act,prior", [("elu", "elu", "normal_zero_mean_one_std"), ("noprior", "relu", False)])
+def test_reference_variant_fixture(tag, act, prior):
+    """tests/golden/ref_small_variants.npz (generated by the reference itself): ELU hidden activations, and latent_prior_type=False
+    (z = encoder output, no KL term) -- forward outputs, both phases' losses and every gradient."""
+    g = np.load(os.path.join(G, "ref_small_variants.npz"))
+    cfg = dict(dsb=int(g["dsb"]), da=int(g["da"]), z=int(g["z"]), te=(16, 2), md=(24, 3), wm=(32, 2))
+    layers = {k: orc.gen_layers(cfg[k][0], cfg[k][1], act_hidden=act) for k in ("te", "md", "wm")}
+    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + "/sd/")}
+    m = P.product_model(cfg, layers, sd, prior=prior, max_batch=128, act=act)
+    x = torch.Tensor(g["X"])[:, 0, :].cuda()
+    eps = torch.from_numpy(g["eps"]).cuda()
+    logits, state = m(input_dict={"obs": x, "obs_flat": x, "eps": eps}, state=None, seq_lens=None)
+    P.assert_close("logits", logits, torch.from_numpy(g[tag + "/logits"]))
+    P.assert_close("z", m._cur_task_encoder_variable, torch.from_numpy(g[tag + "/z_task"]))
+    P.assert_close("future", m._cur_future_state, torch.from_numpy(g[tag + "/future"]))
+    P.assert_close("value", m.value_function(), torch.from_numpy(g[tag + "/value"]))
+    eng = m.engine()
+    B = int(g["B"])
+    eng.alloc_transitions(B)
+    eng.ingest(torch.from_numpy(g["X"]).cuda(), torch.from_numpy(g["Y"]).cuda())
+    for world in (True, False):
+        ph = tag + ("/world" if world else "/vae")
+        m.set_learnable_task_encoder(not world); m.set_learnable_motor_decoder(not world); m.set_learnable_world_model(world)
+        eng.set_cursor(0)
+        loss = eng.world_step(B) if world else eng.vae_step(B, eps=eps, kl_coeff=1.0, cyc_coeff=0.05)
+        torch.cuda.synchronize()
+        ref_loss = float(g[ph + "/loss"])
+        assert abs(float(loss[0]) - ref_loss) <= P.ATOL + P.RTOL * abs(ref_loss), (ph, float(loss[0]), ref_loss)
+        ref = {k[len(ph) + 6:]: g[k] for k in g.files if k.startswith(ph + "/grad/")}
+        got = P.grads_by_net(m)
+        assert set(got) == set(ref)
+        for k in ref:
+            assert P.rel_l2(got[k], torch.from_numpy(ref[k])) < 5e-3, (ph, k, P.rel_l2(got[k], torch.from_numpy(ref[k])))
+
+
 # ---- forward / inference API ----------------------------------------------------------------------------------------------
 def test_forward_parts_and_aliases():
     from physicsvae_b200 import torch_models as tm
