@@ -7,7 +7,7 @@ Fixtures
   ref_loco_ckpt.npz    outputs of the shipped checkpoint data/pretrained/loco_modelV1.pt on a seeded input
                         -- weights are NOT copied (12.5 MB), only sha256 + outputs.
   ref_dataset.npz      load_dataset_for_PhysicsVAE on a synthetic README-format pickle: X / Y arrays and batch sizes.
-  ref_small_variants.npz  tiny model, ELU hidden activations and latent_prior_type=False: init, forward outputs, losses, gradients.
+  ref_small_variants.npz  tiny model; ELU / tanh / sigmoid hidden activations and latent_prior_type=False: init, forward outputs, losses, gradients.
   ref_trajectory.npz   four epochs of the reference's own TrainModel.step() (two world-model epochs, phase switch, two VAE epochs;
                        Adam lr 5e-4, StepLR, batch 32 with a short last batch, latent_prior_noise False so that no RNG is involved):
                        the pickle, the seeded initial state dict, the per-epoch mean_train_loss and the final state dict.
@@ -86,7 +86,8 @@ def small_variants():
     out = {"B": B, "dsb": dsb, "da": da, "z": z, "X": X, "Y": Y}
     torch.manual_seed(7)
     out["eps"] = torch.randn(B, z).numpy()
-    for tag, act, prior in (("elu", "elu", "normal_zero_mean_one_std"), ("noprior", "relu", False)):
+    for tag, act, prior in (("elu", "elu", "normal_zero_mean_one_std"), ("noprior", "relu", False),
+                            ("tanh", "tanh", "normal_zero_mean_one_std"), ("sigmoid", "sigmoid", "normal_zero_mean_one_std")):
         te, md, wm, vf = (tpv.gen_layers(16, 2, act_hidden=act), tpv.gen_layers(24, 3, act_hidden=act), tpv.gen_layers(32, 2, act_hidden=act),
                           tpv.gen_layers(16, 2, act_hidden=act))
         for l in (te, md, wm):

@@ -189,7 +189,8 @@ def test_reference_fixture_forward_losses_gradients():
             assert P.rel_l2(got[k], torch.from_numpy(ref[k])) < 5e-3, k
 
 
-@pytest.mark.parametrize("tag,act,prior", [("elu", "elu", "normal_zero_mean_one_std"), ("noprior", "relu", False)])
+@pytest.mark.parametrize("tag,act,prior", [("elu", "elu", "normal_zero_mean_one_std"), ("noprior", "relu", False),
+                                           ("tanh", "tanh", "normal_zero_mean_one_std"), ("sigmoid", "sigmoid", "normal_zero_mean_one_std")])
 def test_reference_variant_fixture(tag, act, prior):
     """tests/golden/ref_small_variants.npz (generated by the reference itself): ELU hidden activations, and latent_prior_type=False
     (z = encoder output, no KL term) -- forward outputs, both phases' losses and every gradient."""
