@@ -8,6 +8,7 @@ Fixtures
                         -- weights are NOT copied (12.5 MB), only sha256 + outputs.
   ref_dataset.npz      load_dataset_for_PhysicsVAE on a synthetic README-format pickle: X / Y arrays and batch sizes.
   ref_small_variants.npz  tiny model; ELU / tanh / sigmoid hidden activations and latent_prior_type=False: init, forward outputs, losses, gradients.
+  ref_lookahead.npz    compute_loss with lookahead 3 (autoregressive rollout): losses and gradients of both phases.
   ref_trajectory.npz   four epochs of the reference's own TrainModel.step() (two world-model epochs, phase switch, two VAE epochs;
                        Adam lr 5e-4, StepLR, batch 32 with a short last batch, latent_prior_noise False so that no RNG is involved):
                        the pickle, the seeded initial state dict, the per-epoch mean_train_loss and the final state dict.
@@ -119,6 +120,41 @@ def small_variants():
     np.savez_compressed(os.path.join(OUT, "ref_small_variants.npz"), **out)
 
 
+def lookahead():
+    """ref_lookahead.npz: compute_loss with lookahead 3 (the autoregressive rollout, train_physics_vae.py:367-428) on a tiny model:
+    init, X [B, 3, 2*dsb], Y [B, 3, da], the three eps draws, both phases' losses and every gradient."""
+    tpv, tm, rmt = refload.load()
+    dsb, da, z, B, L = 11, 4, 3, 24, 3
+    te, md, wm, vf = tpv.gen_layers(16, 2), tpv.gen_layers(24, 3), tpv.gen_layers(32, 2), tpv.gen_layers(16, 2)
+    for l in (te, md, wm):
+        l[-1]["init_weight"] = {"name": "normc", "std": 0.3}
+    torch.manual_seed(11)
+    model = refload.build_reference_model(dsb, da, z, te, md, wm, vf_layers=vf)
+    data = orc.synthetic_episodes(2, 30, dsb, da, seed=12)
+    X, Y = orc.build_transitions(data["episodes"], num_samples=B, lookahead=L)
+    x, y = torch.Tensor(X), torch.Tensor(Y)
+    out = {"B": B, "L": L, "dsb": dsb, "da": da, "z": z, "X": X, "Y": Y}
+    for k, v in model.state_dict().items():
+        out["sd/" + k] = v.detach().numpy().copy()
+    torch.manual_seed(5)
+    out["eps"] = torch.stack([torch.randn(B, z) for _ in range(L)]).numpy()
+    for world in (True, False):
+        model.zero_grad()
+        model.set_learnable_task_encoder(not world)
+        model.set_learnable_motor_decoder(not world)
+        model.set_learnable_world_model(world)
+        torch.manual_seed(5)
+        loss = refload.reference_compute_loss(model, x, y, world, kl_coeff=1.0, cyc_coeff=0.05, lookahead=L)
+        loss.backward()
+        tag = "world" if world else "vae"
+        out[tag + "/loss"] = float(loss)
+        for k, p_ in model.named_parameters():
+            if p_.grad is not None:
+                out[tag + "/grad/" + k] = p_.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "ref_lookahead.npz"), **out)
+    print("ref_lookahead.npz: world loss %.8f vae loss %.8f" % (out["world/loss"], out["vae/loss"]))
+
+
 def loco_ckpt():
     tpv, tm, rmt = refload.load()
     path = os.path.join(refload.REFERENCE, "data", "pretrained", "loco_modelV1.pt")
@@ -202,3 +238,4 @@ if __name__ == "__main__":
     dataset()
     trajectory()
     small_variants()
+    lookahead()

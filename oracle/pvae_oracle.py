@@ -197,9 +197,43 @@ def compute_loss(model, x, y, world, kl_coeff=1.0, a_rec_coeff=1.0, s_rec_coeff=
     return total, parts
 
 
+def compute_loss_lookahead(model, x, y, world, kl_coeff=1.0, a_rec_coeff=1.0, s_rec_coeff=None, cyc_coeff=1e-3, eps=None):
+    """The general form of compute_loss (train_physics_vae.py:361-435) for `lookahead` L >= 1: x [B, L, 2*dsb], y [B, L, da],
+    eps [L, B, z] or None.  An autoregressive rollout: the body state of step t + 1 is the world model's prediction from the
+    DECODED action of step t (`s1 = self.model._cur_future_state`, :421), so the full forward runs in both phases and gradients
+    flow through time; the four terms are averaged over the L steps (:423-428).  The CLI hard-wires L = 1 (:277), for which this
+    equals compute_loss; the CUDA path does not implement L > 1 yet -- this pins what it will have to match."""
+    if world:
+        a_c, kl_c, s_c, cyc_c = 0.0, 0.0, 1.0, 0.0
+    else:
+        a_c, kl_c, s_c, cyc_c = a_rec_coeff, kl_coeff, (0.0 if s_rec_coeff is None else s_rec_coeff), cyc_coeff
+    dsb, L = model.dsb, x.shape[1]
+    parts = {"a": 0.0, "kl": 0.0, "s": 0.0, "cyc": 0.0}
+    s1 = x[:, 0, :dsb]                                                               # :365
+    for t in range(L):
+        s2_gt, y_gt = x[:, t, dsb:], y[:, t, :]                                      # :369-375
+        logits = model.forward(torch.cat([s1, s2_gt], dim=-1), eps=None if eps is None else eps[t])   # :377-378, always
+        y_t = logits[..., :logits.shape[1] // 2]
+        if a_c > 0.0:
+            parts["a"] = parts["a"] + F.mse_loss(y_t, y_gt)                          # :381-382
+            if model.latent_prior_type and kl_c > 0.0:
+                mu, logvar = model.cur["mu"], model.cur["logvar"]
+                parts["kl"] = parts["kl"] + torch.mean(-0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp(), dim=1), dim=0)
+        if s_c > 0:
+            parts["s"] = parts["s"] + F.mse_loss(model.forward_world(s1, y_gt), s2_gt)    # :412-414
+        if cyc_c > 0:
+            parts["cyc"] = parts["cyc"] + F.mse_loss(model.cur["future"], s2_gt)     # :417-419
+        s1 = model.cur["future"]                                                     # :421
+    if L > 1:
+        parts = {k: v / float(L) for k, v in parts.items()}                          # :423-428
+    total = a_c * parts["a"] + kl_c * parts["kl"] + s_c * parts["s"] + cyc_c * parts["cyc"]
+    return total, parts
+
+
 def loss_and_grads(model, x, y, world, **kw):
     """compute_loss + loss.backward() (torch_models.py:141-142) for the nets that are learnable in this phase.
-    Returns (loss float, parts, {param name: grad}).  Frozen nets are differentiated through but get no grads."""
+    Returns (loss float, parts, {param name: grad}).  Frozen nets are differentiated through but get no grads.
+    x with a lookahead axis ([B, L, 2*dsb]) selects compute_loss_lookahead."""
     train_nets = ["_world_model"] if world else ["_task_encoder", "_motor_decoder"]
     saved = model.params
     leaf = {}
@@ -209,7 +243,7 @@ def loss_and_grads(model, x, y, world, **kw):
         leaf[k] = t
     model.params = leaf
     try:
-        total, parts = compute_loss(model, x, y, world, **kw)
+        total, parts = (compute_loss_lookahead if x.dim() == 3 else compute_loss)(model, x, y, world, **kw)
         total.backward()
     finally:
         model.params = saved

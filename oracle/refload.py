@@ -68,13 +68,13 @@ class _Shell(object):
     """Just enough of train_physics_vae.TrainModel to call the reference's unbound compute_loss on a model."""
 
 
-def reference_compute_loss(model, x, y, world, kl_coeff=1.0, cyc_coeff=1e-3, prior="normal_zero_mean_one_std"):
+def reference_compute_loss(model, x, y, world, kl_coeff=1.0, cyc_coeff=1e-3, prior="normal_zero_mean_one_std", lookahead=1):
     """Calls the reference's own TrainModel.compute_loss (train_physics_vae.py:361-435) on x [B,1,2dsb], y [B,1,da]."""
     import torch
     tpv, tm, rmt = load()
     sh = _Shell()
     sh.model = model
-    sh.lookahead = 1
+    sh.lookahead = lookahead
     sh.latent_prior_type = prior
     sh.loss_fn = tm.get_loss_fn("MSE")
     sh.vae_kl_coeff = 0.0 if world else kl_coeff

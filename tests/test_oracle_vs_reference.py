@@ -97,3 +97,40 @@ def test_trainer_trajectory_matches_live_reference():
         assert abs(o["mean_train_loss"] - r["mean_train_loss"]) <= 2e-6 * abs(r["mean_train_loss"]), (it, o, r)
     for k, v in ref.model.state_dict().items():
         np.testing.assert_allclose(m.params[k].numpy(), v.numpy(), rtol=2e-5, atol=2e-7, err_msg=k)
+
+
+def test_lookahead_rollout_matches_live_reference():
+    """lookahead 3: the autoregressive rollout of compute_loss (train_physics_vae.py:367-428) -- both phases, losses and every
+    gradient (gradients flow through the predicted states), against the reference's own code."""
+    tpv, tm, rmt = refload.load()
+    dsb, da, z, B, L = 11, 4, 3, 24, 3
+    te, md, wm, vf = tpv.gen_layers(16, 2), tpv.gen_layers(24, 3), tpv.gen_layers(32, 2), tpv.gen_layers(16, 2)
+    for l in (te, md, wm):
+        l[-1]["init_weight"] = {"name": "normc", "std": 0.3}
+    torch.manual_seed(11)
+    ref = refload.build_reference_model(dsb, da, z, te, md, wm, vf_layers=vf)
+    m = orc.OracleModel(dsb, da, z, te, md, wm, vf)
+    m.load_state_dict({k: v.detach().clone() for k, v in ref.state_dict().items()})
+    data = orc.synthetic_episodes(2, 30, dsb, da, seed=12)
+    X, Y = orc.build_transitions(data["episodes"], num_samples=B, lookahead=L)
+    assert X.shape == (B, L, 2 * dsb) and Y.shape == (B, L, da)
+    x, y = torch.Tensor(X), torch.Tensor(Y)
+    for world in (True, False):
+        ref.zero_grad()
+        ref.set_learnable_task_encoder(not world); ref.set_learnable_motor_decoder(not world); ref.set_learnable_world_model(world)
+        torch.manual_seed(5)
+        loss = refload.reference_compute_loss(ref, x, y, world, kl_coeff=1.0, cyc_coeff=0.05, lookahead=L)
+        loss.backward()
+        torch.manual_seed(5)
+        eps = torch.stack([torch.randn(B, z) for _ in range(L)])           # one randn_like draw per forward, in step order
+        o_loss, parts, grads = orc.loss_and_grads(m, x, y, world, kl_coeff=1.0, cyc_coeff=0.05, eps=eps)
+        assert abs(o_loss - float(loss)) <= 1e-6 * abs(float(loss)), (world, o_loss, float(loss))
+        want = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+        assert set(grads) == set(want)
+        for k in want:
+            np.testing.assert_allclose(grads[k].numpy(), want[k].numpy(), rtol=2e-5, atol=1e-9, err_msg=k)
+    # lookahead 1 through the general form == the specialised compute_loss
+    x1, y1 = x[:, :1, :], y[:, :1, :]
+    a = orc.loss_and_grads(m, x1, y1, False, cyc_coeff=0.05, eps=eps[:1])
+    b = orc.loss_and_grads(m, x1[:, 0, :], y1[:, 0, :], False, cyc_coeff=0.05, eps=eps[0])
+    assert abs(a[0] - b[0]) <= 1e-7 * abs(b[0]) and all(torch.allclose(a[2][k], b[2][k], rtol=1e-6, atol=1e-9) for k in b[2])
