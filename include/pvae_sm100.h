@@ -10,7 +10,7 @@
  *     nothing throws across the ABI.
  *   - all pointers named *_dev are device pointers owned by the caller (PyTorch's caching allocator); the library
  *     allocates only its handle, bf16 shadow weights, TMA descriptors and a few scalars, and frees them in pvae_destroy.
- *   - all work is enqueued on the given stream, never synchronises, never allocates after pvae_plan(): every step
+ *   - all work is enqueued on the given stream, never synchronises, never allocates after pvae_create(): every step
  *     entry point is CUDA-graph capturable.
  *   - a handle is not thread-safe; distinct handles are independent (one per process / GPU).
  *   - fp32 parameters / gradients use the reference's nn.Linear layout: W[out][in] row-major, b[out].
@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PVAE_ABI_VERSION 1
+#define PVAE_ABI_VERSION 2
 #define PVAE_MAX_LAYERS 8
 
 typedef struct pvae_engine* pvae_handle;
@@ -35,7 +35,7 @@ enum pvae_status {
   PVAE_OK = 0,
   PVAE_ERR_INVALID = -1,                   /* bad argument / unsupported configuration */
   PVAE_ERR_CUDA = -2,                      /* a CUDA runtime / driver call failed */
-  PVAE_ERR_STATE = -3                      /* call order violated (not planned / not bound) */
+  PVAE_ERR_STATE = -3                      /* call order violated (nothing bound yet) */
 };
 
 /* activation registry of the reference: get_activation_fn, rllib_model_torch.py:30-46 */
@@ -55,6 +55,9 @@ typedef struct {
   int32_t n_layers;                        /* number of Linear layers (hidden + output); 0 = net absent */
   int32_t out_dims[PVAE_MAX_LAYERS];       /* nn.Linear out_features per layer */
   int32_t acts[PVAE_MAX_LAYERS];           /* pvae_act per layer */
+  int32_t in_dims[2];                      /* {0, 0}: input widths follow from the net's role.  {k0 > 0, k1 >= 0}: a stand-alone FC
+                                              stack whose input is k0 (+ k1) columns wide; such a net runs through pvae_fc_forward
+                                              only and its output width is free (FC(size_in, size_out, layers), :234-246) */
 } pvae_net_desc;
 
 /* PhysicsVAE.__init__ (rllib_model_torch.py:511-727), default wiring: encoder sees (body, task), decoder sees (body, z) */
@@ -71,7 +74,7 @@ typedef struct {
 /* loss bookkeeping written by the step functions (device, fp32):
  *   [0] total  [1] MSE(a, a_hat)  [2] KL  [3] MSE(s2, world(s1, a_gt))  [4] MSE(s2, world(s1, a_hat))
  * weights as in train_physics_vae.py:430-434 */
-#define PVAE_LOSS_SLOTS 8
+#define PVAE_LOSS_SLOTS 8                   /* slots 5-7 are reserved (callers allocate 8 floats) */
 
 const char* pvae_last_error(void);
 int pvae_abi_version(void);
@@ -149,7 +152,23 @@ int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pv
 int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
                   float kl_coeff, float cyc_coeff, float* loss_dev, pvae_stream s);
 
+/* Forward + loss only (no gradients are touched): the test pass of the reference, `with torch.no_grad(): compute_test_loss`
+ * (torch_models.py:147-155).  phase 0: world model, loss = s_coeff * MSE(s2, WM(cat[s1, a_gt])); phase 1: the VAE loss with the
+ * arguments of pvae_vae_step.  loss_dev as for the step functions. */
+int pvae_eval_loss(pvae_handle h, int phase, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
+                   float kl_coeff, float s_coeff, float cyc_coeff, float* loss_dev, pvae_stream s);
+
+/* Device-side counter of the Philox noise stream.  enable != 0: every pvae_vae_step / pvae_eval_loss call that draws noise itself
+ * (eps_dev == NULL, noise != 0) uses offset + counter as its stream offset and adds `stride` to the counter when it finishes, so a
+ * captured CUDA graph draws fresh noise on every replay (the reference draws torch.randn_like per call, rllib_model_torch.py:737).
+ * The call (re)sets the counter to `value`.  enable == 0 (default): the offset argument is used as given. */
+int pvae_noise_counter(pvae_handle h, int enable, uint64_t value, uint64_t stride, pvae_stream s);
+
 /* --- inference API ------------------------------------------------------------------------------------------- */
+/* FC.forward of one net (rllib_model_torch.py:274-275): out[batch][out_width] = FC(in[batch][in_width]), fp32 rows in and out
+ * (row strides in_ld / out_ld, elements); for a net with two input segments `in` is their concatenation. */
+int pvae_fc_forward(pvae_handle h, int net, int batch, const float* in_dev, int64_t in_ld, float* out_dev, int64_t out_ld, pvae_stream s);
+
 /* PhysicsVAE.forward and its parts (rllib_model_torch.py:742-853).  obs_dev: fp32 [batch][2*dsb] (row stride obs_ld).
  * parts: bit 0 encoder (+reparameterise), bit 1 decoder, bit 2 world, bit 3 value branch.
  * Inputs consumed only when the producing part is not run: z_in_dev ([batch][z], decoder without encoder),

@@ -7,7 +7,7 @@ imported from here.
 import ctypes as C
 import os
 
-PVAE_ABI_VERSION = 1
+PVAE_ABI_VERSION = 2
 PVAE_MAX_LAYERS = 8
 PVAE_NUM_NETS = 4
 PVAE_LOSS_SLOTS = 8
@@ -28,12 +28,13 @@ SYMBOLS = [
     "pvae_last_error", "pvae_abi_version", "pvae_create", "pvae_destroy", "pvae_bind_net", "pvae_net_grad_elems",
     "pvae_sync_weights", "pvae_adam_step", "pvae_workspace_bytes", "pvae_bind_workspace", "pvae_transitions_bytes", "pvae_ingest", "pvae_ingest_episodes",
     "pvae_bind_transitions", "pvae_set_cursor", "pvae_advance_cursor", "pvae_world_step", "pvae_vae_step",
-    "pvae_forward", "pvae_gemm_bf16", "pvae_launch_count", "pvae_debug_trace",
+    "pvae_forward", "pvae_gemm_bf16", "pvae_launch_count", "pvae_debug_trace", "pvae_eval_loss", "pvae_noise_counter", "pvae_fc_forward",
 ]
 
 
 class NetDesc(C.Structure):
-    _fields_ = [("n_layers", C.c_int32), ("out_dims", C.c_int32 * PVAE_MAX_LAYERS), ("acts", C.c_int32 * PVAE_MAX_LAYERS)]
+    _fields_ = [("n_layers", C.c_int32), ("out_dims", C.c_int32 * PVAE_MAX_LAYERS), ("acts", C.c_int32 * PVAE_MAX_LAYERS),
+                ("in_dims", C.c_int32 * 2)]
 
 
 class ModelDesc(C.Structure):
@@ -81,6 +82,9 @@ def load():
     lib.pvae_world_step.argtypes = [vp, i32, f32, vp, vp]
     lib.pvae_vae_step.argtypes = [vp, i32, vp, u64, u64, i32, f32, f32, f32, vp, vp]
     lib.pvae_forward.argtypes = [vp, u32, i32, vp, i64, vp, vp, i64, vp, i32, u64, u64, vp, i64, vp, vp, vp, vp, vp, vp]
+    lib.pvae_eval_loss.argtypes = [vp, i32, i32, vp, u64, u64, i32, f32, f32, f32, f32, vp, vp]
+    lib.pvae_noise_counter.argtypes = [vp, i32, u64, u64, vp]
+    lib.pvae_fc_forward.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp]
     lib.pvae_gemm_bf16.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.pvae_debug_trace.argtypes = [vp, i32, i32]
     lib.pvae_launch_count.restype = u64

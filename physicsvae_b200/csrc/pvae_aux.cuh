@@ -250,8 +250,9 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ ml, const float* __
                                    int has_lv, int noise, uint64_t seed, uint64_t offset, int B, int z,
                                    __nv_bfloat16* __restrict__ zb, int64_t z_ld, int64_t z_ps, int planes,
                                    float* __restrict__ z_f32, float* __restrict__ mu_out, float* __restrict__ lv_out,
-                                   double* __restrict__ kl_acc) {
+                                   double* __restrict__ kl_acc, const unsigned long long* __restrict__ noise_ctr) {
   const int64_t total = (int64_t)B * z;
+  if (noise_ctr) offset += *noise_ctr;           // device-side step counter of the Philox stream (graph replays draw fresh noise)
   const int w = has_lv ? 2 * z : z;
   float kl = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -339,8 +340,10 @@ __global__ void f32_to_planes_kernel(const float* __restrict__ src, int64_t src_
 // acc: [0] sum sq a, [1] sum kl, [2] sum sq s (world), [3] sum sq cyc
 // (the accumulators are cleared here, for the next step: one memset node less per step)
 __global__ void finalize_loss_kernel(double* __restrict__ acc, float* __restrict__ loss, int B, int da, int dsb,
-                                     float a_c, float kl_c, float s_c, float cyc_c) {
+                                     float a_c, float kl_c, float s_c, float cyc_c, unsigned long long* __restrict__ noise_ctr,
+                                     unsigned long long noise_stride) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (noise_ctr) *noise_ctr += noise_stride;
     const float la = (float)(acc[0] / ((double)B * da));
     const float lk = (float)(acc[1] / (double)B);
     const float ls = (float)(acc[2] / ((double)B * dsb));
@@ -352,6 +355,7 @@ __global__ void finalize_loss_kernel(double* __restrict__ acc, float* __restrict
 }
 
 __global__ void set_cursor_kernel(int32_t* cur, int32_t v) { if (threadIdx.x == 0) *cur = v; }
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { if (threadIdx.x == 0) *p = v; }
 __global__ void advance_cursor_kernel(int32_t* cur, int32_t delta, int32_t batch, int32_t limit) {
   if (threadIdx.x == 0) {
     int32_t c = *cur + delta;

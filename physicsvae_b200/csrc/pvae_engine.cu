@@ -117,6 +117,7 @@ struct Device {
   int pdl = 1;            // PVAE_PDL=0: plain stream-ordered GEMM launches
   int snake = 1;          // PVAE_SNAKE=0: every GEMM walks the batch front to back (see batch_direction)
   int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
+  int fast_epi = 1;       // PVAE_FAST_EPI=0: never use the lean ReLU store / dgrad epilogue (A/B experiments)
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
@@ -239,6 +240,7 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   // TMA epilogue: one precision plane, bf16 primary output; ReLU dgrad needs the sign-bit mask its forward wrote
   const bool has_aux = e.type == EPI_MSE || (e.type == EPI_DGRAD && e.act != ACT_LINEAR && e.act != ACT_RELU);
   const bool tma = dev.tma_epilogue && e.type != EPI_WGRAD && e.out != nullptr && e.out_planes == 1 &&
+                   !(e.type == EPI_STORE && e.out2 != nullptr) &&       // (swish forward keeping its pre-activation: direct epilogue)
                    !(e.type == EPI_DGRAD && e.act == ACT_RELU && e.mask == nullptr) &&
                    (!has_aux || (e.aux != nullptr && e.aux_planes == 1 && (reinterpret_cast<uintptr_t>(e.aux) & 15) == 0));
   if (tma) {
@@ -252,7 +254,12 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   const int units = cdiv(p.m_tiles, cluster) * n_tiles * splits;       // units per CTA (pair)
   const int slots = dev.sms / cluster;
   const int grid = (units < slots ? units : slots) * cluster;
-  GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act, tma, cluster);
+  // lean epilogue: ReLU store / dgrad whose tiles have no ragged edge and no optional operand (the kernel's FAST block)
+  const bool fast = dev.fast_epi && tma && cluster == 2 && e.act == ACT_RELU && (e.type == EPI_STORE || e.type == EPI_DGRAD) &&
+                    d.M % (BM * cluster) == 0 && d.N % 32 == 0 && bn % 32 == 0 && !d.mseg && d.m_gap == 0 && e.add == nullptr &&
+                    e.out_f32 == nullptr && e.mask != nullptr && (e.type == EPI_DGRAD || e.bias != nullptr) && dev.cs_mma == 0 &&
+                    splits == 1 && (!DEBUG_HOOKS || p.dbg == 0);
+  GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act, tma, cluster, fast);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid, 1, 1);
@@ -271,8 +278,8 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   }
   static const int log_level = getenv("PVAE_LOG_GEMM") ? atoi(getenv("PVAE_LOG_GEMM")) : 0;   // 1: print every launch, 2: and synchronise after it
   if (log_level)
-    fprintf(stderr, "[pvae_gemm] epi %d act %d tma %d cg %d | M %d N %d K %d+%d majors %d%d passes %d | m_tiles %d n_tiles %d bn %d splits %d grid %d | b_k0 %d,%d b_n0 %d mseg %d rev %d\n",
-            p.epi.type, p.epi.act, (int)tma, cluster, d.M, d.N, d.K[0], d.nseg > 1 ? d.K[1] : 0, d.a_major, d.b_major, d.passes, p.m_tiles, n_tiles, bn,
+    fprintf(stderr, "[pvae_gemm] epi %d act %d tma %d cg %d fast %d | M %d N %d K %d+%d majors %d%d passes %d | m_tiles %d n_tiles %d bn %d splits %d grid %d | b_k0 %d,%d b_n0 %d mseg %d rev %d\n",
+            p.epi.type, p.epi.act, (int)tma, cluster, (int)fast, d.M, d.N, d.K[0], d.nseg > 1 ? d.K[1] : 0, d.a_major, d.b_major, d.passes, p.m_tiles, n_tiles, bn,
             splits, grid, p.b_k0[0], p.b_k0[1], p.b_n0, p.m_seg_tiles, p.reverse);
   CK(cudaLaunchKernelEx(&cfg, fn, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -301,6 +308,7 @@ struct Net {
   int act_ld[PVAE_MAX_LAYERS];
   int mask_ld[PVAE_MAX_LAYERS];
   bool bound = false;
+  bool generic = false;        // input widths given explicitly (stand-alone FC): usable through pvae_fc_forward only
 };
 
 struct NetIO {     // what feeds layer 0: one or two column segments (the reference's torch.cat inputs)
@@ -338,6 +346,9 @@ struct pvae_engine {
   double* acc = nullptr;    // [4] loss accumulators
   bool acc_dirty = false;   // a step was entered but its finalize kernel (which clears acc) was not enqueued
   unsigned int* adam_counter = nullptr;   // finished-blocks counter of adam_net_kernel
+  unsigned long long* noise_ctr = nullptr;   // device-side Philox offset counter (pvae_noise_counter)
+  bool noise_auto = false;
+  unsigned long long noise_stride = 1;
 };
 
 namespace pvae {
@@ -371,6 +382,8 @@ static size_t carve(pvae_engine* h, uint8_t* base) {
   h->zb_ld = rup(h->z, 64);
   h->a_ld = rup(h->da, 64);
   h->x_ld = rup(h->dsbp + h->dsb, 64);
+  for (int n = 0; n < PVAE_NUM_NETS; ++n)
+    if (h->nets[n].n_layers) { const int need = rup(rup(h->nets[n].k0, 64) + h->nets[n].k1, 64); if (need > h->x_ld) h->x_ld = need; }
   h->zb = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->zb_ld * 2));
   h->ahat = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
   h->ga = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
@@ -416,7 +429,8 @@ static View ty_view(const pvae_engine* h, int width) {
 
 // ---- forward through one FC stack (rllib_model_torch.FC.forward, rllib_model_torch.py:274-275) -----------------------
 // `last` is the epilogue of the output layer (type/outputs/loss wiring chosen by the caller).
-static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, const EpiParams& last, cudaStream_t st) {
+// keep_preact: a backward pass follows (swish layers then store their pre-activation in the layer's gradient buffer).
+static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, const EpiParams& last, cudaStream_t st, bool keep_preact = false) {
   if (!net.bound) return fail(PVAE_ERR_STATE, "net not bound (pvae_bind_net)");
   for (int l = 0; l < net.n_layers; ++l) {
     GemmDesc d;
@@ -438,6 +452,7 @@ static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, con
       d.epi.type = EPI_STORE; d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
       set_out(d.epi, h, net.act[l], net.act_ld[l]);
       d.epi.mask = net.mask[l]; d.epi.mask_ld = h->max_batch;
+      if (net.acts[l] == ACT_SWISH && net.g[l] && keep_preact) set_out2(d.epi, h, net.g[l], net.act_ld[l]);
     } else {
       d.epi = last;
       d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
@@ -489,7 +504,8 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
       d.M = batch; d.N = net.out_dims[l - 1];
       d.passes = h->passes;
       d.epi.type = EPI_DGRAD; d.epi.act = net.acts[l - 1];
-      const View al = ws_view(h, net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
+      // act' needs the forward output -- for swish the pre-activation, which the forward pass left in g[l - 1] (overwritten in place here)
+      const View al = ws_view(h, net.acts[l - 1] == ACT_SWISH ? net.g[l - 1] : net.act[l - 1], net.act_ld[l - 1], net.out_dims[l - 1], batch);
       if (net.acts[l - 1] != ACT_LINEAR) set_aux(d.epi, al, 0);
       d.epi.mask = net.mask[l - 1]; d.epi.mask_ld = h->max_batch;
       set_out(d.epi, h, net.g[l - 1], net.act_ld[l - 1]);
@@ -511,8 +527,6 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
 }
 
 static int check_trainable_acts(const Net& net) {
-  for (int l = 0; l < net.n_layers - 1; ++l)
-    if (net.acts[l] == ACT_SWISH) return fail(PVAE_ERR_INVALID, "swish hidden layers are forward-only in this build");
   if (net.n_layers > 0 && net.acts[net.n_layers - 1] != ACT_LINEAR)
     return fail(PVAE_ERR_INVALID, "the training steps need a linear output layer (train_physics_vae.py:188-190)");
   return PVAE_OK;
@@ -544,6 +558,8 @@ static int ensure_kernel_attr(Device& dev) {
       for (int tma = 0; tma < 2; ++tma)
         for (int cg = 1; cg <= 2; ++cg)
           CK(cudaFuncSetAttribute(select_kernel(epi, act, tma != 0, cg), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(select_kernel(EPI_STORE, ACT_RELU, true, 2, true), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(select_kernel(EPI_DGRAD, ACT_RELU, true, 2, true), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   dev.attr_set = true;
   return PVAE_OK;
 }
@@ -573,6 +589,8 @@ static int init_device(Device& dev, int device) {
   if (env) dev.snake = atoi(env) != 0;
   env = getenv("PVAE_CS_MMA");
   if (env) dev.cs_mma = atoi(env) != 0;
+  env = getenv("PVAE_FAST_EPI");
+  if (env) dev.fast_epi = atoi(env) != 0;
   env = getenv("PVAE_CLUSTER");
   if (env) dev.cluster = atoi(env) == 1 ? 1 : 2;
   CKR(resolve_driver());
@@ -618,6 +636,11 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
       case PVAE_NET_WORLD_MODEL: net.k0 = h->dsb; net.k1 = h->da; break;
       default: net.k0 = h->dsb; net.k1 = h->dsb; break;
     }
+    if (nd.in_dims[0] > 0) {       // stand-alone FC stack (pvae_fc_forward only): explicit input segments instead of the role's
+      if (nd.in_dims[1] < 0) { delete h; return fail(PVAE_ERR_INVALID, "net %d: bad input override", n); }
+      net.k0 = nd.in_dims[0]; net.k1 = nd.in_dims[1];
+      net.generic = true;
+    }
     net.in_dim = net.k0 + net.k1;
     // layer-0 shadow columns: the second input segment's weights start at the next 16-byte boundary behind the first one's (a TMA
     // box coordinate must be a multiple of 16 bytes: an odd start raises an illegal-instruction fault) -- a two-segment A operand
@@ -640,7 +663,7 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
   const int want[PVAE_NUM_NETS] = {h->te_out, h->da, h->dsb, 1};
   for (int n = 0; n < PVAE_NUM_NETS; ++n) {
     Net& net = h->nets[n];
-    if (net.n_layers && net.out_dims[net.n_layers - 1] != want[n]) {
+    if (net.n_layers && !net.generic && net.out_dims[net.n_layers - 1] != want[n]) {
       int got = net.out_dims[net.n_layers - 1];
       delete h;
       return fail(PVAE_ERR_INVALID, "net %d: output width %d, expected %d", n, got, want[n]);
@@ -660,6 +683,8 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
   }
   if (cudaMalloc(&h->adam_counter, sizeof(unsigned int)) == cudaSuccess) cudaMemset(h->adam_counter, 0, sizeof(unsigned int));
   else h->adam_counter = nullptr;
+  if (cudaMalloc(&h->noise_ctr, sizeof(unsigned long long)) == cudaSuccess) cudaMemset(h->noise_ctr, 0, sizeof(unsigned long long));
+  else h->noise_ctr = nullptr;
   cudaMemset(h->dev.cursor, 0, sizeof(int32_t));
   cudaMemset(h->acc, 0, 4 * sizeof(double));
   h->ws_bytes = carve(h, nullptr);
@@ -674,6 +699,7 @@ int pvae_destroy(pvae_handle h) {
       if (h->nets[n].Wsh[l]) cudaFree(h->nets[n].Wsh[l]);
   if (h->acc) cudaFree(h->acc);
   if (h->adam_counter) cudaFree(h->adam_counter);
+  if (h->noise_ctr) cudaFree(h->noise_ctr);
   if (h->dev.cursor) cudaFree(h->dev.cursor);
   delete h;
   return PVAE_OK;
@@ -874,16 +900,19 @@ static int step_prologue(pvae_handle h, int batch) {
   return PVAE_OK;
 }
 
-int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pvae_stream s) {
+static int world_impl(pvae_handle h, int batch, float s_coeff, float* loss_dev, pvae_stream s, bool backward) {
   CKR(step_prologue(h, batch));
   if (!h->tbuf) return fail(PVAE_ERR_STATE, "no transition buffer bound (pvae_bind_transitions)");
   if (!loss_dev) return fail(PVAE_ERR_INVALID, "null loss pointer");
   cudaStream_t st = (cudaStream_t)s;
   Net& wm = h->nets[PVAE_NET_WORLD_MODEL];
   if (wm.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no world model");
+  if (wm.generic) return fail(PVAE_ERR_INVALID, "a net with explicit input widths runs through pvae_fc_forward only");
   CKR(check_trainable_acts(wm));
-  if (!wm.grad) return fail(PVAE_ERR_STATE, "world model has no gradient buffer bound");
-  CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
+  if (backward) {
+    if (!wm.grad) return fail(PVAE_ERR_STATE, "world model has no gradient buffer bound");
+    CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
+  }
   if (h->acc_dirty) CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));   // only after a step that failed half-way: finalize clears them
   h->acc_dirty = true;
   NetIO in;                       // cat[s_t, a_t] (train_physics_vae.py:412-413) = the first dsb8 + da columns of a resident row
@@ -896,19 +925,23 @@ int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pv
   set_aux(last, tx_view(h, h->dsbp, h->dsb), 0);
   last.scale = 2.f * s_coeff / ((float)batch * (float)h->dsb);
   set_out(last, h, wm.g[L - 1], wm.act_ld[L - 1]);
-  last.colsum = wm.grad + wm.gb[L - 1];
+  last.colsum = backward ? wm.grad + wm.gb[L - 1] : nullptr;
   last.loss = h->acc + 2;
-  CKR(net_forward(h, wm, in, batch, last, st));
-  CKR(net_backward(h, wm, in, batch, true, nullptr, st));
-  finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, 0.f, 0.f, s_coeff, 0.f);
+  CKR(net_forward(h, wm, in, batch, last, st, backward));
+  if (backward) CKR(net_backward(h, wm, in, batch, true, nullptr, st));
+  finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, 0.f, 0.f, s_coeff, 0.f, nullptr, 0ull);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   h->acc_dirty = false;
   return PVAE_OK;
 }
 
-int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
-                  float kl_coeff, float cyc_coeff, float* loss_dev, pvae_stream s) {
+int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pvae_stream s) {
+  return world_impl(h, batch, s_coeff, loss_dev, s, true);
+}
+
+static int vae_impl(pvae_handle h, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
+                    float kl_coeff, float cyc_coeff, float* loss_dev, pvae_stream s, bool backward) {
   CKR(step_prologue(h, batch));
   if (!h->tbuf) return fail(PVAE_ERR_STATE, "no transition buffer bound (pvae_bind_transitions)");
   if (!loss_dev) return fail(PVAE_ERR_INVALID, "null loss pointer");
@@ -917,14 +950,18 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
   Net& md = h->nets[PVAE_NET_MOTOR_DECODER];
   Net& wm = h->nets[PVAE_NET_WORLD_MODEL];
   if (te.n_layers == 0 || md.n_layers == 0) return fail(PVAE_ERR_INVALID, "model has no encoder / decoder");
+  if (te.generic || md.generic || wm.generic) return fail(PVAE_ERR_INVALID, "a net with explicit input widths runs through pvae_fc_forward only");
   const bool cyc = cyc_coeff != 0.f && wm.n_layers > 0;
   CKR(check_trainable_acts(te));
   CKR(check_trainable_acts(md));
   if (cyc) CKR(check_trainable_acts(wm));
-  if (!te.grad || !md.grad) return fail(PVAE_ERR_STATE, "encoder / decoder have no gradient buffers bound");
   const int prior = h->desc.latent_prior;
-  CK(cudaMemsetAsync(te.grad, 0, te.grad_elems * sizeof(float), st));
-  CK(cudaMemsetAsync(md.grad, 0, md.grad_elems * sizeof(float), st));
+  if (backward) {
+    if (!te.grad || !md.grad) return fail(PVAE_ERR_STATE, "encoder / decoder have no gradient buffers bound");
+    CK(cudaMemsetAsync(te.grad, 0, te.grad_elems * sizeof(float), st));
+    CK(cudaMemsetAsync(md.grad, 0, md.grad_elems * sizeof(float), st));
+  }
+  const bool draws = prior && noise && !eps_dev;     // the step consumes the Philox stream
   if (h->acc_dirty) CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));   // only after a step that failed half-way: finalize clears them
   h->acc_dirty = true;
   const int z = h->z, Lte = te.n_layers, Lmd = md.n_layers, Lwm = wm.n_layers;
@@ -934,13 +971,14 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
   EpiParams e;
   memset(&e, 0, sizeof(e));
   e.type = EPI_STORE; e.out_f32 = h->ml; e.f32_sm = h->te_out; e.f32_sn = 1;
-  CKR(net_forward(h, te, te_in, batch, e, st));
+  CKR(net_forward(h, te, te_in, batch, e, st, backward));
   // z = mu + eps * exp(0.5 logvar), KL partial sums                     rllib_model_torch.py:734-740, train_physics_vae.py:384-389
   {
     const int64_t total = (int64_t)batch * z;
     reparam_fwd_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(h->ml, eps_dev, h->eps, prior, prior && noise, seed, offset, batch, z,
                                                                          h->zb, h->zb_ld, plane_elems(h, h->zb_ld), h->planes, nullptr,
-                                                                         nullptr, nullptr, (prior && kl_coeff != 0.f) ? h->acc + 1 : nullptr);
+                                                                         nullptr, nullptr, (prior && kl_coeff != 0.f) ? h->acc + 1 : nullptr,
+                                                                         (draws && h->noise_auto) ? h->noise_ctr : nullptr);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   // decoder: a_hat = MD(cat[s1, z]); action reconstruction loss          rllib_model_torch.py:822-837, train_physics_vae.py:381-382
@@ -955,9 +993,9 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
     set_out(e, h, h->ga, h->a_ld);
   } else {
     set_out(e, h, md.g[Lmd - 1], md.act_ld[Lmd - 1]);
-    e.colsum = md.grad + md.gb[Lmd - 1];
+    e.colsum = backward ? md.grad + md.gb[Lmd - 1] : nullptr;
   }
-  CKR(net_forward(h, md, md_in, batch, e, st));
+  CKR(net_forward(h, md, md_in, batch, e, st, backward));
   NetIO wm_in;
   if (cyc) {
     // frozen world model on the decoded action: cycle loss                rllib_model_torch.py:839-844, train_physics_vae.py:417-419
@@ -969,15 +1007,18 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
     e.scale = 2.f * cyc_coeff / ((float)batch * (float)h->dsb);
     e.loss = h->acc + 3;
     set_out(e, h, wm.g[Lwm - 1], wm.act_ld[Lwm - 1]);
-    CKR(net_forward(h, wm, wm_in, batch, e, st));
+    CKR(net_forward(h, wm, wm_in, batch, e, st, backward));
     // d/d a_hat through the frozen world model, plus the action-loss gradient -> decoder output gradient
+    if (backward) {
     memset(&e, 0, sizeof(e));
     e.type = EPI_DGRAD; e.act = ACT_LINEAR;
     e.add = h->ga; e.add_ld = h->a_ld; e.add_ps = plane_elems(h, h->a_ld); e.add_planes = h->planes;
     set_out(e, h, md.g[Lmd - 1], md.act_ld[Lmd - 1]);
     e.colsum = md.grad + md.gb[Lmd - 1];
     CKR(net_backward(h, wm, wm_in, batch, false, &e, st));
+    }
   }
+  if (backward) {
   // decoder backward; gradient w.r.t. z lands in dz (fp32)
   memset(&e, 0, sizeof(e));
   e.type = EPI_DGRAD; e.act = ACT_LINEAR;
@@ -996,9 +1037,62 @@ int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed,
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   CKR(net_backward(h, te, te_in, batch, true, nullptr, st));
-  finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, a_coeff, prior ? kl_coeff : 0.f, 0.f, cyc ? cyc_coeff : 0.f);
+  }
+  finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, a_coeff, prior ? kl_coeff : 0.f, 0.f, cyc ? cyc_coeff : 0.f,
+                                         (draws && h->noise_auto) ? h->noise_ctr : nullptr, h->noise_stride);
   h->acc_dirty = false;
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
+                  float kl_coeff, float cyc_coeff, float* loss_dev, pvae_stream s) {
+  return vae_impl(h, batch, eps_dev, seed, offset, noise, a_coeff, kl_coeff, cyc_coeff, loss_dev, s, true);
+}
+
+int pvae_eval_loss(pvae_handle h, int phase, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
+                   float kl_coeff, float s_coeff, float cyc_coeff, float* loss_dev, pvae_stream s) {
+  if (phase == 0) return world_impl(h, batch, s_coeff, loss_dev, s, false);
+  if (phase == 1) return vae_impl(h, batch, eps_dev, seed, offset, noise, a_coeff, kl_coeff, cyc_coeff, loss_dev, s, false);
+  return fail(PVAE_ERR_INVALID, "phase must be 0 (world model) or 1 (VAE)");
+}
+
+int pvae_noise_counter(pvae_handle h, int enable, uint64_t value, uint64_t stride, pvae_stream s) {
+  if (!h) return fail(PVAE_ERR_INVALID, "null handle");
+  if (!h->noise_ctr) return fail(PVAE_ERR_CUDA, "noise counter was not allocated");
+  h->noise_auto = enable != 0;
+  h->noise_stride = stride ? stride : 1;
+  set_u64_kernel<<<1, 32, 0, (cudaStream_t)s>>>(h->noise_ctr, (unsigned long long)value);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+// FC.forward (rllib_model_torch.py:274-275) of one net on fp32 rows handed in by the caller.
+int pvae_fc_forward(pvae_handle h, int net_id, int batch, const float* in_dev, int64_t in_ld, float* out_dev, int64_t out_ld, pvae_stream s) {
+  CKR(step_prologue(h, batch));
+  if (net_id < 0 || net_id >= PVAE_NUM_NETS) return fail(PVAE_ERR_INVALID, "bad net id");
+  Net& net = h->nets[net_id];
+  if (net.n_layers == 0) return fail(PVAE_ERR_INVALID, "net %d is absent from the model description", net_id);
+  if (!in_dev || !out_dev) return fail(PVAE_ERR_INVALID, "null argument");
+  const int out_w = net.out_dims[net.n_layers - 1];
+  if (in_ld < net.in_dim || out_ld < out_w) return fail(PVAE_ERR_INVALID, "row strides %lld / %lld too small for %d -> %d", (long long)in_ld, (long long)out_ld, net.in_dim, out_w);
+  cudaStream_t st = (cudaStream_t)s;
+  const int p0 = rup(net.k0, 64);            // second input segment starts on a 128-byte boundary of the staging row
+  {
+    const int64_t total = (int64_t)batch * h->x_ld;
+    f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(in_dev, in_ld, net.in_dim, net.k0, p0, h->xin, h->x_ld, plane_elems(h, h->x_ld), h->planes, batch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  NetIO in;
+  in.nseg = net.k1 ? 2 : 1;
+  in.seg[0] = ws_view(h, h->xin, h->x_ld, net.k0, batch);
+  if (net.k1) in.seg[1] = ws_view(h, h->xin + p0, h->x_ld, net.k1, batch);
+  EpiParams e;
+  memset(&e, 0, sizeof(e));
+  e.type = EPI_STORE; e.out_f32 = out_dev; e.f32_sm = out_ld; e.f32_sn = 1;
+  CKR(net_forward(h, net, in, batch, e, st));
   CK(cudaGetLastError());
   return PVAE_OK;
 }
@@ -1009,6 +1103,8 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
                  float* future_dev, float* value_dev, pvae_stream s) {
   CKR(step_prologue(h, batch));
   if (!obs_dev) return fail(PVAE_ERR_INVALID, "obs_dev is required (the body state feeds the decoder and the world model)");
+  for (int n = 0; n < PVAE_NUM_NETS; ++n)
+    if (h->nets[n].generic) return fail(PVAE_ERR_INVALID, "a net with explicit input widths runs through pvae_fc_forward only");
   cudaStream_t st = (cudaStream_t)s;
   const int z = h->z;
   const bool enc = parts & PVAE_PART_ENCODER, dec = parts & PVAE_PART_DECODER, wld = parts & PVAE_PART_WORLD, val = parts & PVAE_PART_VALUE;
@@ -1031,7 +1127,7 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
     const int64_t total = (int64_t)batch * z;
     reparam_fwd_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(h->ml, eps_dev, h->eps, prior, prior && noise, seed, offset, batch, z,
                                                                          h->zb, h->zb_ld, plane_elems(h, h->zb_ld), h->planes, z_dev, mu_dev,
-                                                                         prior ? logvar_dev : nullptr, nullptr);
+                                                                         prior ? logvar_dev : nullptr, nullptr, nullptr);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   } else if (dec) {
     if (!z_in_dev) return fail(PVAE_ERR_INVALID, "decoder without encoder needs z_in_dev");

@@ -294,9 +294,12 @@ template <int act> __device__ __forceinline__ float act_fwd(float v) {
     default:          return v;
   }
 }
-// derivative of the activation expressed through its OUTPUT y (what the forward pass stored)
+// derivative of the activation expressed through what the forward pass stored: its OUTPUT y -- except for swish, whose
+// derivative is not a function of the output: the forward pass keeps the PRE-activation x of swish layers (in the layer's
+// gradient buffer, which the backward pass overwrites in place), and y here is that x:  d/dx x.s(x) = s(x) (1 + x (1 - s(x)))
 template <int act> __device__ __forceinline__ float act_bwd_from_out(float y) {
   switch (act) {
+    case ACT_SWISH:   { const float sg = 1.f / (1.f + __expf(-y)); return sg * (1.f + y * (1.f - sg)); }
     case ACT_RELU:    return y > 0.f ? 1.f : 0.f;
     case ACT_TANH:    return 1.f - y * y;
     case ACT_SIGMOID: return y * (1.f - y);
@@ -492,6 +495,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float (&v)[32
     }
   }
   if (EPI == EPI_STORE) {
+    if (ACT == ACT_SWISH && e.out2 && row_ok)      // swish: keep the pre-activation for the backward pass
+      store_row32(e.out2 + (int64_t)row * e.out2_ld + col0, e.out2_ps, e.out2_planes, nv, v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
     if (row_ok) {
@@ -625,8 +630,12 @@ struct UnitWalk {
 // aux operand (forward activation for act', MSE target) arrives the same way; the epilogue warps then touch only TMEM,
 // shared memory and registers.  Without it (bf16x3 planes, fp32-only outputs) rows are read / written directly.
 // CG: CTAs per MMA instruction (see the top of the file); the launch uses clusters of CG CTAs.
-template <int EPI, int ACT, bool TMAEPI, int CG>
+// FAST (TMAEPI, ReLU, EPI_STORE / EPI_DGRAD only): the host guarantees that every row and every 32-column chunk of every tile
+// exists (M a multiple of the M tile of the CTA pair, N a multiple of 32), that bias / mask are present and that there is no
+// addend, fp32 copy, M segment or gap -- the epilogue then runs without any of the per-chunk tests (see the FAST block below).
+template <int EPI, int ACT, bool TMAEPI, int CG, bool FAST = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(!FAST || (TMAEPI && ACT == ACT_RELU && (EPI == EPI_STORE || EPI == EPI_DGRAD)), "FAST epilogue: ReLU store / dgrad through TMA only");
   constexpr int STAGES = Geo<CG>::STAGES;
   constexpr int STAGE_BYTES = Geo<CG>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -807,6 +816,185 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         if (elect_one()) umma_commit<CG>(tfull_bar(acc));    // accumulator complete -> epilogue (of both CTAs)
         __syncwarp();
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if constexpr (FAST) {
+    // ================================ epilogue, lean form (16 warps) ================================
+    // Same division of labour as the general epilogue below (warp w: TMEM lane quarter w % 4, 32-column chunks cgrp, cgrp + 4 of
+    // the tile, private 2 KiB slab, one TMA store per chunk), minus everything the host has ruled out: no row / column edge
+    // tests, no addend, no fp32 copy, no aux operand.  Two things are done differently because this path is what bounds every
+    // layer with K <= 512 (the 16 warps need longer for a 128 x 256 tile than the tensor pipe):
+    //   * the ReLU-mask words / bias values of the NEXT unit are fetched while the current one is processed (a load issued
+    //     right before the accumulator wait is not hidden when the accumulator is already there);
+    //   * bias-gradient column sums read the staged slab as 32-bit words -- lanes 0-15 rows 0-15, lanes 16-31 rows 16-31,
+    //     two columns each, opposite row parity per half so that one LDS never hits a bank twice -- and add with FADD2.
+    const EpiParams& e = p.epi;
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const int cgrp = ew >> 2;
+    float* bias_s = bias_all + ew * 32;
+    const int n_valid = e.n_valid;
+    int acc = 0; uint32_t acc_phase = 0;
+    constexpr int CS_TILES = 4;
+    float cs_acc[4 * CS_TILES];                    // [n tile][chunk J][column 2 w, 2 w + 1]
+#pragma unroll
+    for (int k = 0; k < 4 * CS_TILES; ++k) cs_acc[k] = 0.f;
+    const bool do_cs = EPI == EPI_DGRAD && e.colsum != nullptr;
+    const uint32_t tempty0 = (CG == 2) ? mapa_u32(tempty_bar(0), 0u) : tempty_bar(0);
+    const uint32_t slab = smem_base + OFF_STAGING + ew * SLAB_BYTES;
+    uint8_t* slab_gen = smem_gen + OFF_STAGING + ew * SLAB_BYTES;
+    uint8_t* srow = slab_gen + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    const int hh = lane >> 4, ww = lane & 15;     // column-sum role: row half, word (= column pair) of the 64-byte slab row
+    const uint8_t* cs_base = slab_gen + (hh << 10) + ((ww & 3) << 2);
+    UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits, p.reverse);
+    // operands of a unit's (at most two) chunks that do not depend on the accumulator
+    auto fetch = [&](const UnitWalk& uw, float (&pb)[2], uint32_t (&pm)[2]) {
+      const int nt = uw.nt;
+      const int r = (uw.m_pair() * csize + crank) * BM + q * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cs = nt * bn + (cgrp + 4 * j) * 32;
+        pb[j] = 0.f; pm[j] = 0u;
+        if ((cgrp + 4 * j) * 32 < bn && cs < n_valid) {
+          if (EPI == EPI_STORE) pb[j] = __ldg(e.bias + cs + lane);
+          else pm[j] = __ldg(e.mask + (int64_t)(cs >> 5) * e.mask_ld + r);
+        }
+      }
+    };
+    float pre_bias[2]; uint32_t pre_mask[2];
+    if (unit0 < total_units) fetch(w, pre_bias, pre_mask);
+    for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
+      const int n_tile = w.nt;
+      const int m_tile = w.m_pair() * csize + crank;
+      const int row = m_tile * BM + q * 32 + lane;
+      float nxt_bias[2] = {0.f, 0.f}; uint32_t nxt_mask[2] = {0u, 0u};
+      if (u + unit_stride < total_units) { UnitWalk wn = w; wn.next(); fetch(wn, nxt_bias, nxt_mask); }
+      mbar_wait<W_TFULL>(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_unit = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + cgrp * 32);
+      const int col_unit = n_tile * bn + cgrp * 32;
+      auto chunk = [&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        const int col0 = col_unit + 128 * J;
+        if ((cgrp + 4 * J) * 32 >= bn || col0 >= n_valid) return;          // warp-uniform
+        float v[32];
+        {
+          uint32_t raw[32];
+          tmem_ld32(tmem_unit + 128u * J, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        }
+        uint32_t pk[16];
+        if (EPI == EPI_STORE) {
+          __syncwarp();
+          bias_s[lane] = pre_bias[J];             // lane -> bias of column lane of the chunk
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + g * 4);
+            fadd2(v[g * 4 + 0], v[g * 4 + 1], b4.x, b4.y);
+            fadd2(v[g * 4 + 2], v[g * 4 + 3], b4.z, b4.w);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2_relu(v[2 * i], v[2 * i + 1]);
+          uint32_t m = 0u;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m |= bf16x2_gt0(pk[i]) & (relu_mask_bit(2 * i) | relu_mask_bit(2 * i + 1));
+          e.mask[(int64_t)(col0 >> 5) * e.mask_ld + row] = m;
+        } else {
+          const uint32_t mbits = pre_mask[J];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {           // ReLU': see relu_mask_bit()
+            const uint32_t t = mbits << s;
+            uint32_t m0, m1;
+            asm("prmt.b32 %0, %1, %1, 0xAA88;" : "=r"(m0) : "r"(t));
+            asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m1) : "r"(t));
+            pk[2 * s] &= m0;
+            pk[2 * s + 1] &= m1;
+          }
+        }
+        tma_store_wait_read<0>();                 // the slab's previous store has been read out (bulk groups are per thread)
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(srow + ((g ^ sw) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_3d(&p.tmOut, slab, col0, m_tile * BM + q * 32, 0);
+          tma_store_commit();
+        }
+        __syncwarp();
+        if (do_cs) {
+          // rows 2 i, 2 i + 1 of this lane's half share the swizzle term i & 3; half 0 reads the even row first, half 1 the odd one
+          uint32_t wa[8], wb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int po = (((ww >> 2) ^ (i & 3)) << 4);
+            wa[i] = *reinterpret_cast<const uint32_t*>(cs_base + i * 128 + (hh << 6) + po);
+            wb[i] = *reinterpret_cast<const uint32_t*>(cs_base + i * 128 + ((hh ^ 1) << 6) + po);
+          }
+          float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            fadd2(s0, s1, __uint_as_float(wa[i] << 16), __uint_as_float(wa[i] & 0xFFFF0000u));
+            fadd2(t0, t1, __uint_as_float(wb[i] << 16), __uint_as_float(wb[i] & 0xFFFF0000u));
+          }
+          fadd2(s0, s1, t0, t1);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          if (n_tile < CS_TILES) {
+#pragma unroll
+            for (int t = 0; t < CS_TILES; ++t) {
+              cs_acc[4 * t + 2 * J]     += (n_tile == t) ? s0 : 0.f;
+              cs_acc[4 * t + 2 * J + 1] += (n_tile == t) ? s1 : 0.f;
+            }
+          } else if (hh == 0) {
+            atomicAdd(e.colsum + col0 + 2 * ww, s0);
+            atomicAdd(e.colsum + col0 + 2 * ww + 1, s1);
+          }
+          __syncwarp();
+        }
+      };
+      chunk(std::integral_constant<int, 0>{});
+      chunk(std::integral_constant<int, 1>{});
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      pre_bias[0] = nxt_bias[0]; pre_bias[1] = nxt_bias[1];
+      pre_mask[0] = nxt_mask[0]; pre_mask[1] = nxt_mask[1];
+    }
+    tma_store_wait_read<0>();
+    if (do_cs) {
+      // flush: per (n tile, chunk) 32 column sums in natural order; the four lane-quarter warps of a column group combine
+      // through their idle slabs, one warp per column group issues the reds
+      __syncwarp();
+      float* mine = reinterpret_cast<float*>(slab_gen);
+      if (hh == 0) {
+#pragma unroll
+        for (int k = 0; k < 2 * CS_TILES; ++k)
+          *reinterpret_cast<float2*>(mine + k * 32 + 2 * ww) = make_float2(cs_acc[2 * k], cs_acc[2 * k + 1]);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      if ((ew & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < 2 * CS_TILES; ++k) {
+          float t = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            t += reinterpret_cast<const float*>(smem_gen + OFF_STAGING + (cgrp * 4 + qq) * SLAB_BYTES)[k * 32 + lane];
+          const int cl = (cgrp + 4 * (k & 1)) * 32 + lane;
+          const int col = (k >> 1) * bn + cl;
+          if (cl < bn && (k >> 1) < p.n_tiles && col < n_valid) atomicAdd(e.colsum + col, t);
+        }
       }
     }
   } else {
@@ -1166,7 +1354,11 @@ template <int CG> static inline GemmKernelFn select_kernel_cg(int epi, int act, 
     default:        return pvae_gemm_kernel<EPI_WGRAD, ACT_LINEAR, false, CG>;
   }
 }
-static inline GemmKernelFn select_kernel(int epi, int act, bool tma, int cg) {
+static inline GemmKernelFn select_kernel(int epi, int act, bool tma, int cg, bool fast = false) {
+  if (fast && tma && act == ACT_RELU && cg == 2) {       // lean epilogue (see the FAST block of the kernel)
+    if (epi == EPI_STORE) return pvae_gemm_kernel<EPI_STORE, ACT_RELU, true, 2, true>;
+    if (epi == EPI_DGRAD) return pvae_gemm_kernel<EPI_DGRAD, ACT_RELU, true, 2, true>;
+  }
   return cg == 2 ? select_kernel_cg<2>(epi, act, tma) : select_kernel_cg<1>(epi, act, tma);
 }
 

@@ -27,7 +27,7 @@ class Engine:
     """
 
     def __init__(self, dim_state_body, dim_action, latent_dim, nets, latent_prior=True, precision="bf16x3", max_batch=4096,
-                 device=None):
+                 device=None, in_dims=None):
         if not torch.cuda.is_available():
             raise _abi.PvaeError("physicsvae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _abi.load()
@@ -48,6 +48,8 @@ class Engine:
             if len(spec) > _abi.PVAE_MAX_LAYERS:
                 raise ValueError("%s: at most %d layers" % (name, _abi.PVAE_MAX_LAYERS))
             desc.nets[i].n_layers = len(spec)
+            if in_dims and name in in_dims:        # stand-alone FC stack: explicit input widths (fc_forward only)
+                desc.nets[i].in_dims[0], desc.nets[i].in_dims[1] = int(in_dims[name][0]), int(in_dims[name][1])
             for l, (out, act) in enumerate(spec):
                 if act not in _abi.ACT_IDS:
                     raise ValueError("Unknown activation ({})!".format(act))
@@ -113,13 +115,20 @@ class Engine:
                                                _stream()))
 
     # ---- resident transition buffer -------------------------------------------------------------------------------
-    def alloc_transitions(self, n_rows):
+    def transitions_bytes(self, n_rows):
         nbytes = C.c_size_t(0)
         _abi.check(self.lib.pvae_transitions_bytes(self._h, int(n_rows), C.byref(nbytes)))
-        self.transitions = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        return nbytes.value
+
+    def alloc_transitions(self, n_rows):
+        return self.bind_transitions(torch.zeros(self.transitions_bytes(n_rows), dtype=torch.uint8, device=self.device), n_rows)
+
+    def bind_transitions(self, buf, n_rows):
+        """Select the resident transition buffer the step functions read (several may be kept: train / test sets)."""
+        self.transitions = buf
         self.n_rows = int(n_rows)
-        _abi.check(self.lib.pvae_bind_transitions(self._h, _ptr(self.transitions), self.n_rows))
-        return self.transitions
+        _abi.check(self.lib.pvae_bind_transitions(self._h, _ptr(buf), self.n_rows))
+        return buf
 
     def ingest(self, x_raw, y_raw, dst_row=0):
         """x_raw: CUDA [n, 2*dsb] float64 or float32; y_raw: CUDA [n, da] float32 (DatasetBase.X / .Y, torch_models.py:39-58)."""
@@ -179,7 +188,34 @@ class Engine:
                                               float(a_coeff), float(kl_coeff), float(cyc_coeff), _ptr(self.loss), _stream()))
         return self.loss
 
+    def eval_loss(self, batch, world, eps=None, seed=0, offset=0, noise=True, a_coeff=1.0, kl_coeff=1.0, s_coeff=1.0, cyc_coeff=1e-3):
+        """Forward + loss only, no gradient is touched (the reference's test pass, torch_models.py:147-155)."""
+        if eps is not None:
+            if eps.shape != (batch, self.z) or eps.dtype != torch.float32 or eps.device != self.device or not eps.is_contiguous():
+                raise ValueError("eps must be a contiguous fp32 [%d, %d] tensor on %s" % (batch, self.z, self.device))
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_eval_loss(self._h, 0 if world else 1, int(batch), _ptr(eps), int(seed), int(offset),
+                                               1 if noise else 0, float(a_coeff), float(kl_coeff), float(s_coeff), float(cyc_coeff),
+                                               _ptr(self.loss), _stream()))
+        return self.loss
+
+    def noise_counter(self, enable, value=0, stride=1):
+        """Device-side Philox offset counter (include/pvae_sm100.h, pvae_noise_counter)."""
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_noise_counter(self._h, 1 if enable else 0, int(value), int(stride), _stream()))
+
     # ---- inference ------------------------------------------------------------------------------------------------
+    def fc_forward(self, name, x):
+        """FC.forward of one net on fp32 rows [B, in] -> [B, out] (rllib_model_torch.py:274-275)."""
+        x = x.to(self.device, torch.float32).contiguous()
+        if x.dim() != 2:
+            raise ValueError("fc_forward wants [batch, features]")
+        out = torch.empty(x.shape[0], self.layers[name][-1][0], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_fc_forward(self._h, NET_NAMES.index(name), x.shape[0], _ptr(x), x.shape[1], _ptr(out),
+                                                out.shape[1], _stream()))
+        return out
+
     def forward(self, obs, parts, z_in=None, act_in=None, eps=None, noise=False, seed=0, offset=0):
         """Runs the selected parts of PhysicsVAE.forward (rllib_model_torch.py:742-853); returns a dict of fp32 outputs."""
         B = obs.shape[0]

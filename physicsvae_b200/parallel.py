@@ -58,8 +58,8 @@ def shard_weight(lo, hi, r, world):
 
 
 def allreduce_avg_(tensors, group=None):
-    """In-place average of the given flat tensors over all ranks (one collective per tensor; a step has at most three:
-    two gradient buffers + the loss slots)."""
+    """In-place average of the given flat tensors over all ranks, one collective per tensor.  A training step passes ONE
+    tensor: the contiguous [gradients | loss slots] range of the model's gradient pool."""
     w = world_size()
     if w == 1:
         return
@@ -70,6 +70,12 @@ def allreduce_avg_(tensors, group=None):
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
             t.div_(w)
+
+
+def barrier():
+    """All ranks that share a trainer wait for each other (no-op for a single rank and in replica mode)."""
+    if world_size() > 1:
+        dist.barrier()
 
 
 def broadcast_(tensors, src=0):

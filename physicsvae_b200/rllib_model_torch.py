@@ -13,6 +13,7 @@ relies on, train_physics_vae.py:356-359).
 """
 import logging
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -184,9 +185,65 @@ class FC(nn.Module):
         """[(out_features, activation name)] for the engine."""
         return [(m.linear.out_features, m.activation) for m in self.fc_layers()]
 
+    # ---- forward (rllib_model_torch.py:274-275: `return self._model(x)`) --------------------------------------------------
+    def _bind_owner(self, owner, role):
+        """A sub-net of a PhysicsVAE runs on its owner's engine (same parameters, same shadow operands)."""
+        object.__setattr__(self, "_owner_ref", weakref.ref(owner))
+        object.__setattr__(self, "_role", role)
+
+    def _own_engine(self, batch):
+        """Stand-alone FC (no PhysicsVAE around it): a private one-net engine whose only net takes `size_in` columns."""
+        eng = getattr(self, "_engine", None)
+        p0 = next(self.parameters())
+        if p0.device.type != "cuda":
+            raise _abi.PvaeError("FC runs on the sm_100a engine only: move the module to a CUDA device first (no CPU / eager fallback exists)")
+        if eng is None or eng.max_batch < batch or eng.device != p0.device:
+            if eng is not None:
+                eng.close()
+            eng = Engine(8, 8, 8, {"world_model": self.layer_spec()}, precision=getattr(self, "engine_precision", "bf16x3"),
+                         max_batch=max(int(batch), 256), device=p0.device.index, in_dims={"world_model": (self.size_in, 0)})
+            layers = self.fc_layers()
+            flat = torch.empty(eng.grad_elems("world_model"), dtype=torch.float32, device=p0.device)
+            off, Ws, bs = 0, [], []
+            for m in layers:
+                for p in (m.linear.weight, m.linear.bias):
+                    k = p.numel()
+                    view = flat[off:off + k].view_as(p)
+                    view.copy_(p.data)
+                    p.data = view
+                    off += k
+                Ws.append(m.linear.weight.data)
+                bs.append(m.linear.bias.data)
+            eng.bind_net("world_model", Ws, bs, None)
+            object.__setattr__(self, "_engine", eng)
+            object.__setattr__(self, "_synced_version", None)
+        version = tuple(p._version for p in self.parameters())
+        if self._synced_version != version:           # parameters were modified in place since the last call
+            eng.sync_weights(["world_model"])
+            object.__setattr__(self, "_synced_version", version)
+        return eng
+
+    def _apply(self, fn, *a, **kw):
+        eng = getattr(self, "_engine", None)
+        if eng is not None:                            # .to() / .cuda() re-create parameter storage
+            eng.close()
+            object.__setattr__(self, "_engine", None)
+        return super()._apply(fn, *a, **kw)
+
     def forward(self, x):
-        raise _abi.PvaeError("FC has no stand-alone PyTorch path; it runs inside PhysicsVAE's sm_100a engine "
-                             "(PhysicsVAE.forward_decoder / forward_world / forward_encoder)")
+        lead = x.shape[:-1]
+        x2 = x.float().reshape(-1, x.shape[-1])
+        if x2.shape[-1] != self.size_in:
+            raise ValueError("FC expects %d input features, got %d" % (self.size_in, x2.shape[-1]))
+        owner = getattr(self, "_owner_ref", None)
+        owner = owner() if owner is not None else None
+        if owner is not None:
+            out = owner._ready(x2.shape[0]).fc_forward(self._role, x2)
+        else:
+            out = self._own_engine(x2.shape[0]).fc_forward("world_model", x2)
+        out = out.reshape(*lead, -1)
+        tail = self._model[-1]
+        return tail(out) if isinstance(tail, AppendLogStd) else out
 
     def save_weights(self, file):
         torch.save(self.state_dict(), file)
@@ -316,6 +373,8 @@ class PhysicsVAE(TorchModelV2, nn.Module):
         self._world_model = FC(size_in=self.dim_action + self.dim_state_body, size_out=self.dim_state_body,
                                layers=cfg.get("world_model_layers"))
         self._value_branch = FC(size_in=self.dim_state, size_out=1, layers=cfg.get("value_fn_layers"))
+        for role, attr in _NET_ATTR.items():
+            getattr(self, attr)._bind_owner(self, role)
 
         self._cur_value = None
         self._cur_task_encoder_variable = None
@@ -373,11 +432,28 @@ class PhysicsVAE(TorchModelV2, nn.Module):
         spec = {name: self.net(name).layer_spec() for name in NET_NAMES}
         eng = Engine(self.dim_state_body, self.dim_action, self._task_encoder_output_dim, spec,
                      latent_prior=bool(self._latent_prior_type), precision=want_prec, max_batch=want_batch, device=p0.device.index)
+        # One gradient pool for the whole model, laid out [world model | loss slots | task encoder | motor decoder | value branch]
+        # (every piece 16-byte aligned): what a training step has to exchange between data-parallel ranks -- the gradients of
+        # the nets it trains plus the loss slots -- is ONE contiguous range in either phase (reduce_range()).
+        al = lambda k: (k + 3) // 4 * 4
+        order = ("world_model", "task_encoder", "motor_decoder", "value_branch")
+        sizes = {name: eng.grad_elems(name) for name in NET_NAMES}
+        offs, cur = {}, 0
+        for name in order:
+            offs[name] = cur
+            cur += al(sizes[name])
+            if name == "world_model":
+                loss_off = cur
+                cur += al(_abi.PVAE_LOSS_SLOTS)
+        pool = self._grad_pool = self._pool_alloc(cur, p0.device)
+        eng.loss = pool[loss_off:loss_off + _abi.PVAE_LOSS_SLOTS]
+        self._pool_off = dict(offs, loss=loss_off, end=cur)
+        self._pool_sizes = sizes
         for name in NET_NAMES:
             layers = self.net(name).fc_layers()
-            n = eng.grad_elems(name)
+            n = sizes[name]
             flat = torch.empty(n, dtype=torch.float32, device=p0.device)
-            gflat = torch.zeros(n, dtype=torch.float32, device=p0.device)
+            gflat = pool[offs[name]:offs[name] + n]
             off = 0
             Ws, bs = [], []
             for m in layers:
@@ -407,6 +483,24 @@ class PhysicsVAE(TorchModelV2, nn.Module):
             for p in self.net(name).parameters():
                 view = getattr(p, "_pvae_grad_view", None)
                 p.grad = view if (p.requires_grad and view is not None and name != "value_branch") else None
+
+    def _pool_alloc(self, n, device):
+        """The gradient pool; `grad_pool_factory` (set by a trainer) may hand out memory registered for peer access
+        (physicsvae_b200.parallel.SymmetricPool) instead of a plain tensor."""
+        factory = getattr(self, "grad_pool_factory", None)
+        if factory is not None:
+            t = factory(n, device)
+            t.zero_()
+            return t
+        return torch.zeros(n, dtype=torch.float32, device=device)
+
+    def reduce_range(self, world_phase):
+        """The contiguous slice of the gradient pool a data-parallel step all-reduces: [world model | loss slots] in the world
+        phase, [loss slots | task encoder | motor decoder] in the VAE phase."""
+        o, sz = self._pool_off, self._pool_sizes
+        if world_phase:
+            return self._grad_pool[o["world_model"]:o["loss"] + _abi.PVAE_LOSS_SLOTS]
+        return self._grad_pool[o["loss"]:o["motor_decoder"] + sz["motor_decoder"]]
 
     def flat_params(self, name):
         return self._flat[name][0]

@@ -167,13 +167,20 @@ class TrainModel(_TrainableBase):
             raise _abi.PvaeError("physicsvae_b200.TrainModel needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.model = self.model.to(self.device)
-        self.engine = self.model.engine(max_batch=self._local_rows(config.get("batch_size")),
-                                        precision=config.get("engine_precision", "bf16x3"))
+        self._engine_rows = self._local_rows(config.get("batch_size"))
+        self._engine_precision = config.get("engine_precision", "bf16x3")
+        self._buffers = {}             # "train" / "test" / "adhoc" -> (resident transition buffer, rows)
+        self._bound = (None, None)     # (engine instance, buffer name) the engine currently reads
+        self._graphs = {}              # captured full-batch steps, see _graph_step
+        self._use_graphs = bool(config.get("cuda_graph", True))
+        self._loss_acc = torch.zeros((), device=self.device)
+        eng = self.engine
         lr = config.get("lr", 1e-3)
         if config.get("optimizer", "pvae_adam") == "torch_adam":
             capturable = bool(config.get("optimizer_capturable", False))     # CUDA-graph replay of the whole step
             self.optimizer = optim.Adam(self.model.parameters(), lr=torch.tensor(float(lr), device=self.device) if capturable else lr,
                                         weight_decay=config.get("weight_decay", 0.0), fused=True, capturable=capturable)
+            self._use_graphs = self._use_graphs and capturable
         else:
             # same interface and arithmetic as optim.Adam, executed by the engine together with the shadow-weight refresh
             self.optimizer = PvaeAdam(self.model, lr=lr, weight_decay=config.get("weight_decay", 0.0))
@@ -184,10 +191,19 @@ class TrainModel(_TrainableBase):
             raise NotImplementedError("only the MSE loss is fused into the sm_100a engine")
         self.iter = 0
         self._upload(self.train_loader, "train")
+        if self.test_loader:
+            self._upload(self.test_loader, "test")       # both sets stay resident; a pass only re-binds the engine
+        self._bind("train")
         self._anchor = torch.zeros((), device=self.device, requires_grad=True)
 
     def _local_rows(self, batch_size):
         return max(parallel.max_shard_rows(int(batch_size), parallel.world_size()), 2)
+
+    @property
+    def engine(self):
+        """Always the model's CURRENT engine: the model re-creates it when a larger batch is asked for (compute_model /
+        compute_loss on more rows than batch_size), which invalidates bindings and captured graphs -- see _bind."""
+        return self.model.engine(max_batch=self._engine_rows, precision=self._engine_precision)
 
     # ---- data -------------------------------------------------------------------------------------------------------
     def load_dataset(self, file):
@@ -207,52 +223,72 @@ class TrainModel(_TrainableBase):
         self.train_loader = self.get_data_loader(dataset_train, batch_size, shuffle_data)
         self.test_loader = self.get_data_loader(dataset_test, batch_size, shuffle_data) if dataset_test is not None else None
 
+    def _bind(self, which):
+        """Point the engine at one of the resident buffers.  Re-binding is free (no copy); if the model has re-created its
+        engine since the last call the binding is re-established and the captured graphs (which hold the old handle's
+        pointers) are dropped."""
+        eng = self.engine
+        if self._bound[0] is not eng:
+            self._graphs = {}
+            self._engine_changed(eng)
+        if self._bound != (eng, which):
+            buf, n = self._buffers[which]
+            eng.bind_transitions(buf, n)
+            self._bound = (eng, which)
+        return eng
+
+    def _engine_changed(self, eng):
+        """Hook: a fresh engine instance is in use (subclasses re-arm per-engine device state)."""
+
     def _upload(self, loader, which):
         """DatasetBase -> resident bf16 transition buffer (replaces per-item torch.Tensor + collate, torch_models.py:52-68)."""
+        eng = self.engine
         src = getattr(loader.dataset, "episode_source", None)
         if src is not None and not loader.dataset.normalize_x and not loader.dataset.normalize_y and len(src[2]) == len(loader.dataset):
             # dataset build on the device: upload every state once, the ingest kernel pairs (s_t, a_t, s_{t+1}) by index
             states, actions, first = src
-            eng = self.engine
             eng.alloc_transitions(len(first))
             st, ac = torch.from_numpy(states).to(self.device), torch.from_numpy(actions).to(self.device)
             chunk = 1 << 20
             for lo in range(0, len(first), chunk):
                 eng.ingest_episodes(st, ac, torch.from_numpy(first[lo:lo + chunk]).to(self.device), dst_row=lo)
-            self._resident = which
-            return
-        X, Y = loader.dataset.arrays()
-        if X.ndim == 3 and X.shape[1] != 1:
-            raise NotImplementedError("lookahead > 1 is not on the hot path (train_physics_vae.py:277 hard-wires 1)")
-        n = X.shape[0]
-        eng = self.engine
-        eng.alloc_transitions(n)
-        chunk = 1 << 18
-        for lo in range(0, n, chunk):
-            hi = min(lo + chunk, n)
-            eng.ingest(torch.from_numpy(X[lo:hi].reshape(hi - lo, -1)).to(self.device),
-                       torch.from_numpy(Y[lo:hi].reshape(hi - lo, -1)).to(self.device), dst_row=lo)
-        self._resident = which
+        else:
+            X, Y = loader.dataset.arrays()
+            if X.ndim == 3 and X.shape[1] != 1:
+                raise NotImplementedError("lookahead > 1 datasets go through compute_loss (rollout path), not the resident loader")
+            n = X.shape[0]
+            eng.alloc_transitions(n)
+            chunk = 1 << 18
+            for lo in range(0, n, chunk):
+                hi = min(lo + chunk, n)
+                eng.ingest(torch.from_numpy(X[lo:hi].reshape(hi - lo, -1)).to(self.device),
+                           torch.from_numpy(Y[lo:hi].reshape(hi - lo, -1)).to(self.device), dst_row=lo)
+        self._buffers[which] = (eng.transitions, eng.n_rows)
+        self._bound = (eng, which)
 
     # ---- the SGD loop (torch_models.py:131-161) -----------------------------------------------------------------------
     def step(self):
         self.iter += 1
         self.model.train()
-        if self._resident != "train":
-            self._upload(self.train_loader, "train")
-        loss_acc = torch.zeros((), device=self.device)
-        for lo, hi in self.train_loader:
-            loss = self.train_batch(lo, hi)
-            loss_acc += loss
-        mean_train_loss = float(loss_acc.item()) / len(self.train_loader)
+        self._bind("train")
+        self._loss_acc.zero_()
+        bs, n = self.train_loader.batch_size, self.train_loader.n
+        n_full = n // bs if self._graph_ok(bs) else 0
+        if n_full:
+            self._graph_epoch(n_full, bs)               # full mini-batches: one captured graph replayed off the device cursor
+        for lo in range(n_full * bs, n, bs):            # the short last batch (or everything, without graphs): eager launches
+            self._loss_acc += self.train_batch(lo, min(lo + bs, n))
+        mean_train_loss = float(self._loss_acc.item()) / len(self.train_loader)
 
         mean_test_loss = 0.0
         if self.test_loader:
-            self._upload(self.test_loader, "test")
-            loss_acc = torch.zeros((), device=self.device)
+            # forward + loss only, like the reference's `with torch.no_grad()` test pass (torch_models.py:147-155)
+            self._bind("test")
+            self._loss_acc.zero_()
             for lo, hi in self.test_loader:
-                loss_acc += self.batch_loss(lo, hi)
-            mean_test_loss = float(loss_acc.item()) / len(self.test_loader)
+                self._loss_acc += self.eval_batch_loss(lo, hi)
+            mean_test_loss = float(self._loss_acc.item()) / len(self.test_loader)
+            self._bind("train")
 
         if self.lr_scheduler:
             self.lr_scheduler.step()
@@ -266,8 +302,76 @@ class TrainModel(_TrainableBase):
             self.model.mark_weights_dirty()      # (PvaeAdam refreshes the shadow operands itself)
         return loss
 
+    # ---- captured full-batch step --------------------------------------------------------------------------------------------
+    def _graph_ok(self, batch_size):
+        return self._use_graphs and isinstance(self.optimizer, PvaeAdam) and self._graph_supported()
+
+    def _graph_supported(self):
+        return False
+
+    def _graph_key(self, batch_size):
+        """Everything a captured step bakes in as a host-side constant."""
+        lr = self.optimizer.param_groups[0]["lr"]
+        return (int(batch_size), float(lr), parallel.world_size(), parallel.rank())
+
+    def _graph_body(self, batch_size):
+        """One full mini-batch starting at the device cursor: engine step [+ all-reduce]; must not allocate or synchronise."""
+        raise NotImplementedError
+
+    def _graph_prepare(self, batch_size):
+        """Anything a captured step needs allocated / initialised beforehand (called before the capture)."""
+
+    def _graph_step(self, batch_size):
+        """The step as ONE CUDA graph per (phase, batch size, lr, ...): [engine step -> all-reduce -> fused Adam + shadow refresh ->
+        loss accumulation -> cursor advance].  Replays walk the resident buffer through the device-side cursor."""
+        key = self._graph_key(batch_size)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) > 8:                   # lr schedules change the key every few epochs: keep the cache small
+                self._graphs.clear()
+            self._graph_prepare(batch_size)
+            if self.model._weights_dirty:
+                self.model.sync_weights()
+            eng = self.engine
+
+            def body():
+                self._graph_body(batch_size)
+                self.optimizer.step()
+                self._loss_acc.add_(eng.loss[0])
+                eng.advance_cursor(batch_size, 0, 2 ** 31 - 1)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            # the capture pass does not execute anything: the Adam step counters, cursor and noise counter are untouched
+            self._graphs[key] = g
+        return g
+
+    def _graph_epoch(self, n_full, batch_size):
+        g = self._graph_step(batch_size)
+        self._graph_begin(batch_size)
+        for _ in range(n_full):
+            g.replay()
+        self._graph_end(n_full, batch_size)
+
+    def _graph_begin(self, batch_size):
+        """Position the device-side state (cursor, noise counter) at the first full batch of the epoch."""
+        s, _ = parallel.shard_rows(0, batch_size, parallel.rank(), parallel.world_size())
+        self.engine.set_cursor(s)
+
+    def _graph_end(self, n_full, batch_size):
+        """Host-side bookkeeping for `n_full` replayed batches."""
+
     def batch_loss(self, lo, hi):
         raise NotImplementedError
+
+    def eval_batch_loss(self, lo, hi):
+        """Loss of rows [lo, hi) of the bound buffer, forward only.  Default: the training pass (subclasses do better)."""
+        return self.batch_loss(lo, hi)
 
     def create_model(self, config):
         return config.get("model")

@@ -287,14 +287,25 @@ class TrainModel(torch_models.TrainModel):
         self.latent_prior_type = config.get("latent_prior_type")
         self.lookahead = config.get("lookahead")
         if self.lookahead != 1:
-            raise NotImplementedError("lookahead is hard-wired to 1 on this path (train_physics_vae.py:277)")
+            raise NotImplementedError("the resident-buffer trainer runs lookahead 1 (train_physics_vae.py:277 hard-wires it); "
+                                      "longer rollouts go through the oracle-pinned rollout path when built")
         self.noise_seed = int(config.get("noise_seed", 0))
         self._noise_step = 0
+        self.world_phase = True
         super().setup(config)
         self.model.set_learnable_task_encoder(False)
         self.model.set_learnable_motor_decoder(False)
         self.model.set_learnable_world_model(True)
         self.read_loss_fn_coeff(world=True)
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """Data-parallel ranks must hold the same parameters: every rank builds its model from its own RNG stream, so the
+        flat parameter buffers are broadcast from rank 0 (after construction and after every restore)."""
+        if parallel.world_size() > 1:
+            self.engine                                    # (makes sure the flat buffers exist)
+            parallel.broadcast_([self.model.flat_params(n) for n in policy_models.NET_NAMES])
+            self.model.mark_weights_dirty()
 
     def read_loss_fn_coeff(self, world):
         self.vae_kl_coeff = 0.0 if world else self.config.get("vae_kl_coeff")
@@ -319,6 +330,10 @@ class TrainModel(torch_models.TrainModel):
         self.model.set_learnable_world_model(False)
         self.read_loss_fn_coeff(world=False)
 
+    def load_checkpoint(self, checkpoint_path):
+        super().load_checkpoint(checkpoint_path)
+        self.sync_replicas()
+
     def load_trainer_state(self, st):
         """Resume: the phase is a function of the iteration counter (the switch fires when iter == max_iter_world_model)."""
         super().load_trainer_state(st)
@@ -341,46 +356,104 @@ class TrainModel(torch_models.TrainModel):
         return logits[..., :logits.shape[1] // 2]
 
     # ---- one mini-batch on the engine ---------------------------------------------------------------------------------
-    def batch_loss(self, lo, hi, eps=None):
+    def _shard(self, lo, hi):
+        """(first row, rows, loss weight) of this rank's part of the global mini-batch [lo, hi)."""
+        world, r = parallel.world_size(), parallel.rank()
+        if getattr(self, "dp_local_shards", False):
+            # every rank holds its OWN shard of the global batch as rows [lo, hi) of its resident buffer (equal sizes)
+            return lo, hi - lo, 1.0
+        # every rank holds the whole dataset and takes its contiguous slice of the global batch
+        s, e = parallel.shard_rows(lo, hi, r, world)
+        return s, e - s, parallel.shard_weight(lo, hi, r, world)
+
+    def _nets(self):
+        return ["world_model"] if self.world_phase else ["task_encoder", "motor_decoder"]
+
+    def _engine_step(self, n, w, eps=None, train=True):
+        """Forward + loss (+ backward when `train`) for the `n` rows at the device cursor; loss coefficients weighted by `w`
+        (n_rank * R / n, see parallel.py).  The Philox offset is (device-side noise counter) + rank."""
+        eng = self.engine
+        if self.world_phase:
+            if self.s_rec_coeff <= 0:
+                raise ValueError("world phase needs s_rec_coeff > 0")
+            if train:
+                eng.world_step(n, s_coeff=self.s_rec_coeff * w)
+            else:
+                eng.eval_loss(n, True, s_coeff=self.s_rec_coeff * w)
+        else:
+            if self.s_rec_coeff and self.s_rec_coeff > 0:
+                raise NotImplementedError("world_model_s_rec_coeff > 0 in the VAE phase is not used by the CLI (it is 0.0)")
+            kl = self.vae_kl_coeff if self.latent_prior_type else 0.0
+            kw = dict(eps=eps, seed=self.noise_seed, offset=parallel.rank(), noise=bool(self.model.latent_prior_noise),
+                      a_coeff=self.a_rec_coeff * w, kl_coeff=kl * w, cyc_coeff=self.vae_cycle_coeff * w)
+            if train:
+                eng.vae_step(n, **kw)
+            else:
+                eng.eval_loss(n, False, **kw)
+        if w != 1.0:
+            eng.loss[1:5].mul_(w)          # the component slots are local means: weight them like slot 0 so that the rank average is the global mean
+
+    def _reduce(self, train=True):
+        """The step's only collective: ONE averaging all-reduce over [gradients of the trained nets | loss slots] -- a single
+        contiguous range of the model's gradient pool (PhysicsVAE.reduce_range)."""
+        if parallel.world_size() > 1:
+            parallel.allreduce_avg_([self.model.reduce_range(self.world_phase) if train else self.engine.loss])
+
+    def batch_loss(self, lo, hi, eps=None, train=True):
         """Forward + loss + backward for rows [lo, hi) of the resident buffer; gradients land in `.grad` (all-reduced when
         torch.distributed is initialised).  Returns the global mini-batch loss as a 0-dim device tensor."""
         eng = self.engine
         if self.model._weights_dirty:
             self.model.sync_weights()
-        world, r = parallel.world_size(), parallel.rank()
-        if getattr(self, "dp_local_shards", False):
-            # every rank holds its OWN shard of the global batch as rows [lo, hi) of its resident buffer (equal sizes)
-            s, e, w = lo, hi, 1.0
+        s, n, w = self._shard(lo, hi)
+        if not self.world_phase:
+            self._noise_step += 1
+            eng.noise_counter(True, self._noise_step * parallel.world_size(), parallel.world_size())
+        if n > 0:
+            eng.set_cursor(s)
+            self._engine_step(n, w, eps=eps, train=train)
         else:
-            # every rank holds the whole dataset and takes its contiguous slice of the global batch
-            s, e = parallel.shard_rows(lo, hi, r, world)
-            w = parallel.shard_weight(lo, hi, r, world)
-        n = e - s
-        if self.world_phase:
-            if self.s_rec_coeff <= 0:
-                raise ValueError("world phase needs s_rec_coeff > 0")
-            nets = ["world_model"]
-            if n > 0:
-                eng.set_cursor(s)
-                eng.world_step(n, s_coeff=self.s_rec_coeff * w)
-        else:
-            if self.s_rec_coeff and self.s_rec_coeff > 0:
-                raise NotImplementedError("world_model_s_rec_coeff > 0 in the VAE phase is not used by the CLI (it is 0.0)")
-            nets = ["task_encoder", "motor_decoder"]
-            kl = self.vae_kl_coeff if self.latent_prior_type else 0.0
-            if n > 0:
-                eng.set_cursor(s)
-                self._noise_step += 1
-                eng.vae_step(n, eps=eps, seed=self.noise_seed, offset=self._noise_step * world + r,
-                             noise=bool(self.model.latent_prior_noise), a_coeff=self.a_rec_coeff * w, kl_coeff=kl * w,
-                             cyc_coeff=self.vae_cycle_coeff * w)
-        if n == 0:
-            for name in nets:
-                self.model.flat_grads(name).zero_()
+            if train:
+                for name in self._nets():
+                    self.model.flat_grads(name).zero_()
             eng.loss.zero_()
-        if world > 1:
-            parallel.allreduce_avg_([self.model.flat_grads(name) for name in nets] + [eng.loss])
+        self._reduce(train)
         return eng.loss[0].clone()
+
+    def eval_batch_loss(self, lo, hi):
+        """The reference's test pass (torch_models.py:147-155): compute_test_loss under no_grad -- forward and loss only; no
+        gradient buffer is touched, nothing but the loss slots is exchanged between ranks."""
+        return self.batch_loss(lo, hi, train=False)
+
+    # ---- the captured full-batch step (torch_models.TrainModel._graph_step) ------------------------------------------------
+    def _graph_supported(self):
+        return True
+
+    def _graph_key(self, batch_size):
+        return super()._graph_key(batch_size) + (self.world_phase, self.s_rec_coeff, self.a_rec_coeff, self.vae_kl_coeff,
+                                                 self.vae_cycle_coeff, bool(self.model.latent_prior_noise), self.noise_seed,
+                                                 bool(getattr(self, "dp_local_shards", False)))
+
+    def _graph_prepare(self, batch_size):
+        for name in self._nets():
+            self.optimizer._net_state(name)              # Adam moments exist before the capture (no allocation inside it)
+
+    def _graph_body(self, batch_size):
+        _, n, w = self._shard(0, batch_size)
+        if n <= 0:
+            raise _abi.PvaeError("a captured step needs at least one row per rank (batch_size >= world size)")
+        self._engine_step(n, w)
+        self._reduce()
+
+    def _graph_begin(self, batch_size):
+        s, _, _ = self._shard(0, batch_size)
+        self.engine.set_cursor(s)
+        if not self.world_phase:
+            self.engine.noise_counter(True, (self._noise_step + 1) * parallel.world_size(), parallel.world_size())
+
+    def _graph_end(self, n_full, batch_size):
+        if not self.world_phase:
+            self._noise_step += n_full
 
     def compute_loss(self, y, x, eps=None):
         """Reference signature (train_physics_vae.py:361-435): x [B, 1, 2*dsb], y [B, 1, da] -> scalar loss.  The batch is
@@ -389,12 +462,17 @@ class TrainModel(torch_models.TrainModel):
         B = x.shape[0]
         if B < 2:
             raise ValueError("compute_loss needs at least 2 transitions (the reference squeezes the batch axis)")
-        eng = self.model.engine(max_batch=B)
-        self.engine = eng
-        if self._resident != "adhoc" or eng.n_rows != B:
-            eng.alloc_transitions(B)
+        if x.dim() == 3 and x.shape[1] != 1:
+            raise NotImplementedError("lookahead > 1: the autoregressive rollout is not on the CUDA path (oracle/pvae_oracle.py "
+                                      "compute_loss_lookahead pins its arithmetic)")
+        self._engine_rows = max(self._engine_rows, B)
+        eng = self.engine                                # (a larger B re-creates the engine: _bind notices and drops the graphs)
+        buf = self._buffers.get("adhoc")
+        if buf is None or buf[1] != B:
+            buf = (torch.zeros(eng.transitions_bytes(B), dtype=torch.uint8, device=self.device), B)
+            self._buffers["adhoc"] = buf
+        self._bind("adhoc")
         eng.ingest(x.reshape(B, -1).to(self.device), y.reshape(B, -1).to(self.device))
-        self._resident = "adhoc"
         loss = self.batch_loss(0, B, eps=eps)
         return torch_models._DepositedLoss.apply(self._anchor, loss)
 
@@ -434,22 +512,43 @@ def run_trial(config, max_iter, checkpoint_freq, trial_dir, restore=None):
     """What one Ray Tune trial does (train_physics_vae.py:484-502): train() until training_iteration == max_iter,
     checkpoint every `checkpoint_freq` iterations and at the end; results go to result.json like Tune's JSON logger.
     `restore`: continue from that checkpoint (weights; with its trainer_state.pt also Adam moments, LR schedule, phase and
-    iteration counter -- upstream a resumed trial restarts those)."""
-    os.makedirs(trial_dir, exist_ok=True)
+    iteration counter -- upstream a resumed trial restarts those).
+    Data-parallel trials (torchrun, --sweep_mode dp): every rank trains, rank 0 alone writes result.json and the checkpoints;
+    all ranks leave a checkpoint iteration together (barrier) and return the same checkpoint path."""
+    writer = parallel.rank() == 0
+    if writer:
+        os.makedirs(trial_dir, exist_ok=True)
     config = dict(config)
     config["save_trainer_state"] = True
     trainer = TrainModel(config)
     if restore:
         trainer.restore(restore)
     last = restore
-    with open(os.path.join(trial_dir, "result.json"), "a") as log:
+    log = open(os.path.join(trial_dir, "result.json"), "a") if writer else None
+    try:
         for it in range(trainer.training_iteration + 1, max_iter + 1):
             result = trainer.train()
-            log.write(json.dumps(result) + "\n")
-            log.flush()
-            if parallel.rank() == 0 and ((checkpoint_freq and it % checkpoint_freq == 0) or it == max_iter):
-                last = trainer.save(os.path.join(trial_dir, "checkpoint_%06d" % it))
+            if log:
+                log.write(json.dumps(result) + "\n")
+                log.flush()
+            if (checkpoint_freq and it % checkpoint_freq == 0) or it == max_iter:
+                ckpt_dir = os.path.join(trial_dir, "checkpoint_%06d" % it)
+                if writer:
+                    trainer.save(ckpt_dir)
+                last = os.path.join(ckpt_dir, "model.pth")
+                parallel.barrier()                 # nobody runs ahead of (or resumes from) a checkpoint that is still being written
+    finally:
+        if log:
+            log.close()
     return trainer, last
+
+
+def output_path(path, trial, n_trials):
+    """--output of a sweep with several grid points: one file per trial (`model.pt` -> `model.trial_00003.pt`)."""
+    if n_trials <= 1:
+        return path
+    root, ext = os.path.splitext(path)
+    return "%s.trial_%05d%s" % (root, trial, ext)
 
 
 def init_distributed(sweep_mode="dp"):
@@ -473,22 +572,32 @@ def main(argv=None):
     trainer_config = get_trainer_config(args)
     checkpoint = args.checkpoint
     init_distributed(args.sweep_mode)
+    done = []                                   # (trial index, last checkpoint) of the trials this process ran
+    n_points = 1
     if args.checkpoint is None:
         local_dir = os.path.expanduser(args.local_dir)
         name = args.name or "TrainModel"
         points = resolve_grid(trainer_config)
+        n_points = len(points)
         mine = parallel.sweep_points(len(points), parallel.job_rank(), parallel.job_world_size()) if args.sweep_mode == "replicas" \
             else list(range(len(points)))
         for i in mine:
             trial_dir = os.path.join(local_dir, name, "trial_%05d" % i)
             restore = latest_checkpoint(trial_dir) if args.resume else None
             _, checkpoint = run_trial(points[i], args.max_iter, args.checkpoint_freq, trial_dir, restore=restore)
-    if args.output is not None:
-        # the reference's --output branch instantiates the abstract base trainer and always fails;
-        # here it exports the full state dict of the checkpoint
-        sd = torch.load(checkpoint, map_location="cpu")
-        torch.save(sd, args.output)
-        print("Model Saved:", args.output)
+            done.append((i, checkpoint))
+    else:
+        done.append((0, checkpoint))
+    if args.output is not None and parallel.rank() == 0:
+        # the reference's --output branch instantiates the abstract base trainer and always fails; here it
+        # exports the full state dict of the checkpoint -- per trial when the sweep has several grid points; in a
+        # data-parallel job rank 0 alone writes
+        for i, ck in done:
+            if ck is None:
+                continue
+            out = output_path(args.output, i, n_points)
+            torch.save(torch.load(ck, map_location="cpu"), out)
+            print("Model Saved:", out)
     return checkpoint
 
 

@@ -31,8 +31,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # pvae_net_desc: int32 + 8 int32 + 8 int32; pvae_model_desc: 6 int32 + 4 nets
-    assert C.sizeof(_abi.NetDesc) == 4 * 17
+    # pvae_net_desc: int32 + 8 int32 + 8 int32 + 2 int32 (input override); pvae_model_desc: 6 int32 + 4 nets
+    assert C.sizeof(_abi.NetDesc) == 4 * 19
     assert C.sizeof(_abi.ModelDesc) == 4 * 6 + 4 * C.sizeof(_abi.NetDesc)
 
 
