@@ -1,13 +1,16 @@
 """bench.py -- transitions/sec of the PhysicsVAE training step on B200 (BASELINE.json metric), with the CPU reference arm.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--phase world|vae] [--batch B] [--config default|wide|loco]
-  python bench.py --impl reference ...            the reference algorithm (oracle port) on the box's host cores
+  python bench.py --impl reference ...            the reference's own files (baseline/_ref, else the oracle port) on the host cores
 
 A "step" is one mini-batch SGD step of the hot path: forward + loss + backward (libpvae_sm100 tcgen05 kernels) +
-gradient all-reduce (N > 1) + fused Adam + refresh of the bf16 shadow weights, on a batch of synthetic transitions.
-Default workload = BASELINE.json configs[1]: world-model-only pretrain, dim_state_body 197 / dim_action 45, batch 65536
-per GPU, bf16 operands with fp32 accumulation.  Weak scaling: every rank holds its own resident shard of 4*B transitions.
-Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for how each field is computed.
+gradient all-reduce (N > 1) + fused Adam + refresh of the bf16 shadow weights, on a batch of synthetic transitions,
+executed through the product's own API: `TrainModel.train_steps(K)` = K replays of the step graph that
+`torch_models.TrainModel.step()` captures (physicsvae_b200/torch_models.py).
+Headline workload = BASELINE.json configs[1]: world-model-only pretrain, dim_state_body 197 / dim_action 45, batch 65536
+per GPU, bf16 operands with fp32 accumulation; the same line carries the VAE phase (configs[2]) under `phases.vae`, the
+fp32-accurate bf16x3 mode, and -- on 8 GPUs -- configs[3] / configs[4] under `configs`.  Weak scaling: every rank holds
+its own resident shard of 4*B transitions.  Prints ONE JSON line (rank 0).  DESIGN.md section 6 says how each field is computed.
 """
 import argparse
 import json
@@ -26,6 +29,7 @@ import numpy as np
 import torch
 
 CPU_THREADS = 0
+CPU_KIND = "auto"
 CONFIGS = {
     "default": dict(dsb=197, da=45, z=32, te=(256, 2), md=(512, 3), wm=(1024, 2)),
     "wide": dict(dsb=512, da=128, z=32, te=(1024, 3), md=(1024, 3), wm=(1024, 3)),
@@ -46,9 +50,14 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="mini-batch rows PER GPU")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="rows per step of the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="rows per step of the CPU arm (0: the workload's batch, shrunk only if the run would take too long)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all cores; 1 with --cpu-sample 256 = configs[0])")
+    ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"],
+                    help="CPU arm: the reference's own files staged in baseline/_ref (auto when present) or the oracle port")
+    ap.add_argument("--only-phase", action="store_true", help="measure just --phase (no second phase, no bf16x3 / extra-config legs)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the power-capped (sustained clock) leg per phase")
+    ap.add_argument("--all-configs", action="store_true", help="also run the configs[3] / configs[4] legs when N != 8")
     return ap.parse_args()
 
 
@@ -161,39 +170,73 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port of train_physics_vae.TrainModel.compute_loss + backward + Adam)
+# CPU arm: the reference algorithm on the host cores -- the reference's OWN files when they are staged in baseline/_ref
+# (oracle/stage_ref.py; they import unchanged under oracle/ref_stub), else the oracle port of the same algorithm
 # --------------------------------------------------------------------------------------------------------------------
-def cpu_arm(cfg, phase, rows, steps, warmup, seed=0, min_seconds=0.0, max_seconds=150.0):
-    """`steps` timed mini-batch steps of `rows` transitions each through the oracle port on all host cores.  `min_seconds`:
-    keep stepping until that much time was measured (the cpu_baseline leg wants 10-30 s of CPU work); `max_seconds`: if the
-    requested run would take longer, the per-step sample shrinks (reported) so that the run still ends within minutes."""
+def _reference_stepper(cfg, phase, rows, seed):
+    """(step function, kind): one mini-batch of `rows` transitions through compute_loss + backward + Adam + item.
+    kind "reference": train_physics_vae.TrainModel.compute_loss of the unmodified reference (incl. its discarded full forward in
+    the world phase) on a reference-built model; kind "port": oracle/pvae_oracle.py."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    want = CPU_KIND
+    X, Y = synthetic_arrays(cfg, rows, seed + 1)
+    if want in ("auto", "reference") and os.path.isfile(os.path.join(ref_dir, "train_physics_vae.py")):
+        os.environ["PVAE_REFERENCE"] = ref_dir
+        from oracle import refload
+        refload.REFERENCE = ref_dir
+        tpv, tm, rmt = refload.load()
+        torch.manual_seed(seed)
+        model = refload.build_reference_model(cfg["dsb"], cfg["da"], cfg["z"], tpv.gen_layers(*cfg["te"]), tpv.gen_layers(*cfg["md"]),
+                                              tpv.gen_layers(*cfg["wm"]))
+        world = phase == "world"
+        model.set_learnable_task_encoder(not world); model.set_learnable_motor_decoder(not world); model.set_learnable_world_model(world)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=0.0)          # torch_models.py:119-122
+        x, y = torch.Tensor(X), torch.Tensor(Y)                                          # what DatasetBase + default collate hand over
+
+        def step():
+            opt.zero_grad()
+            loss = refload.reference_compute_loss(model, x, y, world, kl_coeff=1.0, cyc_coeff=1e-3)
+            loss.backward()
+            opt.step()
+            return loss.item()
+        return step, "reference"
+    if want == "reference":
+        raise RuntimeError("baseline/_ref is not staged (python oracle/stage_ref.py where /root/reference exists)")
     from oracle import pvae_oracle as orc
-    cores = CPU_THREADS or os.cpu_count() or 1
-    torch.set_num_threads(cores)
     torch.manual_seed(seed)
     m = orc.OracleModel(cfg["dsb"], cfg["da"], cfg["z"], orc.gen_layers(*cfg["te"]), orc.gen_layers(*cfg["md"]), orc.gen_layers(*cfg["wm"]))
+    tr = orc.OracleTrainer(m, X, Y, batch_size=rows, max_iter_world_model=0 if phase == "vae" else 10 ** 9)
+    return tr.step, "port"
 
-    def trainer(n):
-        X, Y = synthetic_arrays(cfg, n, seed + 1)
-        return orc.OracleTrainer(m, X, Y, batch_size=n, max_iter_world_model=0 if phase == "vae" else 10 ** 9)
-    tr = trainer(rows)
+
+def cpu_arm(cfg, phase, rows, steps, warmup, seed=0, min_seconds=0.0, max_seconds=150.0):
+    """`steps` timed mini-batch steps of `rows` transitions each on all host cores.  `min_seconds`: keep stepping until that much
+    time was measured (the cpu_baseline leg wants 10-30 s of CPU work); `max_seconds`: if the requested run would take longer,
+    the per-step sample shrinks (reported) so that the run still ends within minutes."""
+    cores = CPU_THREADS or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, kind = _reference_stepper(cfg, phase, rows, seed)
     t0 = time.perf_counter()
-    tr.step()
+    step()
     t1 = time.perf_counter() - t0
     while rows > 256 and t1 * (steps + warmup) > max_seconds:
         rows //= 2
-        tr = trainer(rows)
+        step, kind = _reference_stepper(cfg, phase, rows, seed)
         t0 = time.perf_counter()
-        tr.step()
+        step()
         t1 = time.perf_counter() - t0
     for _ in range(max(warmup - 1, 0)):
-        tr.step()
+        step()
     done, t0 = 0, time.perf_counter()
     while done < steps or (time.perf_counter() - t0) < min_seconds:
-        tr.step()
+        step()
         done += 1
     dt = time.perf_counter() - t0
-    return rows * done / dt, dt / done * 1e3, cores, rows, done
+    return rows * done / dt, dt / done * 1e3, cores, rows, done, kind
+
+
+KIND_TEXT = {"reference": "the reference's own train_physics_vae.TrainModel.compute_loss (unmodified files, baseline/_ref) + backward + Adam + item",
+             "port": "oracle port of compute_loss + backward + Adam + item"}
 
 
 def run_reference(args, cfg):
@@ -201,35 +244,237 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(1, args.warmup)
-    value, ms, cores, rows, steps = cpu_arm(cfg, args.phase, args.cpu_sample, steps, warmup)
-    sample = "%d steps of %d transitions (%s phase, %s dims), fp32 torch-CPU on %d threads, compute_loss+backward+Adam+item" % (
-        steps, rows, args.phase, args.config, cores)
+    value, ms, cores, rows, steps, kind = cpu_arm(cfg, args.phase, args.cpu_sample or args.batch, steps, warmup)
+    sample = "%d steps of %d transitions each (%s phase, %s dims) of the batch-%d workload, fp32 torch-CPU on %d threads: %s" % (
+        steps, rows, args.phase, args.config, args.batch, cores, KIND_TEXT[kind])
     line = {"impl": "reference", "metric": "transitions/sec (world-model+VAE step)", "value": value, "unit": "transitions/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload(args, cfg),
-            "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "sample_rows_per_step": rows,
+            "config": workload(args, cfg, args.phase, args.batch),
+            "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload(args, cfg):
+def workload(args, cfg, phase, batch, dims=None):
+    dims = dims or args.config
     return {"workload": "%s-phase train step, dim_state_body=%d dim_action=%d latent=%d, TE %dx%d MD %dx%d WM %dx%d, batch=%d per GPU" % (
-        args.phase, cfg["dsb"], cfg["da"], cfg["z"], cfg["te"][0], cfg["te"][1], cfg["md"][0], cfg["md"][1], cfg["wm"][0], cfg["wm"][1],
-        args.batch), "phase": args.phase, "dims": args.config, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
-        "precision": args.precision if args.impl == "b200" else "fp32", "parallelism": "dp%d" % args.gpus,
-        "resident_rows_per_gpu": 4 * args.batch,
+        phase, cfg["dsb"], cfg["da"], cfg["z"], cfg["te"][0], cfg["te"][1], cfg["md"][0], cfg["md"][1], cfg["wm"][0], cfg["wm"][1],
+        batch), "phase": phase, "dims": dims, "batch_per_gpu": batch, "global_batch": batch * args.gpus,
+        "precision": args.precision, "parallelism": "dp%d" % args.gpus, "resident_rows_per_gpu": 4 * batch,
         "l2": "not flushed: the per-step working set (resident transitions + activations, >1 GB at batch 65536) exceeds the 126 MB L2"}
 
 
 # --------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------------------------
+def make_trainer(cfg, B, precision, rank, world, phase="world", n_rows=None, local_shards=True, seed_base=1000):
+    """The product's trainer (physicsvae_b200.train_physics_vae.TrainModel) on a synthetic resident dataset of 4*B rows."""
+    from physicsvae_b200 import train_physics_vae as tp
+    from physicsvae_b200 import torch_models as tm
+    n_rows = n_rows or 4 * B
+
+    class BenchTrainer(tp.TrainModel):
+        dp_local_shards = local_shards
+
+        def load_dataset(self, file):
+            X, Y = synthetic_arrays(cfg, n_rows, seed=seed_base + (rank if local_shards else 0))
+            return tm.DatasetBase(X, Y, normalize_x=False, normalize_y=False)
+
+        def _local_rows(self, batch_size):
+            return batch_size          # weak scaling: `batch` rows per GPU, each rank owns its shard of the global batch
+
+    box = lambda n: tp.Box(low=-np.ones(n), high=np.ones(n), dtype=np.float64)
+    custom = dict(tp.MODEL_CONFIG)
+    custom.update(observation_space=box(2 * cfg["dsb"]), observation_space_body=box(cfg["dsb"]), observation_space_task=box(cfg["dsb"]),
+                  action_space=box(cfg["da"]), engine_precision=precision, engine_max_batch=B)
+    config = {"max_iter_world_model": 10 ** 9, "model": {"custom_model": "physics_vae", "custom_model_config": custom},
+              "lr": 5e-4, "lr_schedule": "step", "lr_schedule_params": {"step_size": 50, "gamma": 0.7}, "weight_decay": 0.0,
+              "dataset_train": ["synthetic"], "dataset_test": None, "loss": "MSE", "loss_test": "MSE", "batch_size": B,
+              "latent_dim": cfg["z"], "latent_prior_type": "normal_zero_mean_one_std", "act_fn": "relu",
+              "MD_width": cfg["md"][0], "MD_depth": cfg["md"][1], "TE_width": cfg["te"][0], "TE_depth": cfg["te"][1],
+              "lookahead": 1, "world_model_width": cfg["wm"][0], "world_model_depth": cfg["wm"][1], "vae_kl_coeff": 1.0,
+              "motor_decoder_a_rec_coeff": 1.0, "world_model_s_rec_coeff": 0.0, "vae_cycle_coeff": 1e-3,
+              "engine_precision": precision, "noise_seed": 1234}
+    torch.manual_seed(0)                      # same init on every rank (the trainer broadcasts rank 0's parameters anyway)
+    tr = BenchTrainer(config)
+    if phase == "vae":
+        tr._enter_vae_phase()
+    return tr
+
+
+def barrier(world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_steps(tr, steps, warmup, world, dev, sampler=None):
+    """K replays of the product's step graph through TrainModel.train_steps, CUDA events, barrier + synchronize on both sides,
+    max over ranks.  Returns (ms for K steps, clock record or None)."""
+    tr.train_steps(max(warmup, 3), restart=True)
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    tr.train_steps(steps)
+    e1.record()
+    barrier(world)
+    t1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev, world)
+    return ms, (sampler.stop(t0, t1) if sampler else None)
+
+
+def probe_kernel_ms(tr, kev, groups, per_group):
+    """Duration of the engine's launch sequence INSIDE the product's step graph: two external CUDA events recorded as nodes of
+    the graph around pvae_{world,vae}_step.  Each sample is the last replay of a group of `per_group` back-to-back replays."""
+    samples = []
+    for _ in range(groups):
+        tr.train_steps(per_group)
+        torch.cuda.synchronize()
+        v = kev[0].elapsed_time(kev[1])
+        if v > 0:
+            samples.append(v)
+    return sum(samples) / len(samples) if samples else None
+
+
+def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local, sustained_s, dims=None):
+    """Everything one phase contributes to the line: value through the product API, the in-graph kernel time (burst and sustained
+    clock regimes), roofline fractions against the matching measured peaks."""
+    from physicsvae_b200 import _abi
+    fl_world, fl_vae = flops_per_transition(cfg["dsb"], cfg["da"], cfg["z"], [cfg["te"][0]] * cfg["te"][1],
+                                            [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
+    flops_step = (fl_world if phase == "world" else fl_vae) * B
+    if phase == "vae" and tr.world_phase:
+        tr._enter_vae_phase()
+    # launches of one step, counted on an eager mini-batch (the graph replays the same sequence)
+    n0 = _abi.launch_count()
+    tr.train_batch(0, B)
+    # the eager path sets the cursor (and, VAE phase, the noise counter) per call; a replay advances the cursor on the device instead
+    launches_per_step = _abi.launch_count() - n0 - (2 if phase == "vae" else 1) + 1
+    try:
+        kev = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+    except TypeError:
+        kev = None
+    tr._graph_probe = kev
+    ms, clocks = time_steps(tr, steps, warmup, world, dev, ClockSampler(local) if rank == 0 else None)
+    value = B * world * steps / (ms * 1e-3)
+    kernel_ms = probe_kernel_ms(tr, kev, max(5, min(steps, 30)), 1) if kev else None
+    # sustained leg: >= sustained_s seconds of back-to-back steps (the 1 kW power cap pulls the SM clock down), then kernel samples
+    # taken as the last replay of 50-step groups so that the regime holds
+    sus = None
+    if sustained_s > 0:
+        per = ms / steps
+        n_sus = int(max(steps, sustained_s * 1e3 / per))
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        tr.train_steps(n_sus // 2)                                   # ramp into the power-capped regime
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        tr.train_steps(n_sus)
+        e1.record()
+        barrier(world)
+        t1 = time.time()
+        sms = max_over_ranks(e0.elapsed_time(e1), dev, world)
+        k_sus = probe_kernel_ms(tr, kev, 8, 50) if kev else None
+        sclk = sampler.stop(t0, t1) if sampler else None
+        sus = {"steps": n_sus, "ms_per_step": sms / n_sus, "value": B * world * n_sus / (sms * 1e-3), "kernel_ms_per_step": k_sus, "clocks": sclk}
+    pk, pk_src = peaks()
+    # not GEMMs: loss finalisation, fused Adam (one per trained net), cursor advance; VAE phase also reparameterisation fwd / bwd
+    gemm_launches = launches_per_step - {"world": 3, "vae": 6}[phase]
+    traffic = None
+    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the same workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s/%s/%d" % (dims or args.config, phase, B)
+        if key in tj:
+            traffic = tj[key]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roof = None
+    if kernel_ms:
+        ach = flops_step / (kernel_ms * 1e-3) / 1e12
+        ach_s = flops_step / (sus["kernel_ms_per_step"] * 1e-3) / 1e12 if sus and sus.get("kernel_ms_per_step") else None
+        burst_regime = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"])
+        roof = {"bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
+                "peak": pk["bf16_tflops"] if burst_regime else pk["bf16_tflops_sustained"],
+                "frac": ach / (pk["bf16_tflops"] if burst_regime else pk["bf16_tflops_sustained"]),
+                "regime": "burst (median SM clock >= 0.95 max during the timed region)" if burst_regime else "sustained (SM clock below 0.95 max during the timed region)",
+                "frac_burst": ach / pk["bf16_tflops"], "peak_burst": pk["bf16_tflops"],
+                "achieved_sustained": ach_s, "frac_sustained": (ach_s / pk["bf16_tflops_sustained"]) if ach_s else None,
+                "peak_sustained": pk["bf16_tflops_sustained"], "peak_source": pk_src + " (MEASURED_PEAKS.json: cuBLAS bf16 burst / sustained)",
+                "traffic": traffic, "kernel": "pvae_gemm_kernel", "launches_per_step": int(gemm_launches),
+                "avg_launch_ms": kernel_ms / max(gemm_launches, 1), "algorithmic_flops_per_launch": flops_step / max(gemm_launches, 1),
+                "kernel_ms_per_step": kernel_ms, "algorithmic_flops_per_step": flops_step,
+                "timing": "external CUDA events recorded as nodes of the product's step graph around the engine's launch sequence",
+                "whole_step_tflops": flops_step / (ms / steps * 1e-3) / 1e12}
+    tr._graph_probe = None
+    return {"value": value, "ms_per_step": ms / steps, "steps": steps, "clocks": clocks, "roofline": roof, "sustained": sus,
+            "launches_per_step": int(launches_per_step), "loss_after": float(tr.engine.loss[0].item()),
+            "config": workload(args, cfg, phase, B, dims)}
+
+
+def dp_equivalence_check(cfg, world, rank, dev):
+    """N > 1, before anything is timed: ONE data-parallel step of the real path (every rank its slice of a 4096-row global
+    mini-batch, NCCL all-reduce of the [gradients | loss] range) against the same global batch on rank 0 alone, bf16x3."""
+    import torch.distributed as dist
+    from physicsvae_b200 import parallel
+    Bg = 4096
+    out = {}
+    for phase in ("world", "vae"):
+        # trainer batch = the GLOBAL mini-batch; every rank holds the same Bg rows and takes its slice (engine capacity Bg rows, so
+        # that rank 0 can also run the whole batch alone)
+        tr = make_trainer(cfg, Bg, "bf16x3", rank, world, phase=phase, n_rows=Bg, local_shards=False, seed_base=555)
+        tr.model.latent_prior_noise = False
+        tr.batch_loss(0, Bg)
+        dp = tr.model.reduce_range(phase == "world").detach().clone()
+        torch.cuda.synchronize()
+        err = 0.0
+        if rank == 0:
+            parallel.set_replica_mode(True)                   # world_size() == 1: the whole batch here, no collective
+            tr.batch_loss(0, Bg)
+            one = tr.model.reduce_range(phase == "world").detach().clone()
+            parallel.set_replica_mode(False)
+            err = float((dp.double() - one.double()).norm() / one.double().norm())
+        t = torch.tensor([err], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[phase] = float(t.item())
+        del tr
+        torch.cuda.empty_cache()
+    return out
+
+
+def replica_checksum(tr, world, dev):
+    """After the timed steps: every rank must hold bit-identical parameters (replicated Adam on all-reduced gradients)."""
+    import torch.distributed as dist
+    from physicsvae_b200.engine import NET_NAMES
+    sums = torch.stack([tr.model.flat_params(n).double().sum() for n in NET_NAMES] +
+                       [tr.model.flat_params(n).double().abs().sum() for n in NET_NAMES])
+    if world == 1:
+        return True
+    allv = [torch.empty_like(sums) for _ in range(world)]
+    dist.all_gather(allv, sums)
+    return all(bool(torch.equal(v, allv[0])) for v in allv)
+
+
 def run_b200(args, cfg):
     import torch.distributed as dist
     from physicsvae_b200 import _abi, parallel
     from physicsvae_b200 import train_physics_vae as tp
-    from physicsvae_b200 import torch_models as tm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -240,293 +485,154 @@ def run_b200(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
     B, phase = args.batch, args.phase
-    n_rows = 4 * B
+    steps, warmup = args.steps, max(args.warmup, 3)
+    n0_launch = _abi.launch_count() if os.path.exists(_abi.LIB_PATH) else 0
 
-    class BenchTrainer(tp.TrainModel):
-        dp_local_shards = True
-
-        def load_dataset(self, file):
-            X, Y = synthetic_arrays(cfg, n_rows, seed=1000 + rank)
-            return tm.DatasetBase(X, Y, normalize_x=False, normalize_y=False)
-
-        def _local_rows(self, batch_size):
-            return batch_size          # weak scaling: `batch` rows per GPU, each rank owns its shard of the global batch
-
-    box = lambda n: tp.Box(low=-np.ones(n), high=np.ones(n), dtype=np.float64)
-    custom = dict(tp.MODEL_CONFIG)
-    custom.update(observation_space=box(2 * cfg["dsb"]), observation_space_body=box(cfg["dsb"]), observation_space_task=box(cfg["dsb"]),
-                  action_space=box(cfg["da"]), engine_precision=args.precision, engine_max_batch=B)
-    config = {"max_iter_world_model": 0 if phase == "vae" else 10 ** 9, "model": {"custom_model": "physics_vae", "custom_model_config": custom},
-              "lr": 5e-4, "lr_schedule": "step", "lr_schedule_params": {"step_size": 50, "gamma": 0.7}, "weight_decay": 0.0,
-              "dataset_train": ["synthetic"], "dataset_test": None, "loss": "MSE", "loss_test": "MSE", "batch_size": B,
-              "latent_dim": cfg["z"], "latent_prior_type": "normal_zero_mean_one_std", "act_fn": "relu",
-              "MD_width": cfg["md"][0], "MD_depth": cfg["md"][1], "TE_width": cfg["te"][0], "TE_depth": cfg["te"][1],
-              "lookahead": 1, "world_model_width": cfg["wm"][0], "world_model_depth": cfg["wm"][1], "vae_kl_coeff": 1.0,
-              "motor_decoder_a_rec_coeff": 1.0, "world_model_s_rec_coeff": 0.0, "vae_cycle_coeff": 1e-3,
-              "engine_precision": args.precision, "optimizer_capturable": True}
-    torch.manual_seed(0)                      # same init on every rank (replicated parameters)
-    # N > 1: allocate the trainer's device memory (flat gradient buffers included) from NCCL's allocator and register the pool
-    # with the communicator, so that the all-reduce runs zero-copy on the user buffers (NVLS / symmetric memory on NVSwitch)
-    # instead of staging through NCCL's internal buffers.  Opt-in (PVAE_NCCL_POOL=1): measured at N = 2 it changes nothing
-    # (0.567 ms per step either way), and it has not been run at N = 8.
-    import contextlib
-    pool, backend, nccl_pool = None, None, "off"
-    if world > 1 and os.environ.get("PVAE_NCCL_POOL", "0") == "1":
-        try:
-            backend = dist.distributed_c10d._get_default_group()._get_backend(dev)
-            pool = torch.cuda.MemPool(backend.mem_allocator)
-        except Exception as e:  # noqa
-            pool, nccl_pool = None, "unavailable: %s" % repr(e)[:120]
-    with (torch.cuda.use_mem_pool(pool) if pool is not None else contextlib.nullcontext()):
-        tr = BenchTrainer(config)
-        torch.cuda.synchronize()
-    if pool is not None:
-        try:
-            backend.register_mem_pool(pool)
-            nccl_pool = "registered"
-        except Exception as e:  # noqa
-            nccl_pool = "allocated, not registered: %s" % repr(e)[:120]
-    if phase == "vae":
-        tr.model.set_learnable_task_encoder(True); tr.model.set_learnable_motor_decoder(True); tr.model.set_learnable_world_model(False)
-        tr.read_loss_fn_coeff(world=False)
-    eng, model = tr.engine, tr.model
-    nets = ["world_model"] if phase == "world" else ["task_encoder", "motor_decoder"]
-    grads = [model.flat_grads(n) for n in nets]
-
-    # events around the GEMM launch sequence INSIDE the step: recorded as external event nodes of the captured graph, so the
-    # roofline leg times the tensor-core kernels in the very replays of the timed region (no second graph, same cache state)
-    # (external records are only legal during capture: the events are armed after the eager warm-up calls)
-    kev = None
-
-    def one_step():
-        """The hot path on rows [cursor, cursor + B) of this rank's resident shard."""
-        if kev:
-            kev[0].record()
-        if phase == "world":
-            eng.world_step(B, s_coeff=1.0)
-        else:
-            eng.vae_step(B, eps=None, seed=1234, offset=rank, noise=True, a_coeff=1.0, kl_coeff=1.0, cyc_coeff=1e-3)
-        if kev:
-            kev[1].record()
-        if world > 1:
-            parallel.allreduce_avg_(grads)
-        tr.optimizer.step()                 # fused Adam + shadow-weight refresh (physicsvae_b200.optim.PvaeAdam)
-        eng.advance_cursor(B, B, n_rows)
-
-    eng.set_cursor(0)
-    model.sync_weights()
-    n0 = _abi.launch_count()
-    one_step()
-    launches_per_step = _abi.launch_count() - n0
-    for _ in range(2):
-        one_step()
-    torch.cuda.synchronize()
-    graph = None
-    if args.no_graph:
-        kev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    else:
-        try:
-            kev = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
-        except TypeError:
-            kev = None
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    one_step()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = g
-        except Exception as e:  # noqa
-            if rank == 0:
-                print("[bench] CUDA graph capture failed (%s); running eagerly" % (repr(e)[:200]), file=sys.stderr)
-            graph = None
-            kev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            torch.cuda.synchronize()
-    run = (lambda: graph.replay()) if graph is not None else one_step
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        run()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        run()
-    e1.record()
-    barrier()
-    t1 = time.time()
-    ms = e0.elapsed_time(e1)
-    in_region_kernel_ms = None
-    if kev:
-        try:
-            in_region_kernel_ms = kev[0].elapsed_time(kev[1])          # the last step of the timed region
-        except Exception:
-            in_region_kernel_ms = None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dp_check = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    clocks = sampler.stop(t0, t1) if sampler else None
-    loss_after = float(eng.loss[0].item())
-    value = B * world * args.steps / (ms * 1e-3)
-    if os.environ.get("PVAE_TRACE_IDX") and rank == 0:      # tools/gpu_trace.sh: role timeline of one GEMM launch
-        import ctypes
-        nwords = _abi.load().pvae_debug_trace(None, 0, 0)
-        buf = (ctypes.c_ulonglong * nwords)()
-        _abi.load().pvae_debug_trace(buf, nwords, 0)
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        np.save(os.path.join(ROOT, "gpurun_out", "trace_%s.npy" % os.environ["PVAE_TRACE_IDX"]), np.frombuffer(buf, dtype=np.uint64))
+        errs = dp_equivalence_check(cfg, world, rank, dev)
+        dp_check = {"grad_rel_l2_vs_single_rank": errs, "ok": all(v < 1e-5 for v in errs.values())}
 
-    # ---- roofline leg: the tensor-core kernel sequence alone (forward + loss + backward launches of one step), CUDA events
-    #      on the launching stream around pvae_{world,vae}_step only (no Adam / all-reduce / shadow refresh)
-    fl_world, fl_vae = flops_per_transition(cfg["dsb"], cfg["da"], cfg["z"], [cfg["te"][0]] * cfg["te"][1],
-                                                [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
-    flops_step = (fl_world if phase == "world" else fl_vae) * B
-    def kernel_seq():
-        if phase == "world":
-            eng.world_step(B, s_coeff=1.0)
+    tr = make_trainer(cfg, B, args.precision, rank, world, phase=phase)
+    main = measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local, args.sustained_seconds)
+    phases = {}
+    if not args.only_phase:
+        other = "vae" if phase == "world" else "world"
+        if other == "vae":
+            phases["vae"] = measure_phase(args, cfg, tr, "vae", B, world, rank, dev, steps, warmup, local, args.sustained_seconds)
         else:
-            eng.vae_step(B, eps=None, seed=1234, offset=rank, noise=True, a_coeff=1.0, kl_coeff=1.0, cyc_coeff=1e-3)
-        eng.advance_cursor(B, B, n_rows)
-    n0 = _abi.launch_count()
-    kernel_seq()
-    gemm_launches = (_abi.launch_count() - n0) - 2                     # minus finalize_loss + cursor advance
-    torch.cuda.synchronize()
-    kernel_ms, kernel_how = None, None
-    if kev:
-        try:
-            samples = [in_region_kernel_ms] if in_region_kernel_ms else []
-            for _ in range(max(5, min(args.steps, 50))):
-                run()                                   # the SAME graph / step as the timed region
-                torch.cuda.synchronize()
-                samples.append(kev[0].elapsed_time(kev[1]))
-            samples = [x for x in samples if x > 0]
-            if samples:
-                kernel_ms = sum(samples) / len(samples)
-                kernel_how = "external CUDA events around the GEMM launch sequence inside the step's graph, mean of %d replays" % len(samples)
-        except Exception as e:  # noqa
-            kernel_ms = None
-    kgraph = None
-    if kernel_ms is None and not args.no_graph:                      # fallback: the same launch sequence as its own graph
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    kernel_seq()
-            torch.cuda.current_stream().wait_stream(side)
-            kgraph = g
-        except Exception:
-            kgraph = None
-            torch.cuda.synchronize()
-    if kernel_ms is None:
-        krun = (lambda: kgraph.replay()) if kgraph is not None else kernel_seq
-        for _ in range(3):
-            krun()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kiters = max(5, min(args.steps, 50))
-        torch.cuda.synchronize()
-        k0.record()
-        for _ in range(kiters):
-            krun()
-        k1.record()
-        k1.synchronize()
-        kernel_ms = k0.elapsed_time(k1) / kiters
-        kernel_how = "CUDA events around %d replays of the GEMM launch sequence as its own graph" % kiters
-    kgraph = None
-    pk, pk_src = peaks()
-    achieved = flops_step / (kernel_ms * 1e-3) / 1e12
-    traffic = None
-    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the same workload
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s/%s/%d" % (args.config, phase, B)
-        if key in tj:
-            traffic = tj[key]["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
-                "peak_source": pk_src + " (sustained; burst %.1f)" % pk["bf16_tflops"],
-                "kernel": "pvae_gemm_kernel", "launches_per_step": int(gemm_launches),
-                "avg_launch_ms": kernel_ms / max(gemm_launches, 1), "algorithmic_flops_per_launch": flops_step / max(gemm_launches, 1),
-                "kernel_ms_per_step": kernel_ms, "timing": kernel_how, "algorithmic_flops_per_step": flops_step,
-                "whole_step_tflops": flops_step / (ms / args.steps * 1e-3) / 1e12}
+            tr2 = make_trainer(cfg, B, args.precision, rank, world, phase="world")
+            phases["world"] = measure_phase(args, cfg, tr2, "world", B, world, rank, dev, steps, warmup, local, args.sustained_seconds)
+            del tr2
+    replicas_identical = replica_checksum(tr, world, dev)
+    if dp_check is not None:
+        dp_check["replicas_identical_after_timed_steps"] = replicas_identical
+        dp_check["ok"] = dp_check["ok"] and replicas_identical
+    gpu_launches_timed = int(main["launches_per_step"] * steps)
 
-    # ---- end-to-end leg: the reference-facing call with HOST buffers.  Per step, exactly what torch_models.TrainModel.step
-    #      does per mini-batch: x, y (pinned host fp32, as the DataLoader hands them over) -> device, compute_loss, backward,
-    #      optimizer.step, loss.item()
-    xa, ya = synthetic_arrays(cfg, B, seed=77 + rank)
-    xh = torch.from_numpy(xa).float().pin_memory()
-    yh = torch.from_numpy(ya).pin_memory()
-    h2d = xh.numel() * 4 + yh.numel() * 4
-    # double-buffered loader: the copy of mini-batch i + 1 (pinned host -> device, every step) runs on a copy stream while
-    # step i computes; loss.item() at the end of every step is the device -> host read
+    # ---- end-to-end legs (world phase of the headline workload unless --phase vae) ------------------------------------------
+    # (1) "e2e": every step uploads ITS inputs from pinned host memory and reads the loss back.  The mini-batch travels in the
+    #     compact form of the dataset (every state once + per-transition index, TrainModel.compute_loss_episodes): half the bytes
+    #     of the expanded x = [s_t | s_{t+1}] the reference's DataLoader hands over.  Double-buffered on a copy stream.
+    if phase == "world" and not tr.world_phase:
+        tr_e = make_trainer(cfg, B, args.precision, rank, world, phase="world")
+    else:
+        tr_e = tr
+    T = 129
+    E = (B + T - 2) // (T - 1)
+    rng = np.random.default_rng(77 + rank)
+    st = (rng.standard_normal((E, 1, cfg["dsb"])) + np.cumsum(np.concatenate(
+        [np.zeros((E, 1, cfg["dsb"])), 0.05 * rng.standard_normal((E, T - 1, cfg["dsb"]))], axis=1), axis=1)).reshape(E * T, cfg["dsb"])
+    first = (np.arange(E)[:, None] * T + np.arange(T - 1)[None, :]).reshape(-1)[:B].astype(np.int64)
+    sh = torch.from_numpy(st.astype(np.float32)).pin_memory()
+    ah = torch.from_numpy(rng.uniform(-1, 1, size=(E * T, cfg["da"])).astype(np.float32)).pin_memory()
+    fh = torch.from_numpy(first).pin_memory()
+    h2d = sh.numel() * 4 + ah.numel() * 4 + fh.numel() * 8
     copy_stream = torch.cuda.Stream()
-    bufs = [(torch.empty_like(xh, device=dev), torch.empty_like(yh, device=dev)) for _ in range(2)]
+    bufs = [tuple(torch.empty_like(t, device=dev) for t in (sh, ah, fh)) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
-            bufs[i % 2][0].copy_(xh, non_blocking=True)
-            bufs[i % 2][1].copy_(yh, non_blocking=True)
+            for d, s_ in zip(bufs[i % 2], (sh, ah, fh)):
+                d.copy_(s_, non_blocking=True)
             ready[i % 2].record(copy_stream)
 
     def e2e_step(i, last=False):
         if not last:
             prefetch(i + 1)                  # buffer (i + 1) % 2 was last read by step i - 1, which loss.item() has retired
         torch.cuda.current_stream().wait_event(ready[i % 2])
-        x, y = bufs[i % 2]
-        loss = tr.compute_loss(y, x)
+        s_, a_, f_ = bufs[i % 2]
+        loss = tr_e.compute_loss_episodes(s_, a_, f_)
         loss.backward()
-        tr.optimizer.step()
+        tr_e.optimizer.step()
         return loss.item()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(steps, 20))
     prefetch(0)
     for i in range(3):
         e2e_step(i)
-    barrier()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(3, 3 + e2e_steps):
         e2e_step(i, last=(i == 2 + e2e_steps))
     e1.record()
-    barrier()
-    ems = e0.elapsed_time(e1)
-    t = torch.tensor([ems], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ems = float(t.item())
+    barrier(world)
+    ems = max_over_ranks(e0.elapsed_time(e1), dev, world)
     e2e = {"value": B * world * e2e_steps / (ems * 1e-3), "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-           "steps": e2e_steps, "ms_per_step": ems / e2e_steps, "api": "double-buffered pinned-host loader -> TrainModel.compute_loss(y, x) + backward + optimizer.step + loss.item()"}
+           "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
+           "api": "double-buffered pinned-host loader (unique states + index) -> TrainModel.compute_loss_episodes + backward + optimizer.step + loss.item()"}
+    # (2) "e2e_resident": what the reference's Trainable.step() does -- whole epochs over the dataset -- with the dataset uploaded
+    #     once at setup: TrainModel.step() = graph replays + one loss read-back per epoch (+ the LR scheduler)
+    epochs = max(2, min(steps // 4, 10))
+    tr_e.step()
+    barrier(world)
+    e0.record()
+    for _ in range(epochs):
+        r = tr_e.step()
+    e1.record()
+    barrier(world)
+    rms = max_over_ranks(e0.elapsed_time(e1), dev, world)
+    e2e_res = {"value": B * world * 4 * epochs / (rms * 1e-3), "unit": "transitions/s", "epochs": epochs, "steps_per_epoch": 4,
+               "ms_per_step": rms / (4 * epochs), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 1, "mean_train_loss": r["mean_train_loss"],
+               "api": "TrainModel.step() over the resident dataset (uploaded once by setup()); one loss read-back per epoch"}
+    if tr_e is not tr:
+        del tr_e
+
+    # ---- secondary legs ----------------------------------------------------------------------------------------------------
+    extra = {}
+    if not args.only_phase and args.precision == "bf16":
+        # the fp32-accurate arithmetic (hi/lo split bf16, three tensor-core passes): the mode that meets rtol=1e-3 / atol=1e-5
+        del tr
+        torch.cuda.empty_cache()
+        t3 = make_trainer(cfg, B, "bf16x3", rank, world, phase=phase)
+        k3 = max(5, min(steps, 20))
+        ms3, _ = time_steps(t3, k3, 3, world, dev)
+        extra["bf16x3"] = {"value": B * world * k3 / (ms3 * 1e-3), "ms_per_step": ms3 / k3, "steps": k3, "phase": phase,
+                           "note": "fp32-accurate mode (tests: rtol=1e-3 / atol=1e-5 against the fp32 oracle at this batch size)"}
+        del t3
+        torch.cuda.empty_cache()
+        tr = None
+    cfgs = {}
+    if not args.only_phase and (world == 8 or args.all_configs):
+        # BASELINE.json configs[3]: full VAE, global batch 262144 on 8 GPUs (32768 rows per GPU);
+        # configs[4]: wide dims (dsb 512, da 128, hidden 3x1024), global batch 131072 on 8 GPUs (16384 rows per GPU), both phases
+        tr = None
+        torch.cuda.empty_cache()
+        kc = max(20, min(steps, 100))
+        for name, cname, ph, rows in (("cfg4_vae_262144_global", "default", "vae", 262144 // 8), ("cfg5_wide_131072_global_world", "wide", "world", 131072 // 8),
+                                      ("cfg5_wide_131072_global_vae", "wide", "vae", 131072 // 8)):
+            c = CONFIGS[cname]
+            tc = make_trainer(c, rows, args.precision, rank, world, phase=ph)
+            r_ = measure_phase(args, c, tc, ph, rows, world, rank, dev, kc, 5, local, 0.0, dims=cname)
+            cfgs[name] = {k: r_[k] for k in ("value", "ms_per_step", "steps", "roofline", "config", "launches_per_step")}
+            del tc
+            torch.cuda.empty_cache()
 
     if rank == 0:
-        line = {"metric": "transitions/sec (world-model+VAE step)", "value": value, "unit": "transitions/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        line = {"metric": "transitions/sec (world-model+VAE step)", "value": main["value"], "unit": "transitions/s", "n_gpus": world,
+                "steps": steps, "warmup": warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3(fp32-accurate)",
-                "data": "synthetic", "config": workload(args, cfg), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
-                "cuda_graph": graph is not None, "nccl_user_buffers": nccl_pool, "roofline": roofline, "loss_after": loss_after}
+                "data": "synthetic", "config": main["config"], "clocks": main["clocks"], "e2e": e2e, "e2e_resident": e2e_res,
+                "gpu_launches": gpu_launches_timed, "launches_per_step": main["launches_per_step"],
+                "api": "physicsvae_b200.train_physics_vae.TrainModel.train_steps (replays of the step graph TrainModel.step() captures)",
+                "cuda_graph": True, "roofline": main["roofline"], "sustained": main["sustained"], "loss_after": main["loss_after"],
+                "phases": {k: {kk: v[kk] for kk in ("value", "ms_per_step", "steps", "clocks", "roofline", "sustained", "launches_per_step", "config", "loss_after")}
+                           for k, v in phases.items()},
+                "library_launches_total": int(_abi.launch_count() - n0_launch)}
+        line.update(extra)
+        if cfgs:
+            line["configs"] = cfgs
+        if dp_check is not None:
+            line["dp_check"] = dp_check
         if not args.no_cpu_baseline:
-            v, cms, cores, rows, nsteps = cpu_arm(cfg, phase, args.cpu_sample, 3, 1, min_seconds=10.0)
-            line["cpu_baseline"] = {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port", "ms_per_step": cms,
-                                    "sample": "%d steps of %d transitions (%s phase, ~10 s), oracle port of compute_loss+backward+Adam+item, "
-                                              "fp32 torch-CPU on %d threads" % (nsteps, rows, phase, cores)}
+            v, cms, cores, rows, nsteps, kind = cpu_arm(cfg, phase, args.cpu_sample or 4096, 3, 1, min_seconds=10.0)
+            line["cpu_baseline"] = {"value": v, "unit": "transitions/s", "cores": cores, "kind": kind, "ms_per_step": cms,
+                                    "sample": "%d steps of %d transitions (%s phase, ~10 s) of the batch-%d workload, fp32 torch-CPU on %d threads: %s" % (
+                                        nsteps, rows, phase, B, cores, KIND_TEXT[kind])}
         print(json.dumps(line), flush=True)
     # Teardown: a CUDA graph that captured NCCL work keeps the communicator busy and destroy_process_group() can block on
-    # it forever; every rank is done with collectives here, so drop the graph and leave without the collective teardown.
-    graph = None
+    # it forever; every rank is done with collectives here, so leave without the collective teardown.
     torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
@@ -606,7 +712,7 @@ def run_torch(args, cfg):
     pk, _ = peaks()
     print(json.dumps({"impl": "torch", "metric": "transitions/sec (world-model+VAE step)", "value": B / (ms * 1e-3), "unit": "transitions/s",
                       "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-                      "dtype": "bf16 autocast (cuBLASLt) + fp32 masters", "data": "synthetic", "config": workload(args, cfg), "cuda_graph": True,
+                      "dtype": "bf16 autocast (cuBLASLt) + fp32 masters", "data": "synthetic", "config": workload(args, cfg, args.phase, args.batch), "cuda_graph": True,
                       "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
                                    "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                                    "note": "whole step (library kernels are not separable by event inside the graph)"}}), flush=True)
@@ -616,6 +722,7 @@ if __name__ == "__main__":
     a = parse()
     c = CONFIGS[a.config]
     CPU_THREADS = a.cpu_threads
+    CPU_KIND = a.cpu_kind
     if a.impl == "torch":
         run_torch(a, c)
     elif a.impl == "reference":

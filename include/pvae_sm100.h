@@ -134,7 +134,8 @@ int pvae_ingest_episodes(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t
 /* select the buffer the step functions read from; mini-batch b = rows [cursor, cursor + batch) */
 int pvae_bind_transitions(pvae_handle h, const void* buf_dev, int64_t buf_rows);
 int pvae_set_cursor(pvae_handle h, int64_t row, pvae_stream s);
-/* cursor += delta; if cursor + batch > limit then cursor = 0  (device-side, graph-replayable) */
+/* cursor += delta; if cursor + batch > limit then cursor = cursor mod delta -- a rank that started on row s < delta (its slice of
+ * the first global mini-batch of `delta` rows) is back on row s, a single rank on row 0  (device-side, graph-replayable) */
 int pvae_advance_cursor(pvae_handle h, int64_t delta, int64_t batch, int64_t limit, pvae_stream s);
 
 /* --- the training steps (forward + loss + backward; gradients land in the bound grad buffers) ------------------ */

@@ -8,6 +8,8 @@ Fixtures
                         -- weights are NOT copied (12.5 MB), only sha256 + outputs.
   ref_dataset.npz      load_dataset_for_PhysicsVAE on a synthetic README-format pickle: X / Y arrays and batch sizes.
   ref_small_variants.npz  tiny model; ELU / tanh / sigmoid hidden activations and latent_prior_type=False: init, forward outputs, losses, gradients.
+  ref_small_variants2.npz  the same recipe for swish hidden activations (rllib's Swish: x * sigmoid(beta x), beta a parameter initialised
+                       to 1) and for the xavier_normal / xavier_uniform initialisers of get_initializer (rllib_model_torch.py:220-232).
   ref_lookahead.npz    compute_loss with lookahead 3 (autoregressive rollout): losses and gradients of both phases.
   ref_trajectory.npz   four epochs of the reference's own TrainModel.step() (two world-model epochs, phase switch, two VAE epochs;
                        Adam lr 5e-4, StepLR, batch 32 with a short last batch, latent_prior_noise False so that no RNG is involved):
@@ -118,6 +120,54 @@ def small_variants():
                     out[ph + "/grad/" + k] = p_.grad.detach().numpy().copy()
         print("ref_small_variants.npz %s: world loss %.8f vae loss %.8f" % (tag, out[tag + "/world/loss"], out[tag + "/vae/loss"]))
     np.savez_compressed(os.path.join(OUT, "ref_small_variants.npz"), **out)
+
+
+def small_variants2():
+    """ref_small_variants2.npz: swish hidden layers, and the two xavier initialisers (seeded init + losses + gradients)."""
+    tpv, tm, rmt = refload.load()
+    dsb, da, z, B = 13, 5, 4, 48
+    data = orc.synthetic_episodes(1, 65, dsb, da, seed=6)
+    X, Y = orc.build_transitions(data["episodes"], num_samples=B)
+    x, y = torch.Tensor(X), torch.Tensor(Y)
+    out = {"B": B, "dsb": dsb, "da": da, "z": z, "X": X, "Y": Y}
+    torch.manual_seed(7)
+    out["eps"] = torch.randn(B, z).numpy()
+    prior = "normal_zero_mean_one_std"
+    for tag, act, init in (("swish", "swish", None), ("xavier_normal", "relu", {"name": "xavier_normal", "gain": 1.0}),
+                           ("xavier_uniform", "relu", {"name": "xavier_uniform", "gain": 1.4})):
+        te, md, wm, vf = (tpv.gen_layers(16, 2, act_hidden=act), tpv.gen_layers(24, 3, act_hidden=act), tpv.gen_layers(32, 2, act_hidden=act),
+                          tpv.gen_layers(16, 2, act_hidden=act))
+        for l in (te, md, wm):
+            l[-1]["init_weight"] = {"name": "normc", "std": 0.3}
+        if init is not None:
+            for l in (te, md, wm, vf):
+                for layer in l:
+                    layer["init_weight"] = dict(init)
+        torch.manual_seed(3)
+        model = refload.build_reference_model(dsb, da, z, te, md, wm, vf_layers=vf, prior=prior)
+        for k, v in model.state_dict().items():
+            out[tag + "/sd/" + k] = v.detach().numpy().copy()
+        torch.manual_seed(7)
+        logits, _ = model(input_dict={"obs": x[:, 0, :], "obs_flat": x[:, 0, :]}, state=None, seq_lens=None)
+        out[tag + "/logits"] = logits.detach().numpy()
+        out[tag + "/z_task"] = model._cur_task_encoder_variable.detach().numpy()
+        out[tag + "/future"] = model._cur_future_state.detach().numpy()
+        out[tag + "/value"] = model._cur_value.detach().numpy()
+        for world in (True, False):
+            model.zero_grad()
+            model.set_learnable_task_encoder(not world)
+            model.set_learnable_motor_decoder(not world)
+            model.set_learnable_world_model(world)
+            torch.manual_seed(7)
+            loss = refload.reference_compute_loss(model, x, y, world, kl_coeff=1.0, cyc_coeff=0.05, prior=prior)
+            loss.backward()
+            ph = tag + ("/world" if world else "/vae")
+            out[ph + "/loss"] = float(loss)
+            for k, p_ in model.named_parameters():
+                if p_.grad is not None:
+                    out[ph + "/grad/" + k] = p_.grad.detach().numpy().copy()
+        print("ref_small_variants2.npz %s: world loss %.8f vae loss %.8f" % (tag, out[tag + "/world/loss"], out[tag + "/vae/loss"]))
+    np.savez_compressed(os.path.join(OUT, "ref_small_variants2.npz"), **out)
 
 
 def lookahead():
@@ -238,4 +288,5 @@ if __name__ == "__main__":
     dataset()
     trajectory()
     small_variants()
+    small_variants2()
     lookahead()

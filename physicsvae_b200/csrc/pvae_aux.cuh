@@ -356,10 +356,12 @@ __global__ void finalize_loss_kernel(double* __restrict__ acc, float* __restrict
 
 __global__ void set_cursor_kernel(int32_t* cur, int32_t v) { if (threadIdx.x == 0) *cur = v; }
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { if (threadIdx.x == 0) *p = v; }
+// cursor += delta; past the end it wraps to (cursor mod delta): a rank that started at row s < delta (its slice of the first global
+// mini-batch) is back on row s, a single rank on row 0
 __global__ void advance_cursor_kernel(int32_t* cur, int32_t delta, int32_t batch, int32_t limit) {
   if (threadIdx.x == 0) {
     int32_t c = *cur + delta;
-    if (c + batch > limit) c = 0;
+    if (c + batch > limit) c = delta > 0 ? c % delta : 0;
     *cur = c;
   }
 }

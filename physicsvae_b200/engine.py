@@ -146,7 +146,7 @@ class Engine:
             _abi.check(self.lib.pvae_ingest(self._h, _ptr(self.transitions), self.n_rows, int(dst_row), _ptr(x_raw),
                                             1 if x_raw.dtype == torch.float64 else 0, _ptr(y_raw), x_raw.shape[0], _stream()))
 
-    def ingest_episodes(self, states, actions, first_state, dst_row=0):
+    def ingest_episodes(self, states, actions, first_state, dst_row=0, check=True):
         """Dataset build on the device: states CUDA [S, dsb] float64 / float32 (all episodes back to back, every state once),
         actions CUDA [S, da] float32, first_state CUDA [n] int64 (state row of s_t per transition; s_{t+1} is the next row)."""
         if self.transitions is None:
@@ -158,7 +158,8 @@ class Engine:
         states = states.to(self.device).contiguous()
         actions = actions.to(self.device, torch.float32).contiguous()
         first_state = first_state.to(self.device, torch.int64).contiguous()
-        if first_state.numel() and (int(first_state.min()) < 0 or int(first_state.max()) + 1 >= states.shape[0]):
+        # (the range check reads the index back to the host: per-step callers that built the index themselves skip it)
+        if check and first_state.numel() and (int(first_state.min()) < 0 or int(first_state.max()) + 1 >= states.shape[0]):
             raise ValueError("first_state index out of range")
         with torch.cuda.device(self.device):
             _abi.check(self.lib.pvae_ingest_episodes(self._h, _ptr(self.transitions), self.n_rows, int(dst_row), _ptr(states),

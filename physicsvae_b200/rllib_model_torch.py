@@ -56,13 +56,27 @@ except Exception:  # noqa
             ModelCatalog._registry[name] = cls
 
 
+class Swish(nn.Module):
+    """ray.rllib.utils.torch_ops.Swish (ray 1.11): x * sigmoid(beta * x) with `_beta` a parameter initialised to 1.0 -- kept so
+    that state dicts of swish nets interchange with the reference (`..._model.{i}._model.1._beta`).  The engine evaluates
+    swish with beta = 1 and does not train beta (PhysicsVAE.sync_weights refuses any other value): a documented deviation,
+    the training CLI never selects swish (train_physics_vae.py:266 hard-wires relu)."""
+
+    def __init__(self):
+        super().__init__()
+        self._beta = nn.Parameter(torch.tensor(1.0), requires_grad=False)
+
+    def forward(self, x):
+        return x * torch.sigmoid(self._beta * x)
+
+
 def get_activation_fn(name=None):
     """Activation registry (rllib_model_torch.py:30-46).  Returns the nn.Module class (None for linear); the class is
     only a marker here -- the engine applies the activation inside the GEMM epilogue."""
     if name in ["linear", None]:
         return None
     if name in ["swish", "silu"]:
-        return nn.SiLU
+        return Swish
     if name == "relu":
         return nn.ReLU
     if name == "tanh":
@@ -515,6 +529,9 @@ class PhysicsVAE(TorchModelV2, nn.Module):
 
     def sync_weights(self, names=None):
         eng = self.engine()
+        betas = [m._beta for m in self.modules() if isinstance(m, Swish)]
+        if betas and not bool((torch.stack([b.detach().reshape(()) for b in betas]) == 1.0).all()):
+            raise NotImplementedError("swish layers run with beta = 1 on the sm_100a engine (rllib's trainable beta is not implemented)")
         eng.sync_weights(names)
         if names is None:
             self._weights_dirty = False
@@ -682,13 +699,13 @@ class PhysicsVAE(TorchModelV2, nn.Module):
     def set_learnable_task_encoder(self, learnable):
         if self._task_encoder:
             for name, param in self._task_encoder.named_parameters():
-                param.requires_grad = learnable
+                param.requires_grad = learnable and not name.endswith("_beta")
         self._attach_grads()
 
     def set_learnable_motor_decoder(self, learnable, free_log_std=True):
         if self._motor_decoder:
             for name, param in self._motor_decoder.named_parameters():
-                param.requires_grad = learnable
+                param.requires_grad = learnable and not name.endswith("_beta")
                 if "log_std" in name:
                     param.requires_grad = free_log_std
         self._attach_grads()
@@ -699,7 +716,7 @@ class PhysicsVAE(TorchModelV2, nn.Module):
     def set_learnable_world_model(self, learnable):
         if self._world_model:
             for name, param in self._world_model.named_parameters():
-                param.requires_grad = learnable
+                param.requires_grad = learnable and not name.endswith("_beta")
         self._attach_grads()
 
 

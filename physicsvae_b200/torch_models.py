@@ -312,7 +312,12 @@ class TrainModel(_TrainableBase):
     def _graph_key(self, batch_size):
         """Everything a captured step bakes in as a host-side constant."""
         lr = self.optimizer.param_groups[0]["lr"]
-        return (int(batch_size), float(lr), parallel.world_size(), parallel.rank())
+        return (int(batch_size), float(lr), parallel.world_size(), parallel.rank(), id(getattr(self, "_graph_probe", None)))
+
+    def _shard(self, lo, hi):
+        """(first row, rows, loss weight) of this rank's part of the global mini-batch [lo, hi)."""
+        s, e = parallel.shard_rows(lo, hi, parallel.rank(), parallel.world_size())
+        return s, e - s, parallel.shard_weight(lo, hi, parallel.rank(), parallel.world_size())
 
     def _graph_body(self, batch_size):
         """One full mini-batch starting at the device cursor: engine step [+ all-reduce]; must not allocate or synchronise."""
@@ -334,11 +339,14 @@ class TrainModel(_TrainableBase):
                 self.model.sync_weights()
             eng = self.engine
 
+            _, n_local, _ = self._shard(0, batch_size)
+            n_full = self.train_loader.n // batch_size
+
             def body():
                 self._graph_body(batch_size)
                 self.optimizer.step()
                 self._loss_acc.add_(eng.loss[0])
-                eng.advance_cursor(batch_size, 0, 2 ** 31 - 1)
+                eng.advance_cursor(batch_size, n_local, n_full * batch_size)     # wraps to this rank's first row after the last full batch
             torch.cuda.synchronize()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -353,6 +361,7 @@ class TrainModel(_TrainableBase):
 
     def _graph_epoch(self, n_full, batch_size):
         g = self._graph_step(batch_size)
+        self._streaming = None
         self._graph_begin(batch_size)
         for _ in range(n_full):
             g.replay()
@@ -360,8 +369,26 @@ class TrainModel(_TrainableBase):
 
     def _graph_begin(self, batch_size):
         """Position the device-side state (cursor, noise counter) at the first full batch of the epoch."""
-        s, _ = parallel.shard_rows(0, batch_size, parallel.rank(), parallel.world_size())
-        self.engine.set_cursor(s)
+        self.engine.set_cursor(self._shard(0, batch_size)[0])
+
+    def train_steps(self, k, batch_size=None, restart=False):
+        """Streaming mode: `k` mini-batch SGD steps on consecutive FULL mini-batches of the resident training set, wrapping at
+        its end, with no host synchronisation at all -- k replays of the captured step (what `step()` replays per epoch, minus
+        the epoch bookkeeping: the loss accumulates on the device in `_loss_acc`, schedulers are not stepped).  `restart`
+        repositions the cursor on the first mini-batch.  This is the call bench.py times as `value`."""
+        bs = int(batch_size or self.train_loader.batch_size)
+        if not self._graph_ok(bs) or self.train_loader.n < bs:
+            raise _abi.PvaeError("train_steps needs the captured-graph path (PvaeAdam, cuda_graph=True) and at least one full mini-batch")
+        self.model.train()
+        self._bind("train")
+        g = self._graph_step(bs)
+        key = self._graph_key(bs)
+        if restart or getattr(self, "_streaming", None) != key:      # first call, or phase / lr / batch size changed
+            self._graph_begin(bs)
+            self._streaming = key
+        for _ in range(int(k)):
+            g.replay()
+        self._graph_end(int(k), bs)
 
     def _graph_end(self, n_full, batch_size):
         """Host-side bookkeeping for `n_full` replayed batches."""

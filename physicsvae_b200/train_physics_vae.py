@@ -442,12 +442,16 @@ class TrainModel(torch_models.TrainModel):
         _, n, w = self._shard(0, batch_size)
         if n <= 0:
             raise _abi.PvaeError("a captured step needs at least one row per rank (batch_size >= world size)")
+        probe = getattr(self, "_graph_probe", None)     # (bench.py) two external CUDA events around the engine's launch sequence
+        if probe:
+            probe[0].record()
         self._engine_step(n, w)
+        if probe:
+            probe[1].record()
         self._reduce()
 
     def _graph_begin(self, batch_size):
-        s, _, _ = self._shard(0, batch_size)
-        self.engine.set_cursor(s)
+        super()._graph_begin(batch_size)
         if not self.world_phase:
             self.engine.noise_counter(True, (self._noise_step + 1) * parallel.world_size(), parallel.world_size())
 
@@ -478,6 +482,25 @@ class TrainModel(torch_models.TrainModel):
 
     def compute_test_loss(self, y, x):
         return self.compute_loss(y, x)
+
+    def compute_loss_episodes(self, states, actions, first_state, eps=None):
+        """compute_loss for a mini-batch handed over in the COMPACT form of the dataset (episodes_to_index): states [S, dsb] with every
+        state once, actions [S, da], first_state [B] = row of s_t per transition (s_{t+1} is the next row).  Same arithmetic as
+        compute_loss(y, x) on the expanded x = [s_t | s_{t+1}], y = a_t; the upload is ~half the bytes because x is never
+        materialised -- the device-side builder (pvae_ingest_episodes) pairs the rows."""
+        B = int(first_state.shape[0])
+        if B < 2:
+            raise ValueError("compute_loss needs at least 2 transitions (the reference squeezes the batch axis)")
+        self._engine_rows = max(self._engine_rows, B)
+        eng = self.engine
+        buf = self._buffers.get("adhoc")
+        if buf is None or buf[1] != B:
+            buf = (torch.zeros(eng.transitions_bytes(B), dtype=torch.uint8, device=self.device), B)
+            self._buffers["adhoc"] = buf
+        self._bind("adhoc")
+        eng.ingest_episodes(states, actions, first_state, dst_row=0, check=False)
+        loss = self.batch_loss(0, B, eps=eps)
+        return torch_models._DepositedLoss.apply(self._anchor, loss)
 
     def save_checkpoint(self, checkpoint_dir):
         """train_physics_vae.py:440-467: model.pth + model.pt + task_encoder.pt + motor_decoder.pt + world_model.pt."""

@@ -45,8 +45,60 @@ def product_model(cfg, layers, state_dict, prior="normal_zero_mean_one_std", pre
                   value_fn_layers=orc.gen_layers(cfg["te"][0], cfg["te"][1], act_hidden=act),
                   latent_prior_type=prior, engine_precision=precision, engine_max_batch=max_batch)
     model = pm.PhysicsVAE(box(2 * dsb), box(da), 2 * da, {"custom_model_config": custom}, "physics_vae")
-    model.load_state_dict(state_dict)
+    sd = dict(state_dict)
+    for k, v in model.state_dict().items():          # rllib's Swish carries a `_beta` parameter the oracle does not model (beta = 1)
+        if k.endswith("._beta") and k not in sd:
+            sd[k] = v.detach().clone()
+    model.load_state_dict(sd)
     return model.to("cuda:0")
+
+
+def fast_transitions(cfg, n, seed=0):
+    """Vectorised synthetic transitions for the full-size tests (same recipe as oracle.synthetic_episodes):
+    X float64 [n, 2*dsb], Y float32 [n, da]."""
+    rng = np.random.default_rng(seed)
+    T = 129
+    E = (n + T - 2) // (T - 1)
+    dsb = cfg["dsb"]
+    s = rng.standard_normal((E, 1, dsb)) + np.cumsum(
+        np.concatenate([np.zeros((E, 1, dsb)), 0.05 * rng.standard_normal((E, T - 1, dsb))], axis=1), axis=1)
+    X = np.concatenate([s[:, :-1], s[:, 1:]], axis=-1).reshape(-1, 2 * dsb)[:n]
+    Y = rng.uniform(-1, 1, size=(n, cfg["da"])).astype(np.float32)
+    return np.ascontiguousarray(X), Y
+
+
+def make_trainer(cfg, X, Y, batch_size, precision="bf16x3", world_epochs=10 ** 9, state_dict=None, X_test=None, Y_test=None, **extra):
+    """The product's train_physics_vae.TrainModel on given transition arrays (no pickle): DatasetBase(X, Y) straight in."""
+    from physicsvae_b200 import train_physics_vae as tp
+    from physicsvae_b200 import torch_models as tm
+    sets = {"train": (X, Y), "test": (X_test, Y_test)}
+
+    class ArrayTrainer(tp.TrainModel):
+        def load_dataset(self, file):
+            Xa, Ya = sets[file]
+            return tm.DatasetBase(np.asarray(Xa).reshape(len(Xa), 1, -1), np.asarray(Ya).reshape(len(Ya), 1, -1), normalize_x=False, normalize_y=False)
+
+    box = lambda n: tp.Box(low=-np.ones(n), high=np.ones(n), dtype=np.float64)
+    custom = dict(tp.MODEL_CONFIG)
+    custom.update(observation_space=box(2 * cfg["dsb"]), observation_space_body=box(cfg["dsb"]), observation_space_task=box(cfg["dsb"]),
+                  action_space=box(cfg["da"]), engine_precision=precision, engine_max_batch=batch_size)
+    config = {"max_iter_world_model": world_epochs, "model": {"custom_model": "physics_vae", "custom_model_config": custom},
+              "lr": 5e-4, "lr_schedule": "step", "lr_schedule_params": {"step_size": 50, "gamma": 0.7}, "weight_decay": 0.0,
+              "dataset_train": "train", "dataset_test": "test" if X_test is not None else None, "loss": "MSE", "loss_test": "MSE",
+              "batch_size": batch_size, "latent_dim": cfg["z"], "latent_prior_type": "normal_zero_mean_one_std", "act_fn": "relu",
+              "MD_width": cfg["md"][0], "MD_depth": cfg["md"][1], "TE_width": cfg["te"][0], "TE_depth": cfg["te"][1],
+              "lookahead": 1, "world_model_width": cfg["wm"][0], "world_model_depth": cfg["wm"][1], "vae_kl_coeff": 1.0,
+              "motor_decoder_a_rec_coeff": 1.0, "world_model_s_rec_coeff": 0.0, "vae_cycle_coeff": 1e-3,
+              "engine_precision": precision}
+    config.update(extra)
+    tr = ArrayTrainer(config)
+    if state_dict is not None:
+        sd = dict(state_dict)
+        for k, v in tr.model.state_dict().items():
+            if k.endswith("._beta") and k not in sd:
+                sd[k] = v.detach().clone()
+        tr.model.load_state_dict(sd)
+    return tr
 
 
 def transitions(cfg, n, seed=0):

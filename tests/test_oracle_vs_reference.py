@@ -134,3 +134,49 @@ def test_lookahead_rollout_matches_live_reference():
     a = orc.loss_and_grads(m, x1, y1, False, cyc_coeff=0.05, eps=eps[:1])
     b = orc.loss_and_grads(m, x1[:, 0, :], y1[:, 0, :], False, cyc_coeff=0.05, eps=eps[0])
     assert abs(a[0] - b[0]) <= 1e-7 * abs(b[0]) and all(torch.allclose(a[2][k], b[2][k], rtol=1e-6, atol=1e-9) for k in b[2])
+
+
+def test_product_checkpoint_loads_strictly_into_the_live_reference_class(tmp_path):
+    """Interchange, product -> reference: `model.pt` / `world_model.pt` / `motor_decoder.pt` / `task_encoder.pt` written by the
+    product's save_weights* (train_physics_vae.py:440-467's file set) load with strict=True into the reference's own PhysicsVAE
+    through the reference's own loaders (rllib_model_torch.py:870-928), tensor for tensor."""
+    from physicsvae_b200 import rllib_model_torch as pm
+    from physicsvae_b200 import train_physics_vae as tp
+    tpv, tm, rmt = refload.load()
+    dsb, da, z = 23, 7, 6
+    box = lambda n: tp.Box(low=-np.ones(n), high=np.ones(n), dtype=np.float64)
+    custom = dict(pm.PhysicsVAE.DEFAULT_CONFIG)
+    custom.update(observation_space=box(2 * dsb), observation_space_body=box(dsb), observation_space_task=box(dsb), action_space=box(da),
+                  task_encoder_output_dim=z, task_encoder_layers=tp.gen_layers(16, 2), motor_decoder_layers=tp.gen_layers(24, 3),
+                  world_model_layers=tp.gen_layers(32, 2), value_fn_layers=tp.gen_layers(16, 2))
+    torch.manual_seed(21)
+    ours = pm.PhysicsVAE(box(2 * dsb), box(da), 2 * da, {"custom_model_config": custom}, "physics_vae")
+    files = {n: str(tmp_path / (n + ".pt")) for n in ("model", "task_encoder", "motor_decoder", "world_model")}
+    ours.save_weights(files["model"])
+    ours.save_weights_task_encoder(files["task_encoder"])
+    ours.save_weights_motor_decoder(files["motor_decoder"])
+    ours.save_weights_world_model(files["world_model"])
+    torch.manual_seed(99)                                   # a differently initialised reference model
+    ref = refload.build_reference_model(dsb, da, z, tpv.gen_layers(16, 2), tpv.gen_layers(24, 3), tpv.gen_layers(32, 2),
+                                        vf_layers=tpv.gen_layers(16, 2))
+    assert any(not torch.equal(v, ours.state_dict()[k]) for k, v in ref.state_dict().items())
+    missing = ref.load_state_dict(torch.load(files["model"]), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, ours.state_dict()[k]), k
+    # the per-part files through the reference's own loaders
+    torch.manual_seed(100)
+    ref2 = refload.build_reference_model(dsb, da, z, tpv.gen_layers(16, 2), tpv.gen_layers(24, 3), tpv.gen_layers(32, 2),
+                                         vf_layers=tpv.gen_layers(16, 2))
+    ref2.load_weights_task_encoder(files["task_encoder"])
+    ref2.load_weights_motor_decoder(files["motor_decoder"])
+    ref2.load_weights_world_model(files["world_model"])
+    for k, v in ref2.state_dict().items():
+        if not k.startswith("_value_branch"):
+            assert torch.equal(v, ours.state_dict()[k]), k
+    # and the other way round: the reference's file into the product
+    ref2.save_weights(str(tmp_path / "ref_model.pt"))
+    ours2 = pm.PhysicsVAE(box(2 * dsb), box(da), 2 * da, {"custom_model_config": custom}, "physics_vae")
+    ours2.load_weights(str(tmp_path / "ref_model.pt"))
+    for k, v in ours2.state_dict().items():
+        assert torch.equal(v, ref2.state_dict()[k]), k
