@@ -350,9 +350,9 @@ def probe_kernel_ms(tr, kev, groups, per_group):
     return sum(samples) / len(samples) if samples else None
 
 
-def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local, sustained_s, dims=None):
-    """Everything one phase contributes to the line: value through the product API, the in-graph kernel time (burst and sustained
-    clock regimes), roofline fractions against the matching measured peaks."""
+def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local, dims=None):
+    """Burst-clock leg of one phase: value through the product API (K replays of the trainer's own step graph) and the in-graph
+    duration of the engine's launch sequence."""
     from physicsvae_b200 import _abi
     fl_world, fl_vae = flops_per_transition(cfg["dsb"], cfg["da"], cfg["z"], [cfg["te"][0]] * cfg["te"][1],
                                             [cfg["md"][0]] * cfg["md"][1], [cfg["wm"][0]] * cfg["wm"][1])
@@ -360,6 +360,9 @@ def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, loca
     if phase == "vae" and tr.world_phase:
         tr._enter_vae_phase()
     # launches of one step, counted on an eager mini-batch (the graph replays the same sequence)
+    tr._bind("train")
+    if tr.model._weights_dirty:
+        tr.model.sync_weights()                                      # (one-off shadow-operand build: not part of a step)
     n0 = _abi.launch_count()
     tr.train_batch(0, B)
     # the eager path sets the cursor (and, VAE phase, the noise counter) per call; a replay advances the cursor on the device instead
@@ -370,62 +373,72 @@ def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, loca
         kev = None
     tr._graph_probe = kev
     ms, clocks = time_steps(tr, steps, warmup, world, dev, ClockSampler(local) if rank == 0 else None)
-    value = B * world * steps / (ms * 1e-3)
-    kernel_ms = probe_kernel_ms(tr, kev, max(5, min(steps, 30)), 1) if kev else None
-    # sustained leg: >= sustained_s seconds of back-to-back steps (the 1 kW power cap pulls the SM clock down), then kernel samples
-    # taken as the last replay of 50-step groups so that the regime holds
-    sus = None
-    if sustained_s > 0:
-        per = ms / steps
-        n_sus = int(max(steps, sustained_s * 1e3 / per))
-        sampler = ClockSampler(local) if rank == 0 else None
-        if sampler:
-            sampler.start()
-        tr.train_steps(n_sus // 2)                                   # ramp into the power-capped regime
-        barrier(world)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.time()
-        e0.record()
-        tr.train_steps(n_sus)
-        e1.record()
-        barrier(world)
-        t1 = time.time()
-        sms = max_over_ranks(e0.elapsed_time(e1), dev, world)
-        k_sus = probe_kernel_ms(tr, kev, 8, 50) if kev else None
-        sclk = sampler.stop(t0, t1) if sampler else None
-        sus = {"steps": n_sus, "ms_per_step": sms / n_sus, "value": B * world * n_sus / (sms * 1e-3), "kernel_ms_per_step": k_sus, "clocks": sclk}
-    pk, pk_src = peaks()
+    kernel_ms = probe_kernel_ms(tr, kev, max(5, min(steps, 20)), 5) if kev else None
     # not GEMMs: loss finalisation, fused Adam (one per trained net), cursor advance; VAE phase also reparameterisation fwd / bwd
     gemm_launches = launches_per_step - {"world": 3, "vae": 6}[phase]
+    return {"phase": phase, "B": B, "value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "clocks": clocks,
+            "kernel_ms": kernel_ms, "kev": kev, "flops_step": flops_step, "launches_per_step": int(launches_per_step),
+            "gemm_launches": int(gemm_launches), "sustained": None, "config": workload(args, cfg, phase, B, dims), "dims": dims or args.config}
+
+
+def measure_sustained(res, tr, world, rank, dev, local, seconds):
+    """>= `seconds` of back-to-back steps (the 1 kW power cap pulls the SM clock down), then kernel samples taken as the last replay
+    of 50-step groups so that the regime holds."""
+    B, kev = res["B"], res["kev"]
+    per = res["ms_per_step"]
+    n_sus = int(max(res["steps"], seconds * 1e3 / per))
+    sampler = ClockSampler(local) if rank == 0 else None
+    tr.train_steps(n_sus // 2)                                       # ramp into the power-capped regime
+    if sampler:
+        sampler.start()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    tr.train_steps(n_sus)
+    e1.record()
+    barrier(world)
+    t1 = time.time()
+    sms = max_over_ranks(e0.elapsed_time(e1), dev, world)
+    k_sus = probe_kernel_ms(tr, kev, 8, 50) if kev else None
+    res["sustained"] = {"steps": n_sus, "ms_per_step": sms / n_sus, "value": B * world * n_sus / (sms * 1e-3), "kernel_ms_per_step": k_sus,
+                        "clocks": sampler.stop(t0, t1) if sampler else None}
+
+
+def finish_phase(args, res, tr):
+    """Roofline object of a measured phase: fractions against the measured cuBLAS bf16 peak of the matching clock regime."""
+    tr._graph_probe = None
+    pk, pk_src = peaks()
+    kernel_ms, sus, clocks, flops_step = res["kernel_ms"], res["sustained"], res["clocks"], res["flops_step"]
     traffic = None
     try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the same workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s/%s/%d" % (dims or args.config, phase, B)
+        key = "%s/%s/%d" % (res["dims"], res["phase"], res["B"])
         if key in tj:
             traffic = tj[key]["dram_bytes_per_launch"]
     except Exception:
         pass
     roof = None
     if kernel_ms:
+        gl = max(res["gemm_launches"], 1)
         ach = flops_step / (kernel_ms * 1e-3) / 1e12
         ach_s = flops_step / (sus["kernel_ms_per_step"] * 1e-3) / 1e12 if sus and sus.get("kernel_ms_per_step") else None
         burst_regime = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"])
-        roof = {"bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
-                "peak": pk["bf16_tflops"] if burst_regime else pk["bf16_tflops_sustained"],
-                "frac": ach / (pk["bf16_tflops"] if burst_regime else pk["bf16_tflops_sustained"]),
+        peak = pk["bf16_tflops"] if burst_regime else pk["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "achieved": ach, "unit": "TFLOP/s", "peak": peak, "frac": ach / peak,
                 "regime": "burst (median SM clock >= 0.95 max during the timed region)" if burst_regime else "sustained (SM clock below 0.95 max during the timed region)",
                 "frac_burst": ach / pk["bf16_tflops"], "peak_burst": pk["bf16_tflops"],
                 "achieved_sustained": ach_s, "frac_sustained": (ach_s / pk["bf16_tflops_sustained"]) if ach_s else None,
                 "peak_sustained": pk["bf16_tflops_sustained"], "peak_source": pk_src + " (MEASURED_PEAKS.json: cuBLAS bf16 burst / sustained)",
-                "traffic": traffic, "kernel": "pvae_gemm_kernel", "launches_per_step": int(gemm_launches),
-                "avg_launch_ms": kernel_ms / max(gemm_launches, 1), "algorithmic_flops_per_launch": flops_step / max(gemm_launches, 1),
+                "traffic": traffic, "kernel": "pvae_gemm_kernel", "launches_per_step": res["gemm_launches"],
+                "avg_launch_ms": kernel_ms / gl, "algorithmic_flops_per_launch": flops_step / gl,
                 "kernel_ms_per_step": kernel_ms, "algorithmic_flops_per_step": flops_step,
                 "timing": "external CUDA events recorded as nodes of the product's step graph around the engine's launch sequence",
-                "whole_step_tflops": flops_step / (ms / steps * 1e-3) / 1e12}
-    tr._graph_probe = None
-    return {"value": value, "ms_per_step": ms / steps, "steps": steps, "clocks": clocks, "roofline": roof, "sustained": sus,
-            "launches_per_step": int(launches_per_step), "loss_after": float(tr.engine.loss[0].item()),
-            "config": workload(args, cfg, phase, B, dims)}
+                "whole_step_tflops": flops_step / (res["ms_per_step"] * 1e-3) / 1e12}
+    out = {k: res[k] for k in ("value", "ms_per_step", "steps", "clocks", "sustained", "launches_per_step", "config")}
+    out["roofline"] = roof
+    out["loss_after"] = float(tr.engine.loss[0].item())
+    return out
 
 
 def dp_equivalence_check(cfg, world, rank, dev):
@@ -493,17 +506,25 @@ def run_b200(args, cfg):
         errs = dp_equivalence_check(cfg, world, rank, dev)
         dp_check = {"grad_rel_l2_vs_single_rank": errs, "ok": all(v < 1e-5 for v in errs.values())}
 
+    # burst-clock legs of both phases first (a sustained leg leaves the GPU power-capped), then the sustained legs
     tr = make_trainer(cfg, B, args.precision, rank, world, phase=phase)
-    main = measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local, args.sustained_seconds)
-    phases = {}
+    res = {phase: measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local)}
+    trainers = {phase: tr}
     if not args.only_phase:
         other = "vae" if phase == "world" else "world"
-        if other == "vae":
-            phases["vae"] = measure_phase(args, cfg, tr, "vae", B, world, rank, dev, steps, warmup, local, args.sustained_seconds)
-        else:
-            tr2 = make_trainer(cfg, B, args.precision, rank, world, phase="world")
-            phases["world"] = measure_phase(args, cfg, tr2, "world", B, world, rank, dev, steps, warmup, local, args.sustained_seconds)
-            del tr2
+        time.sleep(1.0)
+        trainers[other] = make_trainer(cfg, B, args.precision, rank, world, phase=other)
+        res[other] = measure_phase(args, cfg, trainers[other], other, B, world, rank, dev, steps, warmup, local)
+    if args.sustained_seconds > 0:
+        for ph in res:
+            measure_sustained(res[ph], trainers[ph], world, rank, dev, local, args.sustained_seconds)
+    done = {ph: finish_phase(args, res[ph], trainers[ph]) for ph in res}
+    main = done[phase]
+    phases = {ph: v for ph, v in done.items() if ph != phase}
+    for ph in list(trainers):
+        if ph != phase:
+            del trainers[ph]
+    torch.cuda.empty_cache()
     replicas_identical = replica_checksum(tr, world, dev)
     if dp_check is not None:
         dp_check["replicas_identical_after_timed_steps"] = replicas_identical
@@ -514,10 +535,7 @@ def run_b200(args, cfg):
     # (1) "e2e": every step uploads ITS inputs from pinned host memory and reads the loss back.  The mini-batch travels in the
     #     compact form of the dataset (every state once + per-transition index, TrainModel.compute_loss_episodes): half the bytes
     #     of the expanded x = [s_t | s_{t+1}] the reference's DataLoader hands over.  Double-buffered on a copy stream.
-    if phase == "world" and not tr.world_phase:
-        tr_e = make_trainer(cfg, B, args.precision, rank, world, phase="world")
-    else:
-        tr_e = tr
+    tr_e = tr
     T = 129
     E = (B + T - 2) // (T - 1)
     rng = np.random.default_rng(77 + rank)
@@ -604,8 +622,8 @@ def run_b200(args, cfg):
                                       ("cfg5_wide_131072_global_vae", "wide", "vae", 131072 // 8)):
             c = CONFIGS[cname]
             tc = make_trainer(c, rows, args.precision, rank, world, phase=ph)
-            r_ = measure_phase(args, c, tc, ph, rows, world, rank, dev, kc, 5, local, 0.0, dims=cname)
-            cfgs[name] = {k: r_[k] for k in ("value", "ms_per_step", "steps", "roofline", "config", "launches_per_step")}
+            r_ = finish_phase(args, measure_phase(args, c, tc, ph, rows, world, rank, dev, kc, 5, local, dims=cname), tc)
+            cfgs[name] = {k: r_[k] for k in ("value", "ms_per_step", "steps", "clocks", "roofline", "config", "launches_per_step")}
             del tc
             torch.cuda.empty_cache()
 

@@ -185,6 +185,19 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
                  uint64_t offset, float* act_out_dev, int64_t act_out_ld, float* mu_dev, float* logvar_dev, float* z_dev,
                  float* future_dev, float* value_dev, pvae_stream s);
 
+/* --- data-parallel gradient exchange (the reference is single-process, there is nothing it replaces) ------------------
+ * Averaging all-reduce, in place, of the fp32 range [offset, offset + count) of a SYMMETRIC allocation: the same buffer layout
+ * allocated on every rank of one node and mapped into every peer (torch.distributed._symmetric_memory / CUDA IPC / VMM), its base
+ * address on rank p being peer_ptrs_host[p] (a host array of `world` device addresses as seen from THIS rank).  One kernel: device-side
+ * rank barrier through flags inside the allocation, rank r reduces slice r over NVLink (peer loads, or multimem.ld_reduce when
+ * multicast_ptr != 0) and writes the averaged slice into every rank's copy (peer stores / multimem.st), barrier.  All ranks must call
+ * it the same number of times; every replica ends up with bit-identical values.  The flag block -- pvae_symm_flag_elems() fp32-sized
+ * words at flags_offset inside the same allocation, zeroed on every rank before the first call -- carries the sequence numbers, so the
+ * call is CUDA-graph replayable.  world <= 8. */
+int pvae_symm_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int rank, int world, int64_t offset_elems, int64_t count_elems,
+                        int64_t flags_offset_elems, pvae_stream s);
+int64_t pvae_symm_flag_elems(void);
+
 /* --- kernel-level entry (unit tests, bench roofline) ----------------------------------------------------------- */
 /* D[M][N] (fp32, row-major) = A . B^T on the tcgen05 path.
  *   a_major 0: A is [M][K] row-major (ld K);  1: A is [K][M] row-major (ld M)

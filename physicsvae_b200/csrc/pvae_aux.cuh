@@ -336,6 +336,95 @@ __global__ void f32_to_planes_kernel(const float* __restrict__ src, int64_t src_
   }
 }
 
+// ---- data-parallel gradient exchange over peer memory (NVLink 5 / NVSwitch) ------------------------------------------------------
+// One kernel = barrier + reduce-scatter + all-gather of a contiguous fp32 range that lives at the same offset of a symmetric
+// (peer-mapped) allocation on every rank -- the [gradients | loss slots] range of the model's gradient pool:
+//   1. every CTA b announces itself to CTA b of every peer (flag in the PEER's copy of the pool) and waits for theirs: once a
+//      peer's kernel is running, that peer's weight-gradient kernels have completed (stream order);
+//   2. rank r owns slice r of the range: it loads the slice from every rank (plain loads on the peer pointers, or ONE
+//      multimem.ld_reduce on the multicast address when the pool is multicast-bound: the switch adds), scales by 1 / world and
+//      stores the result into every rank's copy in place (peer stores, or ONE multimem.st) -- a slice is read and written by its
+//      owner only, so in-place is race-free, and because one rank computes each element all replicas end up bit-identical;
+//   3. the same barrier again: every rank's copy is complete before Adam reads it, and nobody's next step clears its
+//      gradients while a peer still reads them.
+// Sequence numbers live in the pool (per CTA, bumped by the kernel itself), so a captured CUDA graph replays it.
+constexpr int AR_CTAS = 64, AR_THREADS = 512, AR_MAX_RANKS = 8;
+struct SymmArgs {
+  float* peer[AR_MAX_RANKS];      // base of the symmetric allocation on every rank (peer-mapped addresses)
+  float* mc;                      // multicast address of the same allocation, or null
+  int32_t rank, world;
+  int64_t off, count;             // the range [off, off + count) in fp32 elements; off and count are multiples of 4
+  int64_t flags_off;              // where the flag block starts (fp32 elements): [AR_CTAS][AR_MAX_RANKS] arrival flags, then [AR_CTAS] sequence counters
+  float scale;
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void symm_barrier(const SymmArgs& a, uint32_t* my_flags, uint32_t seq) {
+  __syncthreads();
+  if ((int)threadIdx.x < a.world) {
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(a.peer[threadIdx.x] + a.flags_off) + blockIdx.x * AR_MAX_RANKS + a.rank;
+    st_release_sys(theirs, seq);
+    const uint32_t* mine = my_flags + blockIdx.x * AR_MAX_RANKS + threadIdx.x;
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
+      if ((++spins & 0x3FFFu) == 0) {                 // bounded: a rank that never arrives must not hang the GPU
+        uint64_t t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 20000000000ull) {            // 20 s
+          printf("pvae symm_allreduce: rank %d CTA %d still waits for rank %d (seq %u)\n", a.rank, (int)blockIdx.x, (int)threadIdx.x, seq);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(AR_THREADS) symm_allreduce_kernel(const SymmArgs a) {
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(a.peer[a.rank] + a.flags_off);
+  uint32_t* ctr = my_flags + AR_CTAS * AR_MAX_RANKS + blockIdx.x;
+  const uint32_t seq = *ctr;
+  symm_barrier(a, my_flags, seq + 1);
+  const int64_t n4 = a.count >> 2;
+  const int64_t per = (n4 + a.world - 1) / a.world;
+  const int64_t lo = (int64_t)a.rank * per, hi = lo + per < n4 ? lo + per : n4;
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = a.off + (i << 2);
+    float4 s;
+    if (a.mc) {
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w) : "l"(a.mc + e) : "memory");
+    } else {
+      s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < AR_MAX_RANKS; ++p) {
+        if (p < a.world) {                              // fixed order 0 .. world-1: the sum does not depend on who computes it
+          float4 v;
+          asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a.peer[p] + e) : "memory");
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+      }
+    }
+    s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
+    if (a.mc) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc + e), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+    } else {
+#pragma unroll
+      for (int p = 0; p < AR_MAX_RANKS; ++p)
+        if (p < a.world)
+          asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.peer[p] + e), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+    }
+  }
+  __threadfence_system();
+  symm_barrier(a, my_flags, seq + 2);
+  if (threadIdx.x == 0) *ctr = seq + 2;
+}
+
 // ---- loss bookkeeping ---------------------------------------------------------------------------------------------
 // acc: [0] sum sq a, [1] sum kl, [2] sum sq s (world), [3] sum sq cyc
 // (the accumulators are cleared here, for the next step: one memset node less per step)

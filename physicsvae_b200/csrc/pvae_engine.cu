@@ -1174,6 +1174,32 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
   return PVAE_OK;
 }
 
+// Averaging all-reduce of a contiguous fp32 range of a symmetric (peer-mapped) allocation, one kernel (pvae_aux.cuh).
+int pvae_symm_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int rank, int world, int64_t offset_elems, int64_t count_elems,
+                        int64_t flags_offset_elems, pvae_stream s) {
+  if (!peer_ptrs_host) return fail(PVAE_ERR_INVALID, "null peer pointer table");
+  if (world < 2 || world > AR_MAX_RANKS || rank < 0 || rank >= world) return fail(PVAE_ERR_INVALID, "rank %d / world %d outside [2, %d]", rank, world, AR_MAX_RANKS);
+  if (offset_elems < 0 || count_elems <= 0 || (offset_elems & 3) || (count_elems & 3) || (flags_offset_elems & 3))
+    return fail(PVAE_ERR_INVALID, "range [%lld, +%lld) / flag block %lld must be multiples of 4 elements", (long long)offset_elems, (long long)count_elems, (long long)flags_offset_elems);
+  if (flags_offset_elems < offset_elems + count_elems && flags_offset_elems + pvae_symm_flag_elems() > offset_elems)
+    return fail(PVAE_ERR_INVALID, "the flag block overlaps the reduced range");
+  SymmArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int p = 0; p < world; ++p) {
+    if (!peer_ptrs_host[p] || (peer_ptrs_host[p] & 15)) return fail(PVAE_ERR_INVALID, "peer pointer %d is null or not 16-byte aligned", p);
+    a.peer[p] = reinterpret_cast<float*>(peer_ptrs_host[p]);
+  }
+  a.mc = reinterpret_cast<float*>(multicast_ptr);
+  a.rank = rank; a.world = world; a.off = offset_elems; a.count = count_elems; a.flags_off = flags_offset_elems;
+  a.scale = 1.f / (float)world;
+  symm_allreduce_kernel<<<AR_CTAS, AR_THREADS, 0, (cudaStream_t)s>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
+int64_t pvae_symm_flag_elems(void) { return (int64_t)AR_CTAS * AR_MAX_RANKS + AR_CTAS; }
+
 // Debug: copy the per-unit clock stamps of the most recent GEMM launches (PVAE_DBG bit 5) to the host; returns the number
 // of 64-bit words written (see g_trace in pvae_gemm.cuh).  Not part of the reference-facing interface.
 int pvae_debug_trace(unsigned long long* out_host, int max_words, int clear) {

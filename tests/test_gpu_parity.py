@@ -422,10 +422,19 @@ def test_cli_main_grid_checkpoints_output_and_resume(tmp_path):
         for c in ("checkpoint_000001", "checkpoint_000002"):
             assert sorted(os.listdir(root / t / c)) == ["model.pt", "model.pth", "motor_decoder.pt", "task_encoder.pt", "trainer_state.pt",
                                                         "world_model.pt"]
-    sd = torch.load(out)
-    assert len(sd) == 26 and all(k.split(".")[0] in ("_task_encoder", "_motor_decoder", "_world_model", "_value_branch") for k in sd)
+    # a sweep with several grid points exports one file per trial (a single path would hold whichever trial finished last)
+    assert not os.path.exists(out)
     ref = torch.load(ck)
-    assert all(torch.equal(sd[k], ref[k]) for k in ref)
+    for t in (0, 1):
+        sd = torch.load(str(tmp_path / ("exported.trial_%05d.pt" % t)))
+        assert len(sd) == 26 and all(k.split(".")[0] in ("_task_encoder", "_motor_decoder", "_world_model", "_value_branch") for k in sd)
+        want = torch.load(str(root / ("trial_%05d" % t) / "checkpoint_000002" / "model.pth"))
+        assert all(torch.equal(sd[k], want[k]) for k in want)
+    # a single grid point keeps the path as given
+    one = str(tmp_path / "single.pt")
+    tp.main(["--data_train", f, "--max_iter_world_model", "1", "--batch_size", "32", "--latent_dim", "4", "--local_dir", str(tmp_path / "results1"),
+             "--name", "one", "--max_iter", "1", "--output", one])
+    assert os.path.exists(one)
     ck3 = tp.main(base + ["--max_iter", "3", "--resume"])
     assert ck3 == str(root / "trial_00001" / "checkpoint_000003" / "model.pth")
     for t in ("trial_00000", "trial_00001"):
