@@ -466,6 +466,17 @@ def dp_equivalence_check(cfg, world, rank, dev):
         t = torch.tensor([err], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[phase] = float(t.item())
+        if parallel.allreduce_kind()["kind"].startswith("symm"):
+            # the library's peer-memory kernel against NCCL on the same rank-dependent data
+            rng = tr.model.reduce_range(phase == "world")
+            rng.copy_(torch.randn(rng.numel(), device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank)))
+            want = rng.detach().clone()
+            dist.all_reduce(want, op=dist.ReduceOp.AVG)
+            parallel.allreduce_avg_([rng])
+            torch.cuda.synchronize()
+            d = torch.tensor([float((rng.double() - want.double()).norm() / want.double().norm())], device=dev, dtype=torch.float64)
+            dist.all_reduce(d, op=dist.ReduceOp.MAX)
+            out[phase + "_peer_kernel_vs_nccl"] = float(d.item())
         del tr
         torch.cuda.empty_cache()
     return out
@@ -504,7 +515,7 @@ def run_b200(args, cfg):
     dp_check = None
     if world > 1:
         errs = dp_equivalence_check(cfg, world, rank, dev)
-        dp_check = {"grad_rel_l2_vs_single_rank": errs, "ok": all(v < 1e-5 for v in errs.values())}
+        dp_check = {"grad_rel_l2_vs_single_rank": errs, "ok": all(v < 1e-5 for v in errs.values())}      # (peer-kernel vs NCCL: < 1e-5 too)
 
     # burst-clock legs of both phases first (a sustained leg leaves the GPU power-capped), then the sustained legs
     tr = make_trainer(cfg, B, args.precision, rank, world, phase=phase)
@@ -641,6 +652,7 @@ def run_b200(args, cfg):
         line.update(extra)
         if cfgs:
             line["configs"] = cfgs
+        line["allreduce"] = parallel.allreduce_kind()
         if dp_check is not None:
             line["dp_check"] = dp_check
         if not args.no_cpu_baseline:

@@ -1,8 +1,18 @@
 """Data-parallel plumbing: the only multi-GPU strategy the path has.  One process per GPU; every
 global mini-batch [lo, hi) is cut into contiguous per-rank row ranges; each rank's loss coefficients are weighted by
-n_rank * R / n so that the AVERAGE of the per-rank gradients (one all-reduce over the flat fp32 gradient buffers) equals
-the gradient of the global mean loss exactly, also for ragged last batches.  torch.distributed (NCCL over NVLink on GPUs,
-gloo in the CPU tests) is plumbing; there is no other collective on the path."""
+n_rank * R / n so that the AVERAGE of the per-rank gradients (ONE all-reduce over the contiguous [gradients | loss slots]
+range of the model's gradient pool) equals the gradient of the global mean loss exactly, also for ragged last batches.
+
+The all-reduce itself: when the ranks share one NVLink / NVSwitch node the gradient pool is a SYMMETRIC allocation
+(torch.distributed._symmetric_memory: the same buffer mapped into every peer) and the exchange is the library's own single
+kernel over peer memory (pvae_symm_allreduce, include/pvae_sm100.h: device-side rank barrier, rank r reduces slice r with peer
+loads -- or multimem.ld_reduce through the switch -- and stores it into every replica).  torch.distributed's NCCL all-reduce
+(gloo in the CPU tests) is the fallback and the parity path (PVAE_SYMM_AR=0); torch.distributed is plumbing -- rendezvous,
+broadcast of the initial parameters, barriers."""
+import ctypes as C
+import os
+import sys
+
 import torch
 import torch.distributed as dist
 
@@ -57,15 +67,106 @@ def shard_weight(lo, hi, r, world):
     return (e - s) * world / float(hi - lo)
 
 
+class SymmetricPool(object):
+    """An fp32 buffer allocated symmetrically on every rank of the node and mapped into every peer, plus the flag block the
+    library's all-reduce kernel synchronises through.  `view` is what the model uses as its gradient pool."""
+
+    def __init__(self, n, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _abi
+        self.lib = _abi.load()
+        group = dist.group.WORLD
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.n = int(n)
+        self.flags_off = (self.n + 3) // 4 * 4
+        total = self.flags_off + int(self.lib.pvae_symm_flag_elems())
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)          # needed by older releases, a deprecated no-op in newer ones
+        except Exception:  # noqa
+            pass
+        self.buf = symm.empty(total, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
+            raise RuntimeError("unexpected symmetric-memory pointer table")
+        self.peer = (C.c_uint64 * self.world)(*ptrs)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.mc = mc if os.environ.get("PVAE_SYMM_MULTIMEM", "0") == "1" else 0       # opt-in: reduce inside the switch (NVLS)
+        self.has_multicast = bool(mc)
+        self.view = self.buf[:self.n]
+        torch.cuda.synchronize(device)
+        dist.barrier()                                 # every rank's flag block is zeroed before anyone can signal into it
+
+    def contains(self, t):
+        b = self.buf.data_ptr()
+        return t.dtype == torch.float32 and b <= t.data_ptr() and t.data_ptr() + t.numel() * 4 <= b + self.flags_off * 4
+
+    def allreduce_avg_(self, t):
+        off = (t.data_ptr() - self.buf.data_ptr()) // 4
+        count = (t.numel() + 3) // 4 * 4               # pieces of the pool are padded to 16 bytes: the tail words are zeros
+        if off % 4 or off + count > self.flags_off:
+            raise ValueError("range is not 16-byte aligned inside the symmetric pool")
+        from . import _abi
+        _abi.check(self.lib.pvae_symm_allreduce(self.peer, self.mc, self.rank, self.world, off, count, self.flags_off,
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+_symm_pools = []
+_symm_note = {"kind": "nccl", "why": "single rank"}
+
+
+def symmetric_pool_factory():
+    """A `grad_pool_factory` for PhysicsVAE (rllib_model_torch.py: _pool_alloc) that hands out symmetric memory, or None when the
+    job cannot use it (one rank, replica mode, not NCCL, more than 8 ranks, PVAE_SYMM_AR=0).  Allocation is collective: every
+    rank of the job builds its model / engine at the same points of the program."""
+    if world_size() == 1 or not dist.is_initialized():
+        return None
+    if os.environ.get("PVAE_SYMM_AR", "1") == "0":
+        _symm_note.update(kind="nccl", why="PVAE_SYMM_AR=0")
+        return None
+    if dist.get_backend() != "nccl" or dist.get_world_size() > 8:
+        _symm_note.update(kind=str(dist.get_backend()), why="symmetric memory needs NCCL ranks on one node (<= 8)")
+        return None
+
+    def factory(n, device):
+        try:
+            pool = SymmetricPool(n, device)
+        except Exception as e:  # noqa  (no peer access / no fabric handle support: every rank fails alike)
+            _symm_note.update(kind="nccl", why="symmetric allocation failed: %s" % repr(e)[:160])
+            if job_rank() == 0:
+                print("[physicsvae_b200] symmetric gradient pool unavailable (%s); using NCCL all-reduce" % repr(e)[:160], file=sys.stderr)
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        _symm_pools[:] = [p for p in _symm_pools if p.buf is not None][-3:] + [pool]      # keep the last few alive (engines get re-created)
+        _symm_note.update(kind="symm-multimem" if pool.mc else "symm-p2p", why="multicast available" if pool.has_multicast else "no multicast binding")
+        return pool.view
+    return factory
+
+
+def allreduce_kind():
+    """What the gradient exchange of this job runs on: "symm-p2p" / "symm-multimem" (the library's own kernel over peer memory),
+    "nccl" / "gloo" (torch.distributed), and why."""
+    return dict(_symm_note)
+
+
+def graph_capturable():
+    """Can a training step with its collective be captured into a CUDA graph?  (gloo synchronises on the host.)"""
+    return world_size() == 1 or dist.get_backend() == "nccl"
+
+
 def allreduce_avg_(tensors, group=None):
     """In-place average of the given flat tensors over all ranks, one collective per tensor.  A training step passes ONE
-    tensor: the contiguous [gradients | loss slots] range of the model's gradient pool."""
+    tensor: the contiguous [gradients | loss slots] range of the model's gradient pool -- exchanged by the library's own
+    peer-memory kernel when that pool is a symmetric allocation, by torch.distributed otherwise."""
     w = world_size()
     if w == 1:
         return
     native_avg = dist.get_backend(group) == "nccl"      # NCCL averages inside the collective; gloo has no AVG
     for t in tensors:
-        if native_avg:
+        pool = next((p for p in reversed(_symm_pools) if p.contains(t)), None) if group is None else None
+        if pool is not None:
+            pool.allreduce_avg_(t)
+        elif native_avg:
             dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)

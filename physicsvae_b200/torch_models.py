@@ -174,6 +174,9 @@ class TrainModel(_TrainableBase):
         self._graphs = {}              # captured full-batch steps, see _graph_step
         self._use_graphs = bool(config.get("cuda_graph", True))
         self._loss_acc = torch.zeros((), device=self.device)
+        # data-parallel ranks on one NVLink node: the gradient pool lives in symmetric (peer-mapped) memory and the exchange is
+        # the library's own kernel (parallel.SymmetricPool); None = plain tensor + torch.distributed
+        self.model.grad_pool_factory = parallel.symmetric_pool_factory()
         eng = self.engine
         lr = config.get("lr", 1e-3)
         if config.get("optimizer", "pvae_adam") == "torch_adam":
@@ -304,7 +307,7 @@ class TrainModel(_TrainableBase):
 
     # ---- captured full-batch step --------------------------------------------------------------------------------------------
     def _graph_ok(self, batch_size):
-        return self._use_graphs and isinstance(self.optimizer, PvaeAdam) and self._graph_supported()
+        return self._use_graphs and isinstance(self.optimizer, PvaeAdam) and self._graph_supported() and parallel.graph_capturable()
 
     def _graph_supported(self):
         return False

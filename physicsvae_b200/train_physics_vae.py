@@ -581,11 +581,13 @@ def init_distributed(sweep_mode="dp"):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1 and not dist.is_initialized():
         local = int(os.environ.get("LOCAL_RANK", "0"))
+        backend = os.environ.get("PVAE_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
+        if backend == "nccl":
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
-            dist.init_process_group("gloo")
+            dist.init_process_group(backend)          # (gloo moves CUDA tensors through the host: tests with several ranks on one GPU)
     parallel.set_replica_mode(sweep_mode == "replicas")
 
 
