@@ -8,6 +8,7 @@
 #include "../../include/pvae_sm100.h"
 #include "pvae_gemm.cuh"
 #include "pvae_aux.cuh"
+#include "pvae_small.cuh"
 
 #include <atomic>
 #include <cstdarg>
@@ -118,6 +119,7 @@ struct Device {
   int snake = 1;          // PVAE_SNAKE=0: every GEMM walks the batch front to back (see batch_direction)
   int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
   int fast_epi = 1;       // PVAE_FAST_EPI=0: never use the lean ReLU store / dgrad epilogue (A/B experiments)
+  int small_fwd = 1;      // PVAE_SMALL_FWD=0: batches <= 16 of the inference API also take the tensor-core path
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
@@ -346,6 +348,7 @@ struct pvae_engine {
   double* acc = nullptr;    // [4] loss accumulators
   bool acc_dirty = false;   // a step was entered but its finalize kernel (which clears acc) was not enqueued
   unsigned int* adam_counter = nullptr;   // finished-blocks counter of adam_net_kernel
+  float* small_scratch = nullptr;            // fp32 [2][16][SMALL_SCRATCH_COLS]: z and action rows between the chains of the small-batch forward
   unsigned long long* noise_ctr = nullptr;   // device-side Philox offset counter (pvae_noise_counter)
   bool noise_auto = false;
   unsigned long long noise_stride = 1;
@@ -532,6 +535,45 @@ static int check_trainable_acts(const Net& net) {
   return PVAE_OK;
 }
 
+constexpr int SMALL_SCRATCH_COLS = 4096;
+
+// ---- latency path: one cluster kernel per FC stack for <= 16 rows (pvae_small.cuh) ------------------------------------------------
+// in0 / in1: fp32 rows of the two layer-0 input segments (in1 may be null when the net has one segment)
+static bool small_ok(const pvae_engine* h, const Net& net, int batch) {
+  if (!h->dev.small_fwd || batch > SF_MAX_ROWS || net.n_layers > SF_MAX_LAYERS) return false;
+  int width = 0;
+  for (int l = 0; l < net.n_layers; ++l) { width = net.kpad[l] > width ? net.kpad[l] : width; width = net.out_dims[l] > width ? net.out_dims[l] : width; }
+  int bt = 1; while (bt < batch) bt <<= 1;
+  return (size_t)2 * bt * rup(width, 8) * sizeof(float) <= 200 * 1024;
+}
+static int small_chain(pvae_engine* h, Net& net, int batch, const float* in0, int64_t in0_ld, const float* in1, int64_t in1_ld, float* out,
+                       int64_t out_ld, cudaStream_t st) {
+  if (!net.bound) return fail(PVAE_ERR_STATE, "net not bound (pvae_bind_net)");
+  SmallNet sn;
+  memset(&sn, 0, sizeof(sn));
+  sn.n_layers = net.n_layers; sn.planes = h->planes;
+  sn.k0 = net.k0; sn.k1 = net.k1; sn.K0pad = net.K0pad;
+  int width = 0;
+  for (int l = 0; l < net.n_layers; ++l) {
+    sn.L[l].W = net.Wsh[l]; sn.L[l].ps = net.wsh_ps[l]; sn.L[l].bias = net.b[l];
+    sn.L[l].out = net.out_dims[l]; sn.L[l].kpad = net.kpad[l]; sn.L[l].act = net.acts[l];
+    width = net.kpad[l] > width ? net.kpad[l] : width;
+    width = net.out_dims[l] > width ? net.out_dims[l] : width;
+  }
+  sn.width = rup(width, 8);
+  int bt = 1; while (bt < batch) bt <<= 1;
+  const size_t smem = (size_t)2 * bt * sn.width * sizeof(float);
+  void (*fn)(const SmallNet, const float*, int64_t, const float*, int64_t, int, float*, int64_t) =
+      bt == 1 ? small_fc_kernel<1> : bt == 2 ? small_fc_kernel<2> : bt == 4 ? small_fc_kernel<4> : bt == 8 ? small_fc_kernel<8> : small_fc_kernel<16>;
+  static bool attr_done[5] = {false, false, false, false, false};
+  const int ai = bt == 1 ? 0 : bt == 2 ? 1 : bt == 4 ? 2 : bt == 8 ? 3 : 4;
+  if (!attr_done[ai]) { CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[ai] = true; }
+  fn<<<SF_CLUSTER, SF_THREADS, smem, st>>>(sn, in0, in0_ld, in1, in1_ld, batch, out, out_ld);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
 static int grid_for(int64_t total, int threads, int sms) {
   int64_t g = (total + threads - 1) / threads;
   const int64_t cap = (int64_t)sms * 8;
@@ -591,6 +633,8 @@ static int init_device(Device& dev, int device) {
   if (env) dev.cs_mma = atoi(env) != 0;
   env = getenv("PVAE_FAST_EPI");
   if (env) dev.fast_epi = atoi(env) != 0;
+  env = getenv("PVAE_SMALL_FWD");
+  if (env) dev.small_fwd = atoi(env) != 0;
   env = getenv("PVAE_CLUSTER");
   if (env) dev.cluster = atoi(env) == 1 ? 1 : 2;
   CKR(resolve_driver());
@@ -683,6 +727,7 @@ int pvae_create(pvae_handle* out, const pvae_model_desc* desc, int device) {
   }
   if (cudaMalloc(&h->adam_counter, sizeof(unsigned int)) == cudaSuccess) cudaMemset(h->adam_counter, 0, sizeof(unsigned int));
   else h->adam_counter = nullptr;
+  if (cudaMalloc(&h->small_scratch, 2 * SF_MAX_ROWS * SMALL_SCRATCH_COLS * sizeof(float)) != cudaSuccess) h->small_scratch = nullptr;
   if (cudaMalloc(&h->noise_ctr, sizeof(unsigned long long)) == cudaSuccess) cudaMemset(h->noise_ctr, 0, sizeof(unsigned long long));
   else h->noise_ctr = nullptr;
   cudaMemset(h->dev.cursor, 0, sizeof(int32_t));
@@ -700,6 +745,7 @@ int pvae_destroy(pvae_handle h) {
   if (h->acc) cudaFree(h->acc);
   if (h->adam_counter) cudaFree(h->adam_counter);
   if (h->noise_ctr) cudaFree(h->noise_ctr);
+  if (h->small_scratch) cudaFree(h->small_scratch);
   if (h->dev.cursor) cudaFree(h->dev.cursor);
   delete h;
   return PVAE_OK;
@@ -1079,6 +1125,8 @@ int pvae_fc_forward(pvae_handle h, int net_id, int batch, const float* in_dev, i
   const int out_w = net.out_dims[net.n_layers - 1];
   if (in_ld < net.in_dim || out_ld < out_w) return fail(PVAE_ERR_INVALID, "row strides %lld / %lld too small for %d -> %d", (long long)in_ld, (long long)out_ld, net.in_dim, out_w);
   cudaStream_t st = (cudaStream_t)s;
+  if (small_ok(h, net, batch))                // a handful of rows: one cluster kernel for the whole stack
+    return small_chain(h, net, batch, in_dev, in_ld, net.k1 ? in_dev + net.k0 : nullptr, in_ld, out_dev, out_ld, st);
   const int p0 = rup(net.k0, 64);            // second input segment starts on a 128-byte boundary of the staging row
   {
     const int64_t total = (int64_t)batch * h->x_ld;
@@ -1110,6 +1158,55 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
   const bool enc = parts & PVAE_PART_ENCODER, dec = parts & PVAE_PART_DECODER, wld = parts & PVAE_PART_WORLD, val = parts & PVAE_PART_VALUE;
   const int obs_w = (enc || val) ? 2 * h->dsb : h->dsb;
   if (obs_ld < obs_w) return fail(PVAE_ERR_INVALID, "obs row stride %lld < %d", (long long)obs_ld, obs_w);
+  {
+    // ---- latency path (batch <= 16): one cluster kernel per FC stack straight from / to the caller's fp32 rows -- at most four
+    //      chain launches + the reparameterisation kernel for a full forward, ONE launch for the runtime's decoder pass-through
+    bool small = h->small_scratch != nullptr && h->z <= SMALL_SCRATCH_COLS && h->da <= SMALL_SCRATCH_COLS;
+    for (int n = 0; n < PVAE_NUM_NETS && small; ++n) {
+      const bool used = (n == PVAE_NET_TASK_ENCODER && enc) || (n == PVAE_NET_MOTOR_DECODER && dec) || (n == PVAE_NET_WORLD_MODEL && wld) ||
+                        (n == PVAE_NET_VALUE_BRANCH && val);
+      if (used && (h->nets[n].n_layers == 0 || !small_ok(h, h->nets[n], batch))) small = false;
+    }
+    if (small) {
+      float* z_rows = h->small_scratch;                                          // [16][z]
+      float* a_rows = h->small_scratch + SF_MAX_ROWS * SMALL_SCRATCH_COLS;      // [16][da]
+      const float* z_src = z_in_dev;
+      int64_t z_ld = z;
+      if (enc) {
+        Net& te = h->nets[PVAE_NET_TASK_ENCODER];
+        CKR(small_chain(h, te, batch, obs_dev, obs_ld, obs_dev + h->dsb, obs_ld, h->ml, h->te_out, st));
+        const int prior = h->desc.latent_prior;
+        float* zf = z_dev ? z_dev : z_rows;
+        reparam_fwd_kernel<<<grid_for((int64_t)batch * z, 256, h->dev.sms), 256, 0, st>>>(h->ml, eps_dev, h->eps, prior, prior && noise, seed, offset, batch, z,
+                                                                                          h->zb, h->zb_ld, plane_elems(h, h->zb_ld), h->planes, zf, mu_dev,
+                                                                                          prior ? logvar_dev : nullptr, nullptr, nullptr);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        z_src = zf;
+      } else if (dec && !z_in_dev) {
+        return fail(PVAE_ERR_INVALID, "decoder without encoder needs z_in_dev");
+      }
+      const float* a_src = act_in_dev;
+      int64_t a_ld = act_in_ld;
+      if (dec) {
+        float* af = act_out_dev ? act_out_dev : a_rows;
+        const int64_t af_ld = act_out_dev ? act_out_ld : h->da;
+        CKR(small_chain(h, h->nets[PVAE_NET_MOTOR_DECODER], batch, obs_dev, obs_ld, z_src, z_ld, af, af_ld, st));
+        a_src = af; a_ld = af_ld;
+      } else if (wld && !act_in_dev) {
+        return fail(PVAE_ERR_INVALID, "world model without decoder needs act_in_dev");
+      }
+      if (wld) {
+        if (!future_dev) return fail(PVAE_ERR_INVALID, "world part needs future_dev");
+        CKR(small_chain(h, h->nets[PVAE_NET_WORLD_MODEL], batch, obs_dev, obs_ld, a_src, a_ld, future_dev, h->dsb, st));
+      }
+      if (val) {
+        if (!value_dev) return fail(PVAE_ERR_INVALID, "value part needs value_dev");
+        CKR(small_chain(h, h->nets[PVAE_NET_VALUE_BRANCH], batch, obs_dev, obs_ld, obs_dev + h->dsb, obs_ld, value_dev, 1, st));
+      }
+      CK(cudaGetLastError());
+      return PVAE_OK;
+    }
+  }
   {
     const int64_t total = (int64_t)batch * h->x_ld;
     f32_to_planes_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(obs_dev, obs_ld, obs_w, h->dsb, h->dsbp, h->xin, h->x_ld, plane_elems(h, h->x_ld), h->planes, batch);

@@ -1,0 +1,178 @@
+// pvae_small.cuh -- latency path of the inference API: a whole FC stack (rllib_model_torch.FC.forward,
+// rllib_model_torch.py:274-275) for a handful of rows in ONE kernel.
+//
+// The runtime consumer of the model calls it with batch 1 (envs/rllib_env_imitation.py:234-264: decoder pass-through per control
+// step); a tcgen05 tile is 128 rows tall, so for <= 16 rows the tensor-core path is pure launch latency (15 launches, 82 us at
+// batch 1 in round 1).  Here one thread-block CLUSTER of 8 CTAs runs the net layer by layer:
+//   * every CTA keeps the full activation vector of every row in its shared memory;
+//   * CTA r computes output neurons [r * out / 8, (r + 1) * out / 8) of the layer -- a warp per neuron, lanes stride the K dimension
+//     with 16-byte loads of the bf16 shadow weights (1.3 MB for the decoder: L2-resident between control steps), fp32 accumulate,
+//     shuffle reduction -- and writes the results into the shared memory of ALL eight CTAs (distributed shared memory,
+//     st.shared::cluster);
+//   * one cluster barrier per layer.
+// Weights are read exactly once per call, split eight ways; nothing but the final output touches global memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace pvae {
+
+constexpr int SF_CLUSTER = 8, SF_THREADS = 256, SF_MAX_ROWS = 16, SF_MAX_LAYERS = 8;
+
+struct SmallLayer {
+  const __nv_bfloat16* W;      // shadow operand [plane][out][kpad]
+  int64_t ps;                  // plane stride (elements)
+  const float* bias;
+  int32_t out, kpad, act, pad;
+};
+struct SmallNet {
+  SmallLayer L[SF_MAX_LAYERS];
+  int32_t n_layers, planes;
+  int32_t k0, k1, K0pad;       // layer-0 input segments in shadow-column order: [0, k0) <- in0, [K0pad, K0pad + k1) <- in1
+  int32_t width;               // shared-memory row stride (floats): max over layers of kpad / out, multiple of 8
+};
+
+__device__ __forceinline__ float small_act(int act, float v) {
+  switch (act) {
+    case 1: return fmaxf(v, 0.f);
+    case 2: return tanhf(v);
+    case 3: return 1.f / (1.f + __expf(-v));
+    case 4: return v > 0.f ? v : expm1f(v);
+    case 5: return v / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+__device__ __forceinline__ uint32_t small_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void small_st_cluster(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void small_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// BT: rows computed (a power of two >= the batch; missing rows are zero rows of shared memory)
+template <int BT>
+__global__ void __cluster_dims__(SF_CLUSTER, 1, 1) __launch_bounds__(SF_THREADS, 1)
+small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_ld, const float* __restrict__ in1, int64_t in1_ld, int B,
+                float* __restrict__ out, int64_t out_ld) {
+  extern __shared__ float sf_smem[];
+  const int width = net.width;
+  float* buf[2] = {sf_smem, sf_smem + BT * width};
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // stage the input rows in shadow-column order (every CTA its own copy); in bf16 mode round like the tensor-core path does
+  for (int i = threadIdx.x; i < BT * width; i += SF_THREADS) {
+    const int b = i / width, c = i - b * width;
+    float v = 0.f;
+    if (b < B) {
+      if (c < net.k0) v = in0[(int64_t)b * in0_ld + c];
+      else if (c >= net.K0pad && c < net.K0pad + net.k1) v = in1[(int64_t)b * in1_ld + (c - net.K0pad)];
+      if (net.planes == 1) v = __bfloat162float(__float2bfloat16_rn(v));
+    }
+    buf[0][i] = v;
+    buf[1][i] = 0.f;
+  }
+  small_cluster_sync();          // (also: every CTA of the cluster is running before anyone writes into its shared memory)
+  int cur = 0;
+  for (int l = 0; l < net.n_layers; ++l) {
+    const SmallLayer& L = net.L[l];
+    const bool last = l == net.n_layers - 1;
+    const int per = (L.out + SF_CLUSTER - 1) / SF_CLUSTER;
+    const int n_lo = crank * per, n_hi = min(n_lo + per, L.out);
+    const float* x = buf[cur];
+    const uint32_t nxt_base = (uint32_t)__cvta_generic_to_shared(buf[cur ^ 1]);
+    // a warp works on NPW neurons at a time (their weight loads are in flight together: the loop is L2-latency bound at batch 1)
+    constexpr int NPW = BT <= 4 ? 4 : 2, NW = SF_THREADS / 32;
+    for (int n0 = n_lo + warp; n0 < n_hi; n0 += NW * NPW) {
+      float acc[NPW][BT];
+#pragma unroll
+      for (int j = 0; j < NPW; ++j)
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[j][b] = 0.f;
+      for (int k = lane * 8; k < L.kpad; k += 256) {        // kpad is a multiple of 64: whole 16-byte pieces
+        uint4 q[NPW], q2[NPW];
+#pragma unroll
+        for (int j = 0; j < NPW; ++j) {
+          const int n = n0 + j * NW;
+          const __nv_bfloat16* wrow = L.W + (int64_t)(n < n_hi ? n : n_lo) * L.kpad + k;
+          q[j] = __ldg(reinterpret_cast<const uint4*>(wrow));
+          if (net.planes > 1) q2[j] = __ldg(reinterpret_cast<const uint4*>(wrow + L.ps));
+        }
+        float xv[BT][8];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+          const float4 x0 = *reinterpret_cast<const float4*>(x + b * width + k);
+          const float4 x1 = *reinterpret_cast<const float4*>(x + b * width + k + 4);
+          xv[b][0] = x0.x; xv[b][1] = x0.y; xv[b][2] = x0.z; xv[b][3] = x0.w; xv[b][4] = x1.x; xv[b][5] = x1.y; xv[b][6] = x1.z; xv[b][7] = x1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < NPW; ++j) {
+          float w[8];
+          const uint32_t qw[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { w[2 * t] = __uint_as_float(qw[t] << 16); w[2 * t + 1] = __uint_as_float(qw[t] & 0xFFFF0000u); }
+          if (net.planes > 1) {
+            const uint32_t q2w[4] = {q2[j].x, q2[j].y, q2[j].z, q2[j].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { w[2 * t] += __uint_as_float(q2w[t] << 16); w[2 * t + 1] += __uint_as_float(q2w[t] & 0xFFFF0000u); }
+          }
+#pragma unroll
+          for (int b = 0; b < BT; ++b) {
+            float a = acc[j][b];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) a = fmaf(w[t], xv[b][t], a);
+            acc[j][b] = a;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) {
+        const int n = n0 + j * NW;
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+          float a = acc[j][b];
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+          acc[j][b] = a;
+        }
+        if (n < n_hi) {                                      // warp-uniform
+          const float bias = L.bias ? __ldg(L.bias + n) : 0.f;
+#pragma unroll
+          for (int b = 0; b < BT; ++b) {
+            float v = small_act(L.act, acc[j][b] + bias);
+            if (last) {
+              if (lane == 0 && b < B) out[(int64_t)b * out_ld + n] = v;
+            } else {
+              if (net.planes == 1) v = __bfloat162float(__float2bfloat16_rn(v));
+              if (lane < SF_CLUSTER) small_st_cluster(small_mapa(nxt_base + (uint32_t)(b * width + n) * 4u, (uint32_t)lane), v);
+            }
+          }
+        }
+      }
+    }
+    if (!last) {
+      // columns [out, kpad_next) of the next input must read as zero: buffers start zeroed and a layer only ever writes [0, out);
+      // the buffer being recycled held the previous layer's INPUT, whose tail beyond this layer's out may be stale -> clear it
+      small_cluster_sync();
+      const int next_k = net.L[l + 1].kpad;
+      float* old = buf[cur];
+      const int prev_w = (l == 0) ? net.L[0].kpad : net.L[l].kpad;
+      (void)next_k;
+      for (int i = threadIdx.x; i < BT * prev_w; i += SF_THREADS) {
+        const int b = i / prev_w, c = i - b * prev_w;
+        old[b * width + c] = 0.f;
+      }
+      cur ^= 1;
+      small_cluster_sync();      // nobody starts writing layer l + 1's outputs into a buffer that a peer is still clearing
+    }
+  }
+}
+
+}  // namespace pvae

@@ -437,6 +437,10 @@ class TrainModel(torch_models.TrainModel):
     def _graph_prepare(self, batch_size):
         for name in self._nets():
             self.optimizer._net_state(name)              # Adam moments exist before the capture (no allocation inside it)
+        if not self.world_phase:
+            # the device-side noise counter must be ON while the step is captured: the library decides at launch time whether the
+            # reparameterisation kernel reads it (and the finalisation kernel bumps it)
+            self.engine.noise_counter(True, (self._noise_step + 1) * parallel.world_size(), parallel.world_size())
 
     def _graph_body(self, batch_size):
         _, n, w = self._shard(0, batch_size)
