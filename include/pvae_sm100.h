@@ -153,6 +153,20 @@ int pvae_world_step(pvae_handle h, int batch, float s_coeff, float* loss_dev, pv
 int pvae_vae_step(pvae_handle h, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
                   float kl_coeff, float cyc_coeff, float* loss_dev, pvae_stream s);
 
+/* compute_loss with lookahead L > 1 (train_physics_vae.py:361-435): an autoregressive rollout.  Step t runs the whole model on
+ * (s1_t, s2_gt_t) with s1_0 from the data and s1_{t+1} = the world model's prediction from the decoded action of step t (:421); the loss
+ * terms are means over the L steps (:423-428); gradients flow through time (every net is differentiated w.r.t. its body-state
+ * input).  phase 0: coefficients (a, kl, s, cyc) = (0, 0, s_coeff, 0), gradients for the world model; phase 1: (a, kl, 0, cyc),
+ * gradients for encoder + decoder.  tbufs_host: host array of L resident transition buffers (pvae_ingest of X[:, t, :], Y[:, t, :]),
+ * all of buf_rows rows; the mini-batch is rows [cursor, cursor + batch) of each.  eps_dev: [L][batch][z] or NULL (Philox, offset + t).
+ * Needs 2 * L copies of the workspace (pvae_rollout_workspace_bytes / pvae_bind_rollout_workspace): one per step, and in phase 0 one
+ * more per step for the second world-model pass (on the ground-truth action, :412-414). */
+int pvae_rollout_workspace_bytes(pvae_handle h, int lookahead, size_t* bytes);
+int pvae_bind_rollout_workspace(pvae_handle h, void* ws_dev, size_t bytes, int lookahead);
+int pvae_rollout_step(pvae_handle h, int phase, int batch, int lookahead, const void* const* tbufs_host, int64_t buf_rows, const float* eps_dev,
+                      uint64_t seed, uint64_t offset, int noise, float a_coeff, float kl_coeff, float s_coeff, float cyc_coeff, float* loss_dev,
+                      pvae_stream s);
+
 /* Forward + loss only (no gradients are touched): the test pass of the reference, `with torch.no_grad(): compute_test_loss`
  * (torch_models.py:147-155).  phase 0: world model, loss = s_coeff * MSE(s2, WM(cat[s1, a_gt])); phase 1: the VAE loss with the
  * arguments of pvae_vae_step.  loss_dev as for the step functions. */

@@ -430,13 +430,16 @@ __global__ void __launch_bounds__(AR_THREADS) symm_allreduce_kernel(const SymmAr
 // (the accumulators are cleared here, for the next step: one memset node less per step)
 __global__ void finalize_loss_kernel(double* __restrict__ acc, float* __restrict__ loss, int B, int da, int dsb,
                                      float a_c, float kl_c, float s_c, float cyc_c, unsigned long long* __restrict__ noise_ctr,
-                                     unsigned long long noise_stride) {
+                                     unsigned long long noise_stride, int steps = 1) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (noise_ctr) *noise_ctr += noise_stride;
-    const float la = (float)(acc[0] / ((double)B * da));
-    const float lk = (float)(acc[1] / (double)B);
-    const float ls = (float)(acc[2] / ((double)B * dsb));
-    const float lc = (float)(acc[3] / ((double)B * dsb));
+    // `steps` > 1: the accumulators hold the sums over the steps of an autoregressive rollout, the loss terms are their means
+    // over the steps (train_physics_vae.py:423-428)
+    const double inv = 1.0 / (double)steps;
+    const float la = (float)(acc[0] * inv / ((double)B * da));
+    const float lk = (float)(acc[1] * inv / (double)B);
+    const float ls = (float)(acc[2] * inv / ((double)B * dsb));
+    const float lc = (float)(acc[3] * inv / ((double)B * dsb));
     loss[1] = la; loss[2] = lk; loss[3] = ls; loss[4] = lc;
     loss[0] = a_c * la + kl_c * lk + s_c * ls + cyc_c * lc;
     acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; acc[3] = 0.0;

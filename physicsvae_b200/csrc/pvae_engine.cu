@@ -340,6 +340,10 @@ struct pvae_engine {
   __nv_bfloat16* ga = nullptr;
   __nv_bfloat16* xin = nullptr;   int x_ld = 0;
   __nv_bfloat16* ain = nullptr;
+  __nv_bfloat16* fut = nullptr;   int f_ld = 0;      // predicted next state of a rollout step (the next step's body state), bf16 planes
+  // rollout (lookahead > 1): `roll_slots` copies of the workspace, one per (step, world-model pass)
+  uint8_t* roll_ws = nullptr;
+  int roll_slots = 0;
   // transitions
   const __nv_bfloat16* tbuf = nullptr;
   int64_t tbuf_rows = 0;
@@ -392,6 +396,8 @@ static size_t carve(pvae_engine* h, uint8_t* base) {
   h->ga = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
   h->xin = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->x_ld * 2));
   h->ain = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->a_ld * 2));
+  h->f_ld = rup(h->dsb, 64);
+  h->fut = reinterpret_cast<__nv_bfloat16*>(take((size_t)h->planes * B * h->f_ld * 2));
   return off;
 }
 
@@ -468,7 +474,9 @@ static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, con
 // ---- backward through one FC stack: g[L-1] (gradient w.r.t. the output layer's pre-activation) is already in place ---
 // train: accumulate dW / db into the bound gradient buffer.  in_epi: if non-null, also produce the gradient w.r.t. the
 // SECOND input segment of layer 0 (z for the decoder, the action for the world model) with this epilogue.
-static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bool train, const EpiParams* in_epi, cudaStream_t st) {
+// in0_epi: likewise for the FIRST input segment (the body state: autoregressive rollouts differentiate through it).
+static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bool train, const EpiParams* in_epi, cudaStream_t st,
+                        const EpiParams* in0_epi = nullptr) {
   const int L = net.n_layers;
   if (train && !net.grad) return fail(PVAE_ERR_STATE, "net has no gradient buffer bound");
   for (int l = L - 1; l >= 0; --l) {
@@ -525,6 +533,17 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
       d.epi = *in_epi;
       CKR(launch_gemm(h->dev, d, st));
     }
+    if (l == 0 && in0_epi) {
+      GemmDesc d;
+      d.a_major = MAJOR_K; d.b_major = MAJOR_MN;
+      d.A[0] = gl; d.K[0] = net.out_dims[0];
+      d.B = shadow_view(h, net, 0);
+      d.b_n0 = 0;
+      d.M = batch; d.N = net.k0;
+      d.passes = h->passes;
+      d.epi = *in0_epi;
+      CKR(launch_gemm(h->dev, d, st));
+    }
   }
   return PVAE_OK;
 }
@@ -540,11 +559,12 @@ constexpr int SMALL_SCRATCH_COLS = 4096;
 // ---- latency path: one cluster kernel per FC stack for <= 16 rows (pvae_small.cuh) ------------------------------------------------
 // in0 / in1: fp32 rows of the two layer-0 input segments (in1 may be null when the net has one segment)
 static bool small_ok(const pvae_engine* h, const Net& net, int batch) {
-  if (!h->dev.small_fwd || batch > SF_MAX_ROWS || net.n_layers > SF_MAX_LAYERS) return false;
+  // (measured: past 4 rows the CUDA-core dot products lose to the 26 us tensor-core path -- every weight piece needs one shared-memory read per row)
+  if (!h->dev.small_fwd || batch > SF_SMALL_ROWS || net.n_layers > SF_MAX_LAYERS) return false;
   int width = 0;
   for (int l = 0; l < net.n_layers; ++l) { width = net.kpad[l] > width ? net.kpad[l] : width; width = net.out_dims[l] > width ? net.out_dims[l] : width; }
   int bt = 1; while (bt < batch) bt <<= 1;
-  return (size_t)2 * bt * rup(width, 8) * sizeof(float) <= 200 * 1024;
+  return (size_t)2 * bt * rup(width, 32) * sizeof(float) <= 200 * 1024;
 }
 static int small_chain(pvae_engine* h, Net& net, int batch, const float* in0, int64_t in0_ld, const float* in1, int64_t in1_ld, float* out,
                        int64_t out_ld, cudaStream_t st) {
@@ -560,13 +580,13 @@ static int small_chain(pvae_engine* h, Net& net, int batch, const float* in0, in
     width = net.kpad[l] > width ? net.kpad[l] : width;
     width = net.out_dims[l] > width ? net.out_dims[l] : width;
   }
-  sn.width = rup(width, 8);
+  sn.width = rup(width, 32);
   int bt = 1; while (bt < batch) bt <<= 1;
   const size_t smem = (size_t)2 * bt * sn.width * sizeof(float);
   void (*fn)(const SmallNet, const float*, int64_t, const float*, int64_t, int, float*, int64_t) =
-      bt == 1 ? small_fc_kernel<1> : bt == 2 ? small_fc_kernel<2> : bt == 4 ? small_fc_kernel<4> : bt == 8 ? small_fc_kernel<8> : small_fc_kernel<16>;
-  static bool attr_done[5] = {false, false, false, false, false};
-  const int ai = bt == 1 ? 0 : bt == 2 ? 1 : bt == 4 ? 2 : bt == 8 ? 3 : 4;
+      bt == 1 ? small_fc_kernel<1> : bt == 2 ? small_fc_kernel<2> : small_fc_kernel<4>;
+  static bool attr_done[3] = {false, false, false};
+  const int ai = bt == 1 ? 0 : bt == 2 ? 1 : 2;
   if (!attr_done[ai]) { CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[ai] = true; }
   fn<<<SF_CLUSTER, SF_THREADS, smem, st>>>(sn, in0, in0_ld, in1, in1_ld, batch, out, out_ld);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1102,6 +1122,193 @@ int pvae_eval_loss(pvae_handle h, int phase, int batch, const float* eps_dev, ui
   if (phase == 0) return world_impl(h, batch, s_coeff, loss_dev, s, false);
   if (phase == 1) return vae_impl(h, batch, eps_dev, seed, offset, noise, a_coeff, kl_coeff, cyc_coeff, loss_dev, s, false);
   return fail(PVAE_ERR_INVALID, "phase must be 0 (world model) or 1 (VAE)");
+}
+
+// ---- autoregressive rollout: compute_loss with lookahead L > 1 (train_physics_vae.py:361-435) ------------------------------------------
+// Step t runs the FULL model on (s1_t, s2_gt_t) where s1_0 is data and s1_{t+1} is the world model's prediction from the DECODED action
+// of step t (`s1 = self.model._cur_future_state`, :421); the four loss terms are averaged over the steps (:423-428).  Gradients flow
+// through time: every net is differentiated w.r.t. its body-state input segment as well, and those gradients are accumulated -- in
+// place, by the dgrad epilogue's addend -- into the output gradient of the previous step's world-model pass.  Every step keeps its own
+// copy of the workspace (activations, masks, mu | logvar, eps, z, decoded action, predicted state); the world phase needs a second
+// world-model pass per step (on the ground-truth action, :412-414) which lives in slots L .. 2L-1.
+int pvae_rollout_workspace_bytes(pvae_handle h, int lookahead, size_t* bytes) {
+  if (!h || !bytes || lookahead < 1) return fail(PVAE_ERR_INVALID, "bad argument");
+  *bytes = (size_t)2 * lookahead * h->ws_bytes;
+  return PVAE_OK;
+}
+
+int pvae_bind_rollout_workspace(pvae_handle h, void* ws_dev, size_t bytes, int lookahead) {
+  if (!h || !ws_dev || lookahead < 1) return fail(PVAE_ERR_INVALID, "bad argument");
+  if (bytes < (size_t)2 * lookahead * h->ws_bytes) return fail(PVAE_ERR_INVALID, "rollout workspace too small: %zu < %zu", bytes, (size_t)2 * lookahead * h->ws_bytes);
+  if ((reinterpret_cast<uintptr_t>(ws_dev) & 1023) != 0) return fail(PVAE_ERR_INVALID, "workspace must be 1024-byte aligned");
+  h->roll_ws = reinterpret_cast<uint8_t*>(ws_dev);
+  h->roll_slots = 2 * lookahead;
+  return PVAE_OK;
+}
+
+static int rollout_impl(pvae_handle h, int phase, int batch, int L, const void* const* tbufs, int64_t buf_rows, const float* eps_dev,
+                        uint64_t seed, uint64_t offset, int noise, float a_coeff, float kl_coeff, float s_coeff, float cyc_coeff,
+                        float* loss_dev, cudaStream_t st) {
+  Net& te = h->nets[PVAE_NET_TASK_ENCODER];
+  Net& md = h->nets[PVAE_NET_MOTOR_DECODER];
+  Net& wm = h->nets[PVAE_NET_WORLD_MODEL];
+  const bool world = phase == 0;
+  const bool train_wm = world, train_vae = !world;
+  const int prior = h->desc.latent_prior;
+  const int z = h->z, Lte = te.n_layers, Lmd = md.n_layers, Lwm = wm.n_layers;
+  const float invL = 1.f / (float)L;
+  if (world) { a_coeff = 0.f; kl_coeff = 0.f; cyc_coeff = 0.f; } else { s_coeff = 0.f; }
+  if (train_wm) CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
+  if (train_vae) {
+    CK(cudaMemsetAsync(te.grad, 0, te.grad_elems * sizeof(float), st));
+    CK(cudaMemsetAsync(md.grad, 0, md.grad_elems * sizeof(float), st));
+  }
+  if (h->acc_dirty) CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));
+  h->acc_dirty = true;
+  auto use_slot = [&](int s_) { carve(h, h->roll_ws + (size_t)s_ * h->ws_bytes); };
+  auto bind_t = [&](int t) { h->tbuf = reinterpret_cast<const __nv_bfloat16*>(tbufs[t]); h->tbuf_rows = buf_rows; };
+  // per-step pointers that another step needs: the predicted state (next step's body-state input) and the output gradient of the
+  // cycle pass's world model (where the next step's body-state gradients are accumulated)
+  std::vector<__nv_bfloat16*> fut(L), wm_glast(L);
+  for (int t = 0; t < L; ++t) { use_slot(t); fut[t] = h->fut; wm_glast[t] = wm.g[Lwm - 1]; }
+  auto s1_view = [&](int t) {        // body state of step t: data for t = 0, the previous step's prediction afterwards
+    return t == 0 ? tx_view(h, 0, h->dsb) : ws_view(h, fut[t - 1], h->f_ld, h->dsb, batch);
+  };
+  EpiParams e;
+  // ------------------------------------------------ forward, t = 0 .. L-1 ------------------------------------------------
+  for (int t = 0; t < L; ++t) {
+    use_slot(t);
+    bind_t(t);
+    NetIO te_in; te_in.nseg = 2; te_in.seg[0] = s1_view(t); te_in.seg[1] = tx_view(h, h->dsbp, h->dsb);
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_STORE; e.out_f32 = h->ml; e.f32_sm = h->te_out; e.f32_sn = 1;
+    CKR(net_forward(h, te, te_in, batch, e, st, true));
+    {
+      const int64_t total = (int64_t)batch * z;
+      reparam_fwd_kernel<<<grid_for(total, 256, h->dev.sms), 256, 0, st>>>(h->ml, eps_dev ? eps_dev + (int64_t)t * batch * z : nullptr, h->eps, prior,
+                                                                           prior && noise, seed, offset + (uint64_t)t, batch, z, h->zb, h->zb_ld,
+                                                                           plane_elems(h, h->zb_ld), h->planes, nullptr, nullptr, nullptr,
+                                                                           (prior && kl_coeff != 0.f && a_coeff > 0.f) ? h->acc + 1 : nullptr, nullptr);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    NetIO md_in; md_in.nseg = 2; md_in.seg[0] = s1_view(t); md_in.seg[1] = ws_view(h, h->zb, h->zb_ld, z, batch);
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_MSE;
+    set_aux(e, ty_view(h, h->da), 0);
+    e.scale = 2.f * a_coeff * invL / ((float)batch * (float)h->da);
+    e.loss = h->acc + 0;
+    set_out2(e, h, h->ahat, h->a_ld);
+    set_out(e, h, h->ga, h->a_ld);
+    CKR(net_forward(h, md, md_in, batch, e, st, true));
+    NetIO wm_in; wm_in.nseg = 2; wm_in.seg[0] = s1_view(t); wm_in.seg[1] = ws_view(h, h->ahat, h->a_ld, h->da, batch);
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_MSE;
+    set_aux(e, tx_view(h, h->dsbp, h->dsb), 0);
+    e.scale = 2.f * cyc_coeff * invL / ((float)batch * (float)h->dsb);
+    e.loss = h->acc + 3;
+    set_out(e, h, wm.g[Lwm - 1], wm.act_ld[Lwm - 1]);
+    set_out2(e, h, h->fut, h->f_ld);
+    // (the bias gradient of this layer needs the gradient that later steps add to g: it is summed by the last accumulating launch
+    //  of step t + 1, or right here for the last step)
+    e.colsum = (train_wm && t == L - 1) ? wm.grad + wm.gb[Lwm - 1] : nullptr;
+    CKR(net_forward(h, wm, wm_in, batch, e, st, true));
+    if (world) {       // second world-model pass, on the ground-truth action: the world phase's loss term
+      use_slot(L + t);
+      NetIO gt_in; gt_in.nseg = 2; gt_in.seg[0] = s1_view(t); gt_in.seg[1] = tx_view(h, h->dsb8, h->da);
+      memset(&e, 0, sizeof(e));
+      e.type = EPI_MSE;
+      set_aux(e, tx_view(h, h->dsbp, h->dsb), 0);
+      e.scale = 2.f * s_coeff * invL / ((float)batch * (float)h->dsb);
+      e.loss = h->acc + 2;
+      set_out(e, h, wm.g[Lwm - 1], wm.act_ld[Lwm - 1]);
+      e.colsum = wm.grad + wm.gb[Lwm - 1];
+      CKR(net_forward(h, wm, gt_in, batch, e, st, true));
+    }
+  }
+  // ------------------------------------------------ backward, t = L-1 .. 0 ------------------------------------------------
+  for (int t = L - 1; t >= 0; --t) {
+    bind_t(t);
+    // gradient w.r.t. this step's body state accumulates into the previous step's cycle-pass output gradient
+    EpiParams acc0;
+    memset(&acc0, 0, sizeof(acc0));
+    if (t > 0) {
+      acc0.type = EPI_DGRAD; acc0.act = ACT_LINEAR;
+      acc0.add = wm_glast[t - 1]; acc0.add_ld = h->f_ld; acc0.add_ps = plane_elems(h, h->f_ld); acc0.add_planes = h->planes;
+      acc0.out = wm_glast[t - 1]; acc0.out_ld = h->f_ld; acc0.out_ps = plane_elems(h, h->f_ld); acc0.out_planes = h->planes;
+    }
+    const EpiParams* p0 = t > 0 ? &acc0 : nullptr;
+    if (world) {
+      use_slot(L + t);
+      NetIO gt_in; gt_in.nseg = 2; gt_in.seg[0] = s1_view(t); gt_in.seg[1] = tx_view(h, h->dsb8, h->da);
+      CKR(net_backward(h, wm, gt_in, batch, true, nullptr, st, p0));
+    }
+    use_slot(t);
+    NetIO te_in; te_in.nseg = 2; te_in.seg[0] = s1_view(t); te_in.seg[1] = tx_view(h, h->dsbp, h->dsb);
+    NetIO md_in; md_in.nseg = 2; md_in.seg[0] = s1_view(t); md_in.seg[1] = ws_view(h, h->zb, h->zb_ld, z, batch);
+    NetIO wm_in; wm_in.nseg = 2; wm_in.seg[0] = s1_view(t); wm_in.seg[1] = ws_view(h, h->ahat, h->a_ld, h->da, batch);
+    // cycle pass of the world model: d a_hat (+ the action-loss gradient) -> decoder output gradient
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_DGRAD; e.act = ACT_LINEAR;
+    e.add = h->ga; e.add_ld = h->a_ld; e.add_ps = plane_elems(h, h->a_ld); e.add_planes = h->planes;
+    set_out(e, h, md.g[Lmd - 1], md.act_ld[Lmd - 1]);
+    e.colsum = train_vae ? md.grad + md.gb[Lmd - 1] : nullptr;
+    CKR(net_backward(h, wm, wm_in, batch, train_wm, &e, st, p0));
+    // decoder
+    memset(&e, 0, sizeof(e));
+    e.type = EPI_DGRAD; e.act = ACT_LINEAR;
+    e.out_f32 = h->dz; e.f32_sm = z; e.f32_sn = 1;
+    CKR(net_backward(h, md, md_in, batch, train_vae, &e, st, p0));
+    {
+      const int w = h->te_out;
+      int rows_per_block = 256 / w; if (rows_per_block < 1) rows_per_block = 1;
+      const int threads = w * rows_per_block;
+      if (threads > 1024) return fail(PVAE_ERR_INVALID, "latent_dim %d too large for the reparameterisation kernel", z);
+      int grid = cdiv(batch, rows_per_block); if (grid > h->dev.sms * 8) grid = h->dev.sms * 8;
+      const float kls = (prior && a_coeff > 0.f) ? kl_coeff * invL / (float)batch : 0.f;
+      reparam_bwd_kernel<<<grid, threads, 0, st>>>(h->dz, h->ml, h->eps, prior, prior && noise, kls, batch, z, te.g[Lte - 1], te.act_ld[Lte - 1],
+                                                   plane_elems(h, te.act_ld[Lte - 1]), h->planes, train_vae ? te.grad + te.gb[Lte - 1] : nullptr);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    // encoder; its body-state gradient is the last contribution to the previous step's output gradient: that launch also sums the
+    // world model's output-layer bias gradient of step t - 1
+    EpiParams last0 = acc0;
+    if (t > 0 && train_wm) last0.colsum = wm.grad + wm.gb[Lwm - 1];
+    CKR(net_backward(h, te, te_in, batch, train_vae, nullptr, st, t > 0 ? &last0 : nullptr));
+  }
+  finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, a_coeff, (prior && a_coeff > 0.f) ? kl_coeff : 0.f, s_coeff, cyc_coeff,
+                                         nullptr, 0ull, L);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  h->acc_dirty = false;
+  return PVAE_OK;
+}
+
+int pvae_rollout_step(pvae_handle h, int phase, int batch, int lookahead, const void* const* tbufs_host, int64_t buf_rows, const float* eps_dev,
+                      uint64_t seed, uint64_t offset, int noise, float a_coeff, float kl_coeff, float s_coeff, float cyc_coeff, float* loss_dev,
+                      pvae_stream s) {
+  CKR(step_prologue(h, batch));
+  if (phase != 0 && phase != 1) return fail(PVAE_ERR_INVALID, "phase must be 0 (world model) or 1 (VAE)");
+  if (lookahead < 1 || !tbufs_host || !loss_dev) return fail(PVAE_ERR_INVALID, "bad argument");
+  if (!h->roll_ws || h->roll_slots < 2 * lookahead) return fail(PVAE_ERR_STATE, "no rollout workspace bound for lookahead %d (pvae_bind_rollout_workspace)", lookahead);
+  if (buf_rows <= 0 || buf_rows > 0x7fffffffLL) return fail(PVAE_ERR_INVALID, "bad buffer row count");
+  for (int t = 0; t < lookahead; ++t) if (!tbufs_host[t]) return fail(PVAE_ERR_INVALID, "null transition buffer for step %d", t);
+  Net& te = h->nets[PVAE_NET_TASK_ENCODER];
+  Net& md = h->nets[PVAE_NET_MOTOR_DECODER];
+  Net& wm = h->nets[PVAE_NET_WORLD_MODEL];
+  if (te.n_layers == 0 || md.n_layers == 0 || wm.n_layers == 0) return fail(PVAE_ERR_INVALID, "a rollout needs encoder, decoder and world model");
+  if (te.generic || md.generic || wm.generic) return fail(PVAE_ERR_INVALID, "a net with explicit input widths runs through pvae_fc_forward only");
+  CKR(check_trainable_acts(te));
+  CKR(check_trainable_acts(md));
+  CKR(check_trainable_acts(wm));
+  if (!te.bound || !md.bound || !wm.bound) return fail(PVAE_ERR_STATE, "nets not bound");
+  if ((phase == 0 && !wm.grad) || (phase == 1 && (!te.grad || !md.grad))) return fail(PVAE_ERR_STATE, "no gradient buffers bound for the trained nets");
+  const __nv_bfloat16* saved_tbuf = h->tbuf;
+  const int64_t saved_rows = h->tbuf_rows;
+  const int r = rollout_impl(h, phase, batch, lookahead, tbufs_host, buf_rows, eps_dev, seed, offset, noise, a_coeff, kl_coeff, s_coeff, cyc_coeff,
+                             loss_dev, (cudaStream_t)s);
+  if (h->ws) carve(h, reinterpret_cast<uint8_t*>(h->ws));      // back to the single-step workspace
+  h->tbuf = saved_tbuf; h->tbuf_rows = saved_rows;
+  return r;
 }
 
 int pvae_noise_counter(pvae_handle h, int enable, uint64_t value, uint64_t stride, pvae_stream s) {

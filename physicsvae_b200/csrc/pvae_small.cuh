@@ -5,11 +5,11 @@
 // step); a tcgen05 tile is 128 rows tall, so for <= 16 rows the tensor-core path is pure launch latency (15 launches, 82 us at
 // batch 1 in round 1).  Here one thread-block CLUSTER of 8 CTAs runs the net layer by layer:
 //   * every CTA keeps the full activation vector of every row in its shared memory;
-//   * CTA r computes output neurons [r * out / 8, (r + 1) * out / 8) of the layer -- a warp per neuron, lanes stride the K dimension
-//     with 16-byte loads of the bf16 shadow weights (1.3 MB for the decoder: L2-resident between control steps), fp32 accumulate,
-//     shuffle reduction -- and writes the results into the shared memory of ALL eight CTAs (distributed shared memory,
-//     st.shared::cluster);
-//   * one cluster barrier per layer.
+//   * CTA r computes a slice of the layer's output neurons -- a warp per neuron, lanes stride the K dimension with 16-byte loads
+//     of the bf16 shadow weights (1.3 MB for the decoder: L2-resident between control steps), fp32 accumulate, shuffle reduction --
+//     into its own shared memory;
+//   * one cluster barrier per layer, after which every CTA pulls the other seven slices out of its peers' shared memory
+//     (distributed shared memory, 16-byte ld.shared::cluster).
 // Weights are read exactly once per call, split eight ways; nothing but the final output touches global memory.
 #pragma once
 #include <cuda_runtime.h>
@@ -18,7 +18,7 @@
 
 namespace pvae {
 
-constexpr int SF_CLUSTER = 8, SF_THREADS = 256, SF_MAX_ROWS = 16, SF_MAX_LAYERS = 8;
+constexpr int SF_CLUSTER = 8, SF_THREADS = 256, SF_MAX_ROWS = 16, SF_SMALL_ROWS = 4, SF_MAX_LAYERS = 8;
 
 struct SmallLayer {
   const __nv_bfloat16* W;      // shadow operand [plane][out][kpad]
@@ -56,13 +56,26 @@ __device__ __forceinline__ void small_cluster_sync() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float4 small_ld_cluster_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // BT: rows computed (a power of two >= the batch; missing rows are zero rows of shared memory)
+//
+// Exchange protocol (double buffer X / Y per CTA, one cluster barrier per layer): layer l reads the full input from X, writes its own
+// slice of the output into its local Y; barrier; every CTA PULLS the seven remote slices out of the peers' Y with 16-byte
+// ld.shared::cluster (scalar remote stores were 4x slower: distributed shared memory moves ~20 B/clk per CTA and pays per
+// transaction); the roles of X and Y swap.  A peer may still be pulling from my Y while I already write my slice of layer l + 1 into X --
+// different buffers -- and I cannot reach layer l + 2 (which writes Y again) before every peer has passed the barrier of layer l + 1,
+// i.e. finished pulling.
 template <int BT>
 __global__ void __cluster_dims__(SF_CLUSTER, 1, 1) __launch_bounds__(SF_THREADS, 1)
 small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_ld, const float* __restrict__ in1, int64_t in1_ld, int B,
                 float* __restrict__ out, int64_t out_ld) {
   extern __shared__ float sf_smem[];
-  const int width = net.width;
+  const int width = net.width;                   // multiple of 32
   float* buf[2] = {sf_smem, sf_smem + BT * width};
   uint32_t crank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -79,17 +92,18 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
     buf[0][i] = v;
     buf[1][i] = 0.f;
   }
-  small_cluster_sync();          // (also: every CTA of the cluster is running before anyone writes into its shared memory)
+  small_cluster_sync();          // (also: every CTA of the cluster is running before anyone reads its shared memory)
   int cur = 0;
   for (int l = 0; l < net.n_layers; ++l) {
     const SmallLayer& L = net.L[l];
     const bool last = l == net.n_layers - 1;
-    const int per = (L.out + SF_CLUSTER - 1) / SF_CLUSTER;
-    const int n_lo = crank * per, n_hi = min(n_lo + per, L.out);
+    // slices of 32-neuron granularity so that a slice is whole 16-byte pieces for the pull
+    const int per = (((L.out + SF_CLUSTER - 1) / SF_CLUSTER) + 31) & ~31;
+    const int n_lo = min((int)crank * per, L.out), n_hi = min(n_lo + per, L.out);
     const float* x = buf[cur];
-    const uint32_t nxt_base = (uint32_t)__cvta_generic_to_shared(buf[cur ^ 1]);
+    float* y = buf[cur ^ 1];
     // a warp works on NPW neurons at a time (their weight loads are in flight together: the loop is L2-latency bound at batch 1)
-    constexpr int NPW = BT <= 4 ? 4 : 2, NW = SF_THREADS / 32;
+    constexpr int NPW = 4, NW = SF_THREADS / 32;
     for (int n0 = n_lo + warp; n0 < n_hi; n0 += NW * NPW) {
       float acc[NPW][BT];
 #pragma unroll
@@ -142,37 +156,48 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
           for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
           acc[j][b] = a;
         }
-        if (n < n_hi) {                                      // warp-uniform
+        if (n < n_hi && lane == 0) {
           const float bias = L.bias ? __ldg(L.bias + n) : 0.f;
 #pragma unroll
           for (int b = 0; b < BT; ++b) {
             float v = small_act(L.act, acc[j][b] + bias);
             if (last) {
-              if (lane == 0 && b < B) out[(int64_t)b * out_ld + n] = v;
+              if (b < B) out[(int64_t)b * out_ld + n] = v;
             } else {
               if (net.planes == 1) v = __bfloat162float(__float2bfloat16_rn(v));
-              if (lane < SF_CLUSTER) small_st_cluster(small_mapa(nxt_base + (uint32_t)(b * width + n) * 4u, (uint32_t)lane), v);
+              y[b * width + n] = v;
             }
           }
         }
       }
     }
     if (!last) {
-      // columns [out, kpad_next) of the next input must read as zero: buffers start zeroed and a layer only ever writes [0, out);
-      // the buffer being recycled held the previous layer's INPUT, whose tail beyond this layer's out may be stale -> clear it
-      small_cluster_sync();
-      const int next_k = net.L[l + 1].kpad;
-      float* old = buf[cur];
-      const int prev_w = (l == 0) ? net.L[0].kpad : net.L[l].kpad;
-      (void)next_k;
-      for (int i = threadIdx.x; i < BT * prev_w; i += SF_THREADS) {
-        const int b = i / prev_w, c = i - b * prev_w;
-        old[b * width + c] = 0.f;
+      small_cluster_sync();                          // every CTA's slice of layer l is in its local y
+      // pull the remote slices (16-byte pieces) and clear the tail [out, next kpad) that the next layer reads as K padding
+      const int pieces = per >> 2;                   // float4 pieces per (slice, row)
+      const uint32_t y_s = (uint32_t)__cvta_generic_to_shared(y);
+      for (int i = threadIdx.x; i < (SF_CLUSTER - 1) * BT * pieces; i += SF_THREADS) {
+        const int pc = i % pieces;
+        const int b = (i / pieces) % BT;
+        const int pr = (int)(crank + 1 + i / (pieces * BT)) % SF_CLUSTER;      // start with the next rank: spread the traffic
+        const int c0 = pr * per + pc * 4;
+        if (c0 < L.out) {
+          const uint32_t off = (uint32_t)(b * width + c0) * 4u;
+          const float4 v = small_ld_cluster_v4(small_mapa(y_s + off, (uint32_t)pr));
+          *reinterpret_cast<float4*>(y + b * width + c0) = v;
+        }
       }
+      __syncthreads();
+      const int next_k = net.L[l + 1].kpad;
+      for (int i = threadIdx.x; i < BT * (next_k - L.out); i += SF_THREADS) {
+        const int b = i / (next_k - L.out), c = L.out + i % (next_k - L.out);
+        y[b * width + c] = 0.f;
+      }
+      __syncthreads();
       cur ^= 1;
-      small_cluster_sync();      // nobody starts writing layer l + 1's outputs into a buffer that a peer is still clearing
     }
   }
+  small_cluster_sync();          // no CTA exits while a peer may still read its shared memory
 }
 
 }  // namespace pvae

@@ -189,6 +189,29 @@ class Engine:
                                               float(a_coeff), float(kl_coeff), float(cyc_coeff), _ptr(self.loss), _stream()))
         return self.loss
 
+    def rollout_step(self, batch, world, buffers, buf_rows, eps=None, seed=0, offset=0, noise=True, a_coeff=1.0, kl_coeff=1.0, s_coeff=1.0,
+                     cyc_coeff=1e-3):
+        """compute_loss with lookahead L = len(buffers) > 1 (train_physics_vae.py:361-435): autoregressive rollout, forward + loss +
+        backward through time.  buffers[t]: resident transition buffer of step t (ingest of X[:, t, :], Y[:, t, :])."""
+        L = len(buffers)
+        if eps is not None:
+            if eps.shape != (L, batch, self.z) or eps.dtype != torch.float32 or eps.device != self.device or not eps.is_contiguous():
+                raise ValueError("eps must be a contiguous fp32 [%d, %d, %d] tensor on %s" % (L, batch, self.z, self.device))
+        need = C.c_size_t(0)
+        _abi.check(self.lib.pvae_rollout_workspace_bytes(self._h, L, C.byref(need)))
+        ws = getattr(self, "_rollout_ws", None)
+        if ws is None or ws.numel() < need.value + 1024 or self._rollout_L < L:
+            ws = self._rollout_ws = torch.zeros(need.value + 1024, dtype=torch.uint8, device=self.device)
+            self._rollout_L = L
+            off = (-ws.data_ptr()) % 1024
+            _abi.check(self.lib.pvae_bind_rollout_workspace(self._h, C.c_void_p(ws.data_ptr() + off), need.value, L))
+        ptrs = (C.c_void_p * L)(*[b.data_ptr() for b in buffers])
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_rollout_step(self._h, 0 if world else 1, int(batch), L, ptrs, int(buf_rows), _ptr(eps), int(seed), int(offset),
+                                                  1 if noise else 0, float(a_coeff), float(kl_coeff), float(s_coeff), float(cyc_coeff),
+                                                  _ptr(self.loss), _stream()))
+        return self.loss
+
     def eval_loss(self, batch, world, eps=None, seed=0, offset=0, noise=True, a_coeff=1.0, kl_coeff=1.0, s_coeff=1.0, cyc_coeff=1e-3):
         """Forward + loss only, no gradient is touched (the reference's test pass, torch_models.py:147-155)."""
         if eps is not None:

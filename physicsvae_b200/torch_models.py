@@ -236,7 +236,7 @@ class TrainModel(_TrainableBase):
             self._engine_changed(eng)
         if self._bound != (eng, which):
             buf, n = self._buffers[which]
-            eng.bind_transitions(buf, n)
+            eng.bind_transitions(buf[0] if isinstance(buf, list) else buf, n)      # (a list: one buffer per rollout step, lookahead > 1)
             self._bound = (eng, which)
         return eng
 
@@ -255,10 +255,24 @@ class TrainModel(_TrainableBase):
             chunk = 1 << 20
             for lo in range(0, len(first), chunk):
                 eng.ingest_episodes(st, ac, torch.from_numpy(first[lo:lo + chunk]).to(self.device), dst_row=lo)
+        elif np.asarray(loader.dataset.X).ndim == 3 and np.asarray(loader.dataset.X).shape[1] > 1:
+            # lookahead L > 1 (autoregressive rollout): one resident buffer per rollout step t, holding (x[:, t], y[:, t])
+            X, Y = loader.dataset.arrays()
+            n, L = X.shape[0], X.shape[1]
+            bufs = []
+            for t in range(L):
+                eng.alloc_transitions(n)
+                chunk = 1 << 18
+                for lo in range(0, n, chunk):
+                    hi = min(lo + chunk, n)
+                    eng.ingest(torch.from_numpy(np.ascontiguousarray(X[lo:hi, t])).to(self.device),
+                               torch.from_numpy(np.ascontiguousarray(Y[lo:hi, t])).to(self.device), dst_row=lo)
+                bufs.append(eng.transitions)
+            self._buffers[which] = (bufs, n)
+            self._bound = (eng, which)
+            return
         else:
             X, Y = loader.dataset.arrays()
-            if X.ndim == 3 and X.shape[1] != 1:
-                raise NotImplementedError("lookahead > 1 datasets go through compute_loss (rollout path), not the resident loader")
             n = X.shape[0]
             eng.alloc_transitions(n)
             chunk = 1 << 18

@@ -285,10 +285,8 @@ class TrainModel(torch_models.TrainModel):
         self.config = config
         self.max_iter_world_model = config.get("max_iter_world_model")
         self.latent_prior_type = config.get("latent_prior_type")
-        self.lookahead = config.get("lookahead")
-        if self.lookahead != 1:
-            raise NotImplementedError("the resident-buffer trainer runs lookahead 1 (train_physics_vae.py:277 hard-wires it); "
-                                      "longer rollouts go through the oracle-pinned rollout path when built")
+        self.lookahead = int(config.get("lookahead"))            # (the CLI hard-wires 1, train_physics_vae.py:277; > 1 = autoregressive rollout)
+        assert self.lookahead >= 1
         self.noise_seed = int(config.get("noise_seed", 0))
         self._noise_step = 0
         self.world_phase = True
@@ -373,6 +371,17 @@ class TrainModel(torch_models.TrainModel):
         """Forward + loss (+ backward when `train`) for the `n` rows at the device cursor; loss coefficients weighted by `w`
         (n_rank * R / n, see parallel.py).  The Philox offset is (device-side noise counter) + rank."""
         eng = self.engine
+        bufs = self._buffers[self._bound[1]][0]
+        if isinstance(bufs, list) and len(bufs) > 1:
+            # lookahead > 1: autoregressive rollout, gradients through time (pvae_rollout_step); the test pass runs the same call and
+            # simply leaves the gradients unused
+            kl = self.vae_kl_coeff if self.latent_prior_type else 0.0
+            eng.rollout_step(n, self.world_phase, bufs, self._buffers[self._bound[1]][1], eps=eps, seed=self.noise_seed,
+                             offset=parallel.rank() + 1000003 * self._noise_step, noise=bool(self.model.latent_prior_noise),
+                             a_coeff=self.a_rec_coeff * w, kl_coeff=kl * w, s_coeff=self.s_rec_coeff * w, cyc_coeff=self.vae_cycle_coeff * w)
+            if w != 1.0:
+                eng.loss[1:5].mul_(w)
+            return
         if self.world_phase:
             if self.s_rec_coeff <= 0:
                 raise ValueError("world phase needs s_rec_coeff > 0")
@@ -427,7 +436,7 @@ class TrainModel(torch_models.TrainModel):
 
     # ---- the captured full-batch step (torch_models.TrainModel._graph_step) ------------------------------------------------
     def _graph_supported(self):
-        return True
+        return self.lookahead == 1          # (a rollout re-carves the workspace per step on the host: eager launches)
 
     def _graph_key(self, batch_size):
         return super()._graph_key(batch_size) + (self.world_phase, self.s_rec_coeff, self.a_rec_coeff, self.vae_kl_coeff,
@@ -470,17 +479,22 @@ class TrainModel(torch_models.TrainModel):
         B = x.shape[0]
         if B < 2:
             raise ValueError("compute_loss needs at least 2 transitions (the reference squeezes the batch axis)")
-        if x.dim() == 3 and x.shape[1] != 1:
-            raise NotImplementedError("lookahead > 1: the autoregressive rollout is not on the CUDA path (oracle/pvae_oracle.py "
-                                      "compute_loss_lookahead pins its arithmetic)")
+        L = x.shape[1] if x.dim() == 3 else 1
         self._engine_rows = max(self._engine_rows, B)
         eng = self.engine                                # (a larger B re-creates the engine: _bind notices and drops the graphs)
         buf = self._buffers.get("adhoc")
-        if buf is None or buf[1] != B:
-            buf = (torch.zeros(eng.transitions_bytes(B), dtype=torch.uint8, device=self.device), B)
+        if buf is None or buf[1] != B or (len(buf[0]) if isinstance(buf[0], list) else 1) != L:
+            mk = lambda: torch.zeros(eng.transitions_bytes(B), dtype=torch.uint8, device=self.device)
+            buf = ([mk() for _ in range(L)], B) if L > 1 else (mk(), B)
             self._buffers["adhoc"] = buf
         self._bind("adhoc")
-        eng.ingest(x.reshape(B, -1).to(self.device), y.reshape(B, -1).to(self.device))
+        if L > 1:                                        # one resident buffer per rollout step: (x[:, t], y[:, t])
+            for t in range(L):
+                eng.bind_transitions(buf[0][t], B)
+                eng.ingest(x[:, t].reshape(B, -1).to(self.device), y[:, t].reshape(B, -1).to(self.device))
+            eng.bind_transitions(buf[0][0], B)
+        else:
+            eng.ingest(x.reshape(B, -1).to(self.device), y.reshape(B, -1).to(self.device))
         loss = self.batch_loss(0, B, eps=eps)
         return torch_models._DepositedLoss.apply(self._anchor, loss)
 
