@@ -173,6 +173,12 @@ int pvae_rollout_step(pvae_handle h, int phase, int batch, int lookahead, const 
 int pvae_eval_loss(pvae_handle h, int phase, int batch, const float* eps_dev, uint64_t seed, uint64_t offset, int noise, float a_coeff,
                    float kl_coeff, float s_coeff, float cyc_coeff, float* loss_dev, pvae_stream s);
 
+/* Deterministic gradients (a decided reduction order).  enable != 0: weight gradients are computed without split-K (one
+ * CTA pair walks the whole batch of its tile in order) and bias gradients by two-pass ordered column sums instead of the epilogues'
+ * atomics -- every gradient is then bit-identical from run to run (slower: the 1024 x 1024 weight gradient uses 16 of 74 CTA pairs).
+ * Default off: fp32 red.global.add in arrival order (differences in the last bits). */
+int pvae_set_deterministic(pvae_handle h, int enable);
+
 /* Device-side counter of the Philox noise stream.  enable != 0: every pvae_vae_step / pvae_eval_loss call that draws noise itself
  * (eps_dev == NULL, noise != 0) uses offset + counter as its stream offset and adds `stride` to the counter when it finishes, so a
  * captured CUDA graph draws fresh noise on every replay (the reference draws torch.randn_like per call, rllib_model_torch.py:737).

@@ -336,6 +336,42 @@ __global__ void f32_to_planes_kernel(const float* __restrict__ src, int64_t src_
   }
 }
 
+// ---- deterministic bias gradients (pvae_set_deterministic): column sums of a bf16 (hi + lo) gradient tensor in a FIXED order ------------
+// pass 1: block (column group of 32, row chunk c of DET_CHUNKS) -- thread (column, row lane of 8) walks its rows in order, the 8 row
+// lanes are combined in order -> partial[c][column];  pass 2: the DET_CHUNKS partials are added in order and accumulated into the
+// bias gradient.  No atomics: the result does not depend on scheduling.
+constexpr int DET_CHUNKS = 64;
+__global__ void colsum_det_partial_kernel(const __nv_bfloat16* __restrict__ g, int64_t ld, int64_t ps, int planes, int rows, int cols,
+                                          float* __restrict__ partial) {
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;                       // 0..7
+  const int per = (rows + DET_CHUNKS - 1) / DET_CHUNKS;
+  const int r0 = blockIdx.y * per, r1 = min(r0 + per, rows);
+  float acc = 0.f;
+  if (col < cols)
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float v = __bfloat162float(g[(int64_t)r * ld + col]);
+      if (planes > 1) v += __bfloat162float(g[ps + (int64_t)r * ld + col]);
+      acc += v;
+    }
+  __shared__ float sh[8][32];
+  sh[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+    partial[(int64_t)blockIdx.y * cols + col] = t;
+  }
+}
+__global__ void colsum_det_final_kernel(const float* __restrict__ partial, int cols, float* __restrict__ colsum) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  float t = 0.f;
+  for (int c = 0; c < DET_CHUNKS; ++c) t += partial[(int64_t)c * cols + col];
+  colsum[col] += t;
+}
+
 // ---- data-parallel gradient exchange over peer memory (NVLink 5 / NVSwitch) ------------------------------------------------------
 // One kernel = barrier + reduce-scatter + all-gather of a contiguous fp32 range that lives at the same offset of a symmetric
 // (peer-mapped) allocation on every rank -- the [gradients | loss slots] range of the model's gradient pool:

@@ -120,6 +120,9 @@ struct Device {
   int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
   int fast_epi = 1;       // PVAE_FAST_EPI=0: never use the lean ReLU store / dgrad epilogue (A/B experiments)
   int small_fwd = 1;      // PVAE_SMALL_FWD=0: batches <= 16 of the inference API also take the tensor-core path
+  int deterministic = 0;  // pvae_set_deterministic: no split-K, bias gradients by ordered column sums (run-to-run bit-identical gradients)
+  float* det_scratch = nullptr;   // [DET_CHUNKS][cols] partial column sums (the engine's small scratch buffer)
+  int det_scratch_elems = 0;
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
 };
@@ -219,7 +222,7 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   const int kb_total = p.kb[0] + p.kb[1];
   const int iters = kb_total * d.passes;
   int splits = 1;
-  if (d.split) {
+  if (d.split && !dev.deterministic) {      // (deterministic mode: one CTA pair walks the whole K range of its tile, in order)
     // Split K so that the work units fill whole waves of the persistent grid: the kernel lasts as long as its busiest
     // CTA (pair), i.e. waves(s) * (k-blocks per unit + the unit's non-overlapped epilogue share).  1024x1024 wgrad at
     // batch 65536: 16 pair tiles on 74 pairs -- 10 splits need 3 waves (72 % busy), 9 splits need 2 (97 %).
@@ -238,6 +241,13 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   p.epi = d.epi;
   p.epi.m_valid = d.M;
   p.epi.n_valid = d.N;
+  // deterministic mode: bias gradients are not summed by the epilogue (atomics across CTAs) but by ordered column sums of the
+  // primary output after the launch
+  float* det_colsum = nullptr;
+  if (dev.deterministic && p.epi.colsum && p.epi.out && dev.det_scratch && (int64_t)DET_CHUNKS * d.N <= dev.det_scratch_elems) {
+    det_colsum = p.epi.colsum;
+    p.epi.colsum = nullptr;
+  }
   const EpiParams& e = p.epi;
   // TMA epilogue: one precision plane, bf16 primary output; ReLU dgrad needs the sign-bit mask its forward wrote
   const bool has_aux = e.type == EPI_MSE || (e.type == EPI_DGRAD && e.act != ACT_LINEAR && e.act != ACT_RELU);
@@ -286,6 +296,12 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   CK(cudaLaunchKernelEx(&cfg, fn, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
+  if (det_colsum) {
+    colsum_det_partial_kernel<<<dim3(cdiv(d.N, 32), DET_CHUNKS), 256, 0, st>>>(p.epi.out, p.epi.out_ld, p.epi.out_ps, p.epi.out_planes, d.M, d.N, dev.det_scratch);
+    colsum_det_final_kernel<<<cdiv(d.N, 128), 128, 0, st>>>(dev.det_scratch, d.N, det_colsum);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+  }
   if (log_level >= 2) CK(cudaStreamSynchronize(st));
   return PVAE_OK;
 }
@@ -959,6 +975,16 @@ int pvae_advance_cursor(pvae_handle h, int64_t delta, int64_t batch, int64_t lim
   return PVAE_OK;
 }
 
+// ordered column sums of a bf16 gradient tensor [batch][cols] accumulated into colsum (deterministic mode)
+static int det_colsum(pvae_engine* h, const __nv_bfloat16* g, int ld, int batch, int cols, float* colsum, cudaStream_t st) {
+  if (!h->dev.det_scratch || (int64_t)DET_CHUNKS * cols > h->dev.det_scratch_elems) return fail(PVAE_ERR_INVALID, "layer too wide for the deterministic column sums");
+  colsum_det_partial_kernel<<<dim3(cdiv(cols, 32), DET_CHUNKS), 256, 0, st>>>(g, ld, plane_elems(h, ld), h->planes, batch, cols, h->dev.det_scratch);
+  colsum_det_final_kernel<<<cdiv(cols, 128), 128, 0, st>>>(h->dev.det_scratch, cols, colsum);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
 static int step_prologue(pvae_handle h, int batch) {
   if (!h) return fail(PVAE_ERR_INVALID, "null handle");
   if (!h->ws) return fail(PVAE_ERR_STATE, "no workspace bound (pvae_bind_workspace)");
@@ -1099,8 +1125,9 @@ static int vae_impl(pvae_handle h, int batch, const float* eps_dev, uint64_t see
     int grid = cdiv(batch, rows_per_block); if (grid > h->dev.sms * 8) grid = h->dev.sms * 8;
     reparam_bwd_kernel<<<grid, threads, 0, st>>>(h->dz, h->ml, h->eps, prior, prior && noise, prior ? kl_coeff / (float)batch : 0.f, batch, z,
                                                  te.g[Lte - 1], te.act_ld[Lte - 1], plane_elems(h, te.act_ld[Lte - 1]), h->planes,
-                                                 te.grad + te.gb[Lte - 1]);
+                                                 h->dev.deterministic ? nullptr : te.grad + te.gb[Lte - 1]);
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (h->dev.deterministic) CKR(det_colsum(h, te.g[Lte - 1], te.act_ld[Lte - 1], batch, w, te.grad + te.gb[Lte - 1], st));
   }
   CKR(net_backward(h, te, te_in, batch, true, nullptr, st));
   }
@@ -1266,8 +1293,10 @@ static int rollout_impl(pvae_handle h, int phase, int batch, int L, const void* 
       int grid = cdiv(batch, rows_per_block); if (grid > h->dev.sms * 8) grid = h->dev.sms * 8;
       const float kls = (prior && a_coeff > 0.f) ? kl_coeff * invL / (float)batch : 0.f;
       reparam_bwd_kernel<<<grid, threads, 0, st>>>(h->dz, h->ml, h->eps, prior, prior && noise, kls, batch, z, te.g[Lte - 1], te.act_ld[Lte - 1],
-                                                   plane_elems(h, te.act_ld[Lte - 1]), h->planes, train_vae ? te.grad + te.gb[Lte - 1] : nullptr);
+                                                   plane_elems(h, te.act_ld[Lte - 1]), h->planes,
+                                                   (train_vae && !h->dev.deterministic) ? te.grad + te.gb[Lte - 1] : nullptr);
       g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (train_vae && h->dev.deterministic) CKR(det_colsum(h, te.g[Lte - 1], te.act_ld[Lte - 1], batch, w, te.grad + te.gb[Lte - 1], st));
     }
     // encoder; its body-state gradient is the last contribution to the previous step's output gradient: that launch also sums the
     // world model's output-layer bias gradient of step t - 1
@@ -1309,6 +1338,15 @@ int pvae_rollout_step(pvae_handle h, int phase, int batch, int lookahead, const 
   if (h->ws) carve(h, reinterpret_cast<uint8_t*>(h->ws));      // back to the single-step workspace
   h->tbuf = saved_tbuf; h->tbuf_rows = saved_rows;
   return r;
+}
+
+int pvae_set_deterministic(pvae_handle h, int enable) {
+  if (!h) return fail(PVAE_ERR_INVALID, "null handle");
+  if (enable && !h->small_scratch) return fail(PVAE_ERR_CUDA, "scratch buffer was not allocated");
+  h->dev.deterministic = enable != 0;
+  h->dev.det_scratch = h->small_scratch;
+  h->dev.det_scratch_elems = 2 * SF_MAX_ROWS * SMALL_SCRATCH_COLS;
+  return PVAE_OK;
 }
 
 int pvae_noise_counter(pvae_handle h, int enable, uint64_t value, uint64_t stride, pvae_stream s) {

@@ -223,6 +223,10 @@ class Engine:
                                                _ptr(self.loss), _stream()))
         return self.loss
 
+    def set_deterministic(self, enable=True):
+        """Run-to-run bit-identical gradients: no split-K, ordered bias-gradient sums (include/pvae_sm100.h, pvae_set_deterministic)."""
+        _abi.check(self.lib.pvae_set_deterministic(self._h, 1 if enable else 0))
+
     def noise_counter(self, enable, value=0, stride=1):
         """Device-side Philox offset counter (include/pvae_sm100.h, pvae_noise_counter)."""
         with torch.cuda.device(self.device):

@@ -178,6 +178,7 @@ class TrainModel(_TrainableBase):
         # the library's own kernel (parallel.SymmetricPool); None = plain tensor + torch.distributed
         self.model.grad_pool_factory = parallel.symmetric_pool_factory()
         eng = self.engine
+        self._engine_changed(eng)
         lr = config.get("lr", 1e-3)
         if config.get("optimizer", "pvae_adam") == "torch_adam":
             capturable = bool(config.get("optimizer_capturable", False))     # CUDA-graph replay of the whole step

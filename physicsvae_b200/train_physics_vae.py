@@ -68,6 +68,8 @@ def arg_parser():
     # multi-GPU launch (torchrun): "dp" = every trial is data-parallel over all ranks; "replicas" = the grid points of the
     # sweep are spread over the ranks, one independent trainer per GPU (what Ray Tune's parallel trials do upstream)
     parser.add_argument("--sweep_mode", type=str, default="dp", choices=["dp", "replicas"])
+    # engine knob (not in the reference): run-to-run bit-identical gradients (no split-K, ordered bias-gradient sums; slower)
+    parser.add_argument("--deterministic", action="store_true")
     return parser
 
 
@@ -241,6 +243,7 @@ def get_trainer_config(args):
         "world_model_s_rec_coeff": 0.0,
         "vae_cycle_coeff": grid_search(args.vae_cycle_coeff),
         "engine_precision": getattr(args, "precision", "bf16x3"),
+        "deterministic": bool(getattr(args, "deterministic", False)),
         "num_data": getattr(args, "num_data", None),
     }
     return trainer_config
@@ -296,6 +299,10 @@ class TrainModel(torch_models.TrainModel):
         self.model.set_learnable_world_model(True)
         self.read_loss_fn_coeff(world=True)
         self.sync_replicas()
+
+    def _engine_changed(self, eng):
+        if self.config.get("deterministic"):
+            eng.set_deterministic(True)             # run-to-run bit-identical gradients (no split-K, ordered bias-gradient sums)
 
     def sync_replicas(self):
         """Data-parallel ranks must hold the same parameters: every rank builds its model from its own RNG stream, so the
