@@ -597,6 +597,8 @@ static int small_chain(pvae_engine* h, Net& net, int batch, const float* in0, in
     width = net.out_dims[l] > width ? net.out_dims[l] : width;
   }
   sn.width = rup(width, 32);
+  static const int small_trace = getenv("PVAE_SMALL_TRACE") ? atoi(getenv("PVAE_SMALL_TRACE")) : 0;
+  sn.trace = small_trace;
   int bt = 1; while (bt < batch) bt <<= 1;
   const size_t smem = (size_t)2 * bt * sn.width * sizeof(float);
   void (*fn)(const SmallNet, const float*, int64_t, const float*, int64_t, int, float*, int64_t) =

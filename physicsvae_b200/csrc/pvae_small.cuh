@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace pvae {
 
@@ -30,7 +31,8 @@ struct SmallNet {
   SmallLayer L[SF_MAX_LAYERS];
   int32_t n_layers, planes;
   int32_t k0, k1, K0pad;       // layer-0 input segments in shadow-column order: [0, k0) <- in0, [K0pad, K0pad + k1) <- in1
-  int32_t width;               // shared-memory row stride (floats): max over layers of kpad / out, multiple of 8
+  int32_t width;               // shared-memory row stride (floats): max over layers of kpad / out, multiple of 32
+  int32_t trace;               // PVAE_SMALL_TRACE=1: CTA 0 prints its per-layer clock breakdown (debugging aid)
 };
 
 __device__ __forceinline__ float small_act(int act, float v) {
@@ -92,7 +94,11 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
     buf[0][i] = v;
     buf[1][i] = 0.f;
   }
+  const bool tr = net.trace && crank == 0 && threadIdx.x == 0;
+  long long t_prev = clock64();
+  if (tr) printf("[small_fc] start\n");
   small_cluster_sync();          // (also: every CTA of the cluster is running before anyone reads its shared memory)
+  if (tr) { const long long t = clock64(); printf("[small_fc] staged + first cluster sync: %lld clk\n", t - t_prev); t_prev = t; }
   int cur = 0;
   for (int l = 0; l < net.n_layers; ++l) {
     const SmallLayer& L = net.L[l];
@@ -171,8 +177,12 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
         }
       }
     }
+    long long t_c = 0;
+    if (tr) { __syncthreads(); t_c = clock64(); printf("[small_fc] layer %d (out %d kpad %d): compute %lld clk\n", l, L.out, L.kpad, t_c - t_prev); t_prev = t_c; }
+    else if (net.trace) __syncthreads();
     if (!last) {
       small_cluster_sync();                          // every CTA's slice of layer l is in its local y
+      if (tr) { const long long t = clock64(); printf("[small_fc]   cluster barrier %lld clk\n", t - t_prev); t_prev = t; }
       // pull the remote slices (16-byte pieces) and clear the tail [out, next kpad) that the next layer reads as K padding
       const int pieces = per >> 2;                   // float4 pieces per (slice, row)
       const uint32_t y_s = (uint32_t)__cvta_generic_to_shared(y);
@@ -194,6 +204,7 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
         y[b * width + c] = 0.f;
       }
       __syncthreads();
+      if (tr) { const long long t = clock64(); printf("[small_fc]   pull + clear %lld clk\n", t - t_prev); t_prev = t; }
       cur ^= 1;
     }
   }
