@@ -94,11 +94,14 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
     buf[0][i] = v;
     buf[1][i] = 0.f;
   }
+  // PVAE_SMALL_TRACE=1: thread 0 of CTA 0 collects clock stamps (start, staged, per layer: computed / barrier passed / pulled) and
+  // prints them once at the end (every __syncthreads below stays warp-uniform: the trace only adds stamps)
   const bool tr = net.trace && crank == 0 && threadIdx.x == 0;
-  long long t_prev = clock64();
-  if (tr) printf("[small_fc] start\n");
+  long long stamp[2 + 3 * SF_MAX_LAYERS];
+  int ns = 0;
+  if (tr) stamp[ns++] = clock64();
   small_cluster_sync();          // (also: every CTA of the cluster is running before anyone reads its shared memory)
-  if (tr) { const long long t = clock64(); printf("[small_fc] staged + first cluster sync: %lld clk\n", t - t_prev); t_prev = t; }
+  if (tr) stamp[ns++] = clock64();
   int cur = 0;
   for (int l = 0; l < net.n_layers; ++l) {
     const SmallLayer& L = net.L[l];
@@ -177,12 +180,11 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
         }
       }
     }
-    long long t_c = 0;
-    if (tr) { __syncthreads(); t_c = clock64(); printf("[small_fc] layer %d (out %d kpad %d): compute %lld clk\n", l, L.out, L.kpad, t_c - t_prev); t_prev = t_c; }
-    else if (net.trace) __syncthreads();
+    if (net.trace) __syncthreads();                  // (uniform: net.trace is a kernel argument)
+    if (tr) stamp[ns++] = clock64();
     if (!last) {
       small_cluster_sync();                          // every CTA's slice of layer l is in its local y
-      if (tr) { const long long t = clock64(); printf("[small_fc]   cluster barrier %lld clk\n", t - t_prev); t_prev = t; }
+      if (tr) stamp[ns++] = clock64();
       // pull the remote slices (16-byte pieces) and clear the tail [out, next kpad) that the next layer reads as K padding
       const int pieces = per >> 2;                   // float4 pieces per (slice, row)
       const uint32_t y_s = (uint32_t)__cvta_generic_to_shared(y);
@@ -204,11 +206,17 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
         y[b * width + c] = 0.f;
       }
       __syncthreads();
-      if (tr) { const long long t = clock64(); printf("[small_fc]   pull + clear %lld clk\n", t - t_prev); t_prev = t; }
+      if (tr) stamp[ns++] = clock64();
       cur ^= 1;
     }
   }
   small_cluster_sync();          // no CTA exits while a peer may still read its shared memory
+  if (tr) {
+    stamp[ns++] = clock64();
+    printf("[small_fc] clocks since start:");
+    for (int i = 1; i < ns; ++i) printf(" %lld", stamp[i] - stamp[0]);
+    printf("  (staged | per layer: computed, barrier, pulled | ... | last computed, exit barrier)\n");
+  }
 }
 
 }  // namespace pvae
