@@ -74,7 +74,7 @@ __device__ __forceinline__ float4 small_ld_cluster_v4(uint32_t addr) {
 // i.e. finished pulling.
 template <int BT>
 __global__ void __cluster_dims__(SF_CLUSTER, 1, 1) __launch_bounds__(SF_THREADS, 1)
-small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_ld, const float* __restrict__ in1, int64_t in1_ld, int B,
+small_fc_kernel(const __grid_constant__ SmallNet net, const float* __restrict__ in0, int64_t in0_ld, const float* __restrict__ in1, int64_t in1_ld, int B,
                 float* __restrict__ out, int64_t out_ld) {
   extern __shared__ float sf_smem[];
   const int width = net.width;                   // multiple of 32
@@ -111,14 +111,18 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
     const int n_lo = min((int)crank * per, L.out), n_hi = min(n_lo + per, L.out);
     const float* x = buf[cur];
     float* y = buf[cur ^ 1];
-    // a warp works on NPW neurons at a time (their weight loads are in flight together: the loop is L2-latency bound at batch 1)
-    constexpr int NPW = 4, NW = SF_THREADS / 32;
+    // A warp works on NPW neurons at a time: their weight loads and bias loads are in flight together, the shuffle reductions of
+    // the NPW sums interleave, and lane j finishes neuron j (bias, activation, store) -- measured at batch 1, the loop is pure
+    // latency (two warps per scheduler): processing neurons one after the other cost ~1000 clocks per neuron.
+    constexpr int NPW = BT <= 2 ? 8 : 4, NW = SF_THREADS / 32;
     for (int n0 = n_lo + warp; n0 < n_hi; n0 += NW * NPW) {
       float acc[NPW][BT];
 #pragma unroll
       for (int j = 0; j < NPW; ++j)
 #pragma unroll
         for (int b = 0; b < BT; ++b) acc[j][b] = 0.f;
+      const int n_mine = n0 + (lane < NPW ? lane : 0) * NW;                 // the neuron this lane finishes
+      const float bias = (L.bias && lane < NPW && n_mine < n_hi) ? __ldg(L.bias + n_mine) : 0.f;
       for (int k = lane * 8; k < L.kpad; k += 256) {        // kpad is a multiple of 64: whole 16-byte pieces
         uint4 q[NPW], q2[NPW];
 #pragma unroll
@@ -148,34 +152,36 @@ small_fc_kernel(const SmallNet net, const float* __restrict__ in0, int64_t in0_l
           }
 #pragma unroll
           for (int b = 0; b < BT; ++b) {
-            float a = acc[j][b];
+            float a0 = acc[j][b], a1 = 0.f;               // two chains per (neuron, row)
 #pragma unroll
-            for (int t = 0; t < 8; ++t) a = fmaf(w[t], xv[b][t], a);
-            acc[j][b] = a;
+            for (int t = 0; t < 4; ++t) { a0 = fmaf(w[t], xv[b][t], a0); a1 = fmaf(w[4 + t], xv[b][4 + t], a1); }
+            acc[j][b] = a0 + a1;
           }
         }
       }
+      // butterfly reductions of all NPW x BT sums (independent chains), then lane j keeps neuron j
+      float mine[BT];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) mine[b] = 0.f;
 #pragma unroll
       for (int j = 0; j < NPW; ++j) {
-        const int n = n0 + j * NW;
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
           float a = acc[j][b];
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-          acc[j][b] = a;
+          mine[b] = (lane == j) ? a : mine[b];
         }
-        if (n < n_hi && lane == 0) {
-          const float bias = L.bias ? __ldg(L.bias + n) : 0.f;
+      }
+      if (lane < NPW && n_mine < n_hi) {
 #pragma unroll
-          for (int b = 0; b < BT; ++b) {
-            float v = small_act(L.act, acc[j][b] + bias);
-            if (last) {
-              if (b < B) out[(int64_t)b * out_ld + n] = v;
-            } else {
-              if (net.planes == 1) v = __bfloat162float(__float2bfloat16_rn(v));
-              y[b * width + n] = v;
-            }
+        for (int b = 0; b < BT; ++b) {
+          float v = small_act(L.act, mine[b] + bias);
+          if (last) {
+            if (b < B) out[(int64_t)b * out_ld + n_mine] = v;
+          } else {
+            if (net.planes == 1) v = __bfloat162float(__float2bfloat16_rn(v));
+            y[b * width + n_mine] = v;
           }
         }
       }
