@@ -21,6 +21,11 @@ except Exception as e:
 PY
 }
 EXTRA=("$@")
-run symm PVAE_SYMM_AR=1 NCCL_DEBUG=WARN
-run nccl PVAE_SYMM_AR=0 NCCL_DEBUG=WARN
-run multimem PVAE_SYMM_AR=1 PVAE_SYMM_MULTIMEM=1 NCCL_DEBUG=WARN
+MODES=${MODES:-"symm nccl multimem"}
+for m in $MODES; do
+  case $m in
+    symm) run symm PVAE_SYMM_AR=1 NCCL_DEBUG=WARN ;;
+    nccl) run nccl PVAE_SYMM_AR=0 NCCL_DEBUG=WARN ;;
+    multimem) run multimem PVAE_SYMM_AR=1 PVAE_SYMM_MULTIMEM=1 NCCL_DEBUG=WARN ;;
+  esac
+done
