@@ -374,8 +374,10 @@ def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, loca
     tr._graph_probe = kev
     ms, clocks = time_steps(tr, steps, warmup, world, dev, ClockSampler(local) if rank == 0 else None)
     kernel_ms = probe_kernel_ms(tr, kev, max(5, min(steps, 20)), 5) if kev else None
-    # not GEMMs: loss finalisation, fused Adam (one per trained net), cursor advance; VAE phase also reparameterisation fwd / bwd
-    gemm_launches = launches_per_step - {"world": 3, "vae": 6}[phase]
+    # not GEMMs: loss finalisation, fused Adam (one per trained net), cursor advance; VAE phase also reparameterisation fwd / bwd;
+    # N > 1 with the symmetric gradient pool: the library's peer-memory all-reduce kernel
+    from physicsvae_b200 import parallel as _par
+    gemm_launches = launches_per_step - {"world": 3, "vae": 6}[phase] - (1 if world > 1 and _par.allreduce_kind()["kind"].startswith("symm") else 0)
     return {"phase": phase, "B": B, "value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "clocks": clocks,
             "kernel_ms": kernel_ms, "kev": kev, "flops_step": flops_step, "launches_per_step": int(launches_per_step),
             "gemm_launches": int(gemm_launches), "sustained": None, "config": workload(args, cfg, phase, B, dims), "dims": dims or args.config}
@@ -622,6 +624,29 @@ def run_b200(args, cfg):
         del t3
         torch.cuda.empty_cache()
         tr = None
+    if not args.only_phase:
+        # the CLI's default mini-batch (train_physics_vae.py --batch_size 256 = BASELINE.json configs[0]'s batch): a launch-bound step,
+        # which is what the captured graph is for -- the same trainer timed replaying its graph and launching every kernel eagerly
+        tr = None
+        torch.cuda.empty_cache()
+        tb = make_trainer(cfg, 256, args.precision, rank, world, phase=phase, n_rows=256 * 64)
+        kb = 500
+        msb, _ = time_steps(tb, kb, 20, world, dev)
+        for i in range(10):
+            tb.train_batch(256 * (i % 64), 256 * (i % 64) + 256)
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(200):
+            tb.train_batch(256 * (i % 64), 256 * (i % 64) + 256)
+        e1.record()
+        barrier(world)
+        mse = max_over_ranks(e0.elapsed_time(e1), dev, world)
+        extra["batch256"] = {"value": 256 * world * kb / (msb * 1e-3), "ms_per_step": msb / kb, "steps": kb, "phase": phase,
+                             "eager_ms_per_step": mse / 200, "eager_value": 256 * world * 200 / (mse * 1e-3),
+                             "note": "CLI default batch 256 per GPU: TrainModel.train_steps (captured graph) vs TrainModel.train_batch (eager launches)"}
+        del tb
+        torch.cuda.empty_cache()
     cfgs = {}
     if not args.only_phase and (world == 8 or args.all_configs):
         # BASELINE.json configs[3]: full VAE, global batch 262144 on 8 GPUs (32768 rows per GPU);
