@@ -636,8 +636,15 @@ struct UnitWalk {
 template <int EPI, int ACT, bool TMAEPI, int CG, bool FAST = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_constant__ GemmParams p) {
   static_assert(!FAST || (TMAEPI && ACT == ACT_RELU && (EPI == EPI_STORE || EPI == EPI_DGRAD)), "FAST epilogue: ReLU store / dgrad through TMA only");
-  constexpr int STAGES = Geo<CG>::STAGES;
+  // The lean epilogue trades one pipeline stage (5 instead of 6 -- 160 KiB of operands in flight per CTA is still twice what the
+  // L2 -> SM feed rate times the TMA latency needs) for a second staging slab per epilogue warp, so that a warp waits for the TMA
+  // store issued TWO chunks ago, not for the one it has just issued (the stores queue behind the operand loads in the SM's single
+  // TMA unit).  Barrier block and bias slices sit at the same offsets in both layouts.
+  constexpr int STAGES = FAST ? 5 : Geo<CG>::STAGES;
   constexpr int STAGE_BYTES = Geo<CG>::STAGE_BYTES;
+  constexpr int WARP_SLAB = FAST ? 2 * SLAB_BYTES : SLAB_BYTES;
+  constexpr int OFF_STG = FAST ? OFF_BARS - EPI_WARPS * WARP_SLAB : OFF_STAGING;
+  static_assert(STAGES * STAGE_BYTES <= OFF_STG, "pipeline overlaps the staging slabs");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle atoms need 1024 B alignment
   if (smem_base - smem_u32(smem_raw) > 512u) {                        // the carve-out assumes at most 512 B of alignment slack
@@ -841,12 +848,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     for (int k = 0; k < 4 * CS_TILES; ++k) cs_acc[k] = 0.f;
     const bool do_cs = EPI == EPI_DGRAD && e.colsum != nullptr;
     const uint32_t tempty0 = (CG == 2) ? mapa_u32(tempty_bar(0), 0u) : tempty_bar(0);
-    const uint32_t slab = smem_base + OFF_STAGING + ew * SLAB_BYTES;
-    uint8_t* slab_gen = smem_gen + OFF_STAGING + ew * SLAB_BYTES;
-    uint8_t* srow = slab_gen + lane * 64;
+    const uint32_t slab0 = smem_base + OFF_STG + ew * WARP_SLAB;           // two 2 KiB slabs per warp, used alternately
+    uint8_t* slab0_gen = smem_gen + OFF_STG + ew * WARP_SLAB;
+    int sbuf = 0;
     const int sw = (lane >> 1) & 3;
     const int hh = lane >> 4, ww = lane & 15;     // column-sum role: row half, word (= column pair) of the 64-byte slab row
-    const uint8_t* cs_base = slab_gen + (hh << 10) + ((ww & 3) << 2);
     UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits, p.reverse);
     // operands of a unit's (at most two) chunks that do not depend on the accumulator
     auto fetch = [&](const UnitWalk& uw, float (&pb)[2], uint32_t (&pm)[2]) {
@@ -917,7 +923,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
             pk[2 * s + 1] &= m1;
           }
         }
-        tma_store_wait_read<0>();                 // the slab's previous store has been read out (bulk groups are per thread)
+        const uint32_t slab = slab0 + (uint32_t)sbuf * SLAB_BYTES;
+        uint8_t* slab_gen = slab0_gen + sbuf * SLAB_BYTES;
+        uint8_t* srow = slab_gen + lane * 64;
+        sbuf ^= 1;
+        tma_store_wait_read<1>();                 // the store issued from THIS slab two chunks ago has been read out (groups are per thread, in order)
         __syncwarp();
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -931,6 +941,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         __syncwarp();
         if (do_cs) {
           // rows 2 i, 2 i + 1 of this lane's half share the swizzle term i & 3; half 0 reads the even row first, half 1 the odd one
+          const uint8_t* cs_base = slab_gen + (hh << 10) + ((ww & 3) << 2);
           uint32_t wa[8], wb[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -977,7 +988,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       // flush: per (n tile, chunk) 32 column sums in natural order; the four lane-quarter warps of a column group combine
       // through their idle slabs, one warp per column group issues the reds
       __syncwarp();
-      float* mine = reinterpret_cast<float*>(slab_gen);
+      float* mine = reinterpret_cast<float*>(slab0_gen);
       if (hh == 0) {
 #pragma unroll
         for (int k = 0; k < 2 * CS_TILES; ++k)
@@ -990,7 +1001,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           float t = 0.f;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq)
-            t += reinterpret_cast<const float*>(smem_gen + OFF_STAGING + (cgrp * 4 + qq) * SLAB_BYTES)[k * 32 + lane];
+            t += reinterpret_cast<const float*>(smem_gen + OFF_STG + (cgrp * 4 + qq) * WARP_SLAB)[k * 32 + lane];
           const int cl = (cgrp + 4 * (k & 1)) * 32 + lane;
           const int col = (k >> 1) * bn + cl;
           if (cl < bn && (k >> 1) < p.n_tiles && col < n_valid) atomicAdd(e.colsum + col, t);
