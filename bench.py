@@ -677,7 +677,8 @@ def run_b200(args, cfg):
         line.update(extra)
         if cfgs:
             line["configs"] = cfgs
-        line["allreduce"] = parallel.allreduce_kind()
+        line["allreduce"] = dict(parallel.allreduce_kind(), overlapped_with_backward=bool(os.environ.get("PVAE_OVERLAP", "1") != "0" and world > 1
+                                                                                          and parallel.allreduce_kind()["kind"].startswith("symm")))
         if dp_check is not None:
             line["dp_check"] = dp_check
         if not args.no_cpu_baseline:

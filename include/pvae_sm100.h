@@ -217,6 +217,17 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
 int pvae_symm_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int rank, int world, int64_t offset_elems, int64_t count_elems,
                         int64_t flags_offset_elems, pvae_stream s);
 int64_t pvae_symm_flag_elems(void);
+/* Overlap: arm the training steps of `h` to exchange the range [offset, offset + count) themselves -- on a side stream, with `ctas`
+ * CTAs, as soon as the gradients inside it are complete (world-model step: after the weight gradient of layer 1, i.e. everything but
+ * layer 0; VAE step: after the decoder's backward pass, i.e. the decoder's gradients) -- while the remaining backward GEMMs run on the
+ * other SMs; the step joins the side stream before it finishes (fork / join are stream events: one CUDA graph).  The caller
+ * exchanges the rest (layer 0 / the encoder, plus the loss slots) after the step with pvae_symm_allreduce.  Every rank must arm the
+ * same range.  peer_ptrs_host == NULL switches it off.  pvae_eval_loss and pvae_rollout_step never fork. */
+int pvae_set_exchange(pvae_handle h, const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int rank, int world, int64_t offset_elems,
+                      int64_t count_elems, int64_t flags_offset_elems, int ctas);
+/* The armed exchange on its own (same range, same CTAs), for a rank whose slice of a mini-batch is empty: it runs no training step but
+ * must still take part in the exchange the other ranks' steps perform. */
+int pvae_run_exchange(pvae_handle h, pvae_stream s);
 
 /* --- kernel-level entry (unit tests, bench roofline) ----------------------------------------------------------- */
 /* D[M][N] (fp32, row-major) = A . B^T on the tcgen05 path.

@@ -29,7 +29,7 @@ SYMBOLS = [
     "pvae_sync_weights", "pvae_adam_step", "pvae_workspace_bytes", "pvae_bind_workspace", "pvae_transitions_bytes", "pvae_ingest", "pvae_ingest_episodes",
     "pvae_bind_transitions", "pvae_set_cursor", "pvae_advance_cursor", "pvae_world_step", "pvae_vae_step",
     "pvae_forward", "pvae_gemm_bf16", "pvae_launch_count", "pvae_debug_trace", "pvae_eval_loss", "pvae_noise_counter", "pvae_fc_forward",
-    "pvae_symm_allreduce", "pvae_symm_flag_elems", "pvae_rollout_workspace_bytes", "pvae_bind_rollout_workspace", "pvae_rollout_step", "pvae_set_deterministic",
+    "pvae_symm_allreduce", "pvae_symm_flag_elems", "pvae_rollout_workspace_bytes", "pvae_bind_rollout_workspace", "pvae_rollout_step", "pvae_set_deterministic", "pvae_set_exchange", "pvae_run_exchange",
 ]
 
 
@@ -90,6 +90,8 @@ def load():
     lib.pvae_bind_rollout_workspace.argtypes = [vp, vp, sz, i32]
     lib.pvae_rollout_step.argtypes = [vp, i32, i32, i32, C.POINTER(vp), i64, vp, u64, u64, i32, f32, f32, f32, f32, vp, vp]
     lib.pvae_set_deterministic.argtypes = [vp, i32]
+    lib.pvae_run_exchange.argtypes = [vp, vp]
+    lib.pvae_set_exchange.argtypes = [vp, C.POINTER(u64), u64, i32, i32, i64, i64, i64, i32]
     lib.pvae_symm_allreduce.argtypes = [C.POINTER(u64), u64, i32, i32, i64, i64, i64, vp]
     lib.pvae_symm_flag_elems.restype = i64
     lib.pvae_symm_flag_elems.argtypes = []

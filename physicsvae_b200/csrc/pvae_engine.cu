@@ -120,6 +120,7 @@ struct Device {
   int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
   int fast_epi = 1;       // PVAE_FAST_EPI=0: never use the lean ReLU store / dgrad epilogue (A/B experiments)
   int small_fwd = 1;      // PVAE_SMALL_FWD=0: batches <= 16 of the inference API also take the tensor-core path
+  int reserved_sms = 0;   // SMs the GEMM grids leave free while the gradient exchange of a data-parallel step runs beside them (pvae_set_exchange)
   int deterministic = 0;  // pvae_set_deterministic: no split-K, bias gradients by ordered column sums (run-to-run bit-identical gradients)
   float* det_scratch = nullptr;   // [DET_CHUNKS][cols] partial column sums (the engine's small scratch buffer)
   int det_scratch_elems = 0;
@@ -227,7 +228,7 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
     // CTA (pair), i.e. waves(s) * (k-blocks per unit + the unit's non-overlapped epilogue share).  1024x1024 wgrad at
     // batch 65536: 16 pair tiles on 74 pairs -- 10 splits need 3 waves (72 % busy), 9 splits need 2 (97 %).
     const int tiles = cdiv(p.m_tiles, cluster) * n_tiles;
-    const int slots = dev.sms / cluster;
+    const int slots = (dev.sms - dev.reserved_sms) / cluster;
     const int epi_cost = 2;                       // k-block equivalents of the fp32 red.add epilogue that is not hidden
     const int max_splits = iters < 96 ? iters : 96;
     long best = -1;
@@ -264,7 +265,7 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
     }
   }
   const int units = cdiv(p.m_tiles, cluster) * n_tiles * splits;       // units per CTA (pair)
-  const int slots = dev.sms / cluster;
+  const int slots = (dev.sms - dev.reserved_sms) / cluster;
   const int grid = (units < slots ? units : slots) * cluster;
   // lean epilogue: ReLU store / dgrad whose tiles have no ragged edge and no optional operand (the kernel's FAST block)
   const bool fast = dev.fast_epi && tma && cluster == 2 && e.act == ACT_RELU && (e.type == EPI_STORE || e.type == EPI_DGRAD) &&
@@ -369,6 +370,15 @@ struct pvae_engine {
   bool acc_dirty = false;   // a step was entered but its finalize kernel (which clears acc) was not enqueued
   unsigned int* adam_counter = nullptr;   // finished-blocks counter of adam_net_kernel
   float* small_scratch = nullptr;            // fp32 [2][16][SMALL_SCRATCH_COLS]: z and action rows between the chains of the small-batch forward
+  // overlapped gradient exchange (pvae_set_exchange): the early range is exchanged on a side stream while the last backward GEMMs run
+  struct {
+    bool on = false;
+    SymmArgs args;                 // peers, rank, world, flags; off / count = the early range
+    int ctas = 8;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool forked = false;
+  } xchg;
   unsigned long long* noise_ctr = nullptr;   // device-side Philox offset counter (pvae_noise_counter)
   bool noise_auto = false;
   unsigned long long noise_stride = 1;
@@ -487,12 +497,37 @@ static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, con
   return PVAE_OK;
 }
 
+// ---- overlapped gradient exchange (data parallel): fork = the gradients of the early range are complete once everything launched so
+// far on `st` has run -> exchange them on the side stream with a few CTAs while the remaining GEMMs run on the other SMs; join before
+// the step ends.  Both are stream-ordered events: capturable (fork / join inside one graph).
+static int exchange_fork(pvae_engine* h, cudaStream_t st) {
+  if (!h->xchg.on || h->xchg.forked) return PVAE_OK;
+  CK(cudaEventRecord(h->xchg.ev_fork, st));
+  CK(cudaStreamWaitEvent(h->xchg.side, h->xchg.ev_fork, 0));
+  symm_allreduce_kernel<<<h->xchg.ctas, AR_THREADS, 0, h->xchg.side>>>(h->xchg.args);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->xchg.ev_join, h->xchg.side));
+  h->xchg.forked = true;
+  h->dev.reserved_sms = h->xchg.ctas;              // the GEMMs launched from here on leave that many SMs to the exchange kernel
+  return PVAE_OK;
+}
+static int exchange_join(pvae_engine* h, cudaStream_t st) {
+  h->dev.reserved_sms = 0;
+  if (!h->xchg.forked) return PVAE_OK;
+  h->xchg.forked = false;
+  CK(cudaStreamWaitEvent(st, h->xchg.ev_join, 0));
+  return PVAE_OK;
+}
+
 // ---- backward through one FC stack: g[L-1] (gradient w.r.t. the output layer's pre-activation) is already in place ---
 // train: accumulate dW / db into the bound gradient buffer.  in_epi: if non-null, also produce the gradient w.r.t. the
 // SECOND input segment of layer 0 (z for the decoder, the action for the world model) with this epilogue.
 // in0_epi: likewise for the FIRST input segment (the body state: autoregressive rollouts differentiate through it).
+// fork_after: launch the overlapped gradient exchange (exchange_fork) right after the weight gradient of that layer -- by then the
+// gradients of layers fork_after .. L-1 (weights and biases) are all in the stream.
 static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bool train, const EpiParams* in_epi, cudaStream_t st,
-                        const EpiParams* in0_epi = nullptr) {
+                        const EpiParams* in0_epi = nullptr, int fork_after = -1) {
   const int L = net.n_layers;
   if (train && !net.grad) return fail(PVAE_ERR_STATE, "net has no gradient buffer bound");
   for (int l = L - 1; l >= 0; --l) {
@@ -522,6 +557,7 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
         if (l == 0 && net.k1 && d.M > net.k0) { d.m_gap0 = net.k0; d.m_gap = net.K0pad - net.k0; }   // fused (first | gap | second) input row
       }
       CKR(launch_gemm(h->dev, d, st));
+      if (l == fork_after) CKR(exchange_fork(h, st));
     }
     if (l > 0) {
       GemmDesc d;
@@ -784,6 +820,9 @@ int pvae_destroy(pvae_handle h) {
   if (h->adam_counter) cudaFree(h->adam_counter);
   if (h->noise_ctr) cudaFree(h->noise_ctr);
   if (h->small_scratch) cudaFree(h->small_scratch);
+  if (h->xchg.side) cudaStreamDestroy(h->xchg.side);
+  if (h->xchg.ev_fork) cudaEventDestroy(h->xchg.ev_fork);
+  if (h->xchg.ev_join) cudaEventDestroy(h->xchg.ev_join);
   if (h->dev.cursor) cudaFree(h->dev.cursor);
   delete h;
   return PVAE_OK;
@@ -1022,7 +1061,13 @@ static int world_impl(pvae_handle h, int batch, float s_coeff, float* loss_dev, 
   last.colsum = backward ? wm.grad + wm.gb[L - 1] : nullptr;
   last.loss = h->acc + 2;
   CKR(net_forward(h, wm, in, batch, last, st, backward));
-  if (backward) CKR(net_backward(h, wm, in, batch, true, nullptr, st));
+  if (backward) {
+    // (data parallel: the gradients of layers 1 .. L-1 are exchanged while dgrad L0 / wgrad L0 run, see pvae_set_exchange)
+    const int r = net_backward(h, wm, in, batch, true, nullptr, st, nullptr, wm.n_layers >= 2 ? 1 : -1);
+    const int rj = exchange_join(h, st);
+    if (r != PVAE_OK) return r;
+    CKR(rj);
+  }
   finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, 0.f, 0.f, s_coeff, 0.f, nullptr, 0ull);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
@@ -1118,6 +1163,7 @@ static int vae_impl(pvae_handle h, int batch, const float* eps_dev, uint64_t see
   e.type = EPI_DGRAD; e.act = ACT_LINEAR;
   e.out_f32 = h->dz; e.f32_sm = z; e.f32_sn = 1;
   CKR(net_backward(h, md, md_in, batch, true, &e, st));
+  CKR(exchange_fork(h, st));      // (data parallel: the decoder's gradients are exchanged while the encoder's backward pass runs)
   // reparameterisation + KL backward -> gradient of the encoder's output layer
   {
     const int w = h->te_out;
@@ -1131,7 +1177,12 @@ static int vae_impl(pvae_handle h, int batch, const float* eps_dev, uint64_t see
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (h->dev.deterministic) CKR(det_colsum(h, te.g[Lte - 1], te.act_ld[Lte - 1], batch, w, te.grad + te.gb[Lte - 1], st));
   }
-  CKR(net_backward(h, te, te_in, batch, true, nullptr, st));
+  {
+    const int r = net_backward(h, te, te_in, batch, true, nullptr, st);
+    const int rj = exchange_join(h, st);
+    if (r != PVAE_OK) return r;
+    CKR(rj);
+  }
   }
   finalize_loss_kernel<<<1, 32, 0, st>>>(h->acc, loss_dev, batch, h->da, h->dsb, a_coeff, prior ? kl_coeff : 0.f, 0.f, cyc ? cyc_coeff : 0.f,
                                          (draws && h->noise_auto) ? h->noise_ctr : nullptr, h->noise_stride);
@@ -1340,6 +1391,45 @@ int pvae_rollout_step(pvae_handle h, int phase, int batch, int lookahead, const 
   if (h->ws) carve(h, reinterpret_cast<uint8_t*>(h->ws));      // back to the single-step workspace
   h->tbuf = saved_tbuf; h->tbuf_rows = saved_rows;
   return r;
+}
+
+int pvae_set_exchange(pvae_handle h, const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int rank, int world, int64_t offset_elems,
+                      int64_t count_elems, int64_t flags_offset_elems, int ctas) {
+  if (!h) return fail(PVAE_ERR_INVALID, "null handle");
+  h->xchg.on = false;
+  h->xchg.forked = false;
+  h->dev.reserved_sms = 0;
+  if (!peer_ptrs_host || world < 2) return PVAE_OK;                 // switched off
+  if (world > AR_MAX_RANKS || rank < 0 || rank >= world) return fail(PVAE_ERR_INVALID, "rank %d / world %d outside [2, %d]", rank, world, AR_MAX_RANKS);
+  if (offset_elems < 0 || count_elems <= 0 || (offset_elems & 3) || (count_elems & 3) || (flags_offset_elems & 3))
+    return fail(PVAE_ERR_INVALID, "range / flag block must be multiples of 4 elements");
+  if (ctas < 1 || ctas > AR_CTAS || ctas >= h->dev.sms / 2) return fail(PVAE_ERR_INVALID, "exchange CTAs %d outside [1, %d]", ctas, AR_CTAS);
+  if (!h->xchg.side) {
+    CK(cudaStreamCreateWithFlags(&h->xchg.side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->xchg.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->xchg.ev_join, cudaEventDisableTiming));
+  }
+  SymmArgs& a = h->xchg.args;
+  memset(&a, 0, sizeof(a));
+  for (int p = 0; p < world; ++p) {
+    if (!peer_ptrs_host[p] || (peer_ptrs_host[p] & 15)) return fail(PVAE_ERR_INVALID, "peer pointer %d is null or not 16-byte aligned", p);
+    a.peer[p] = reinterpret_cast<float*>(peer_ptrs_host[p]);
+  }
+  a.mc = reinterpret_cast<float*>(multicast_ptr);
+  a.rank = rank; a.world = world; a.off = offset_elems; a.count = count_elems; a.flags_off = flags_offset_elems;
+  a.scale = 1.f / (float)world;
+  h->xchg.ctas = ctas;
+  h->xchg.on = true;
+  return PVAE_OK;
+}
+
+int pvae_run_exchange(pvae_handle h, pvae_stream s) {
+  if (!h) return fail(PVAE_ERR_INVALID, "null handle");
+  if (!h->xchg.on) return PVAE_OK;
+  symm_allreduce_kernel<<<h->xchg.ctas, AR_THREADS, 0, (cudaStream_t)s>>>(h->xchg.args);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
 }
 
 int pvae_set_deterministic(pvae_handle h, int enable) {

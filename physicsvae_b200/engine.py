@@ -223,6 +223,11 @@ class Engine:
                                                _ptr(self.loss), _stream()))
         return self.loss
 
+    def run_exchange(self):
+        """The armed early-range exchange on its own (a rank with an empty slice of the mini-batch), pvae_run_exchange."""
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.pvae_run_exchange(self._h, _stream()))
+
     def set_deterministic(self, enable=True):
         """Run-to-run bit-identical gradients: no split-K, ordered bias-gradient sums (include/pvae_sm100.h, pvae_set_deterministic)."""
         _abi.check(self.lib.pvae_set_deterministic(self._h, 1 if enable else 0))

@@ -102,11 +102,27 @@ class SymmetricPool(object):
         b = self.buf.data_ptr()
         return t.dtype == torch.float32 and b <= t.data_ptr() and t.data_ptr() + t.numel() * 4 <= b + self.flags_off * 4
 
-    def allreduce_avg_(self, t):
+    def _span(self, t):
         off = (t.data_ptr() - self.buf.data_ptr()) // 4
         count = (t.numel() + 3) // 4 * 4               # pieces of the pool are padded to 16 bytes: the tail words are zeros
         if off % 4 or off + count > self.flags_off:
             raise ValueError("range is not 16-byte aligned inside the symmetric pool")
+        return off, count
+
+    def arm_overlap(self, engine, early):
+        """Let the engine's training steps exchange `early` themselves, beside their last backward GEMMs (pvae_set_exchange);
+        early None switches it off.  Returns True when armed."""
+        from . import _abi
+        ctas = int(os.environ.get("PVAE_OVERLAP_SMS", "8"))
+        if early is None or os.environ.get("PVAE_OVERLAP", "1") == "0" or not self.contains(early):
+            _abi.check(self.lib.pvae_set_exchange(engine._h, None, 0, 0, 0, 0, 0, 0, 0))
+            return False
+        off, count = self._span(early)
+        _abi.check(self.lib.pvae_set_exchange(engine._h, self.peer, self.mc, self.rank, self.world, off, count, self.flags_off, ctas))
+        return True
+
+    def allreduce_avg_(self, t):
+        off, count = self._span(t)
         from . import _abi
         _abi.check(self.lib.pvae_symm_allreduce(self.peer, self.mc, self.rank, self.world, off, count, self.flags_off,
                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
@@ -141,6 +157,11 @@ def symmetric_pool_factory():
         _symm_note.update(kind="symm-multimem" if pool.mc else "symm-p2p", why="multicast available" if pool.has_multicast else "no multicast binding")
         return pool.view
     return factory
+
+
+def pool_of(t):
+    """The symmetric pool a tensor lives in, or None."""
+    return next((p for p in reversed(_symm_pools) if p.contains(t)), None)
 
 
 def allreduce_kind():

@@ -446,17 +446,18 @@ class PhysicsVAE(TorchModelV2, nn.Module):
         spec = {name: self.net(name).layer_spec() for name in NET_NAMES}
         eng = Engine(self.dim_state_body, self.dim_action, self._task_encoder_output_dim, spec,
                      latent_prior=bool(self._latent_prior_type), precision=want_prec, max_batch=want_batch, device=p0.device.index)
-        # One gradient pool for the whole model, laid out [world model | loss slots | task encoder | motor decoder | value branch]
+        # One gradient pool for the whole model, laid out [motor decoder | task encoder | loss slots | world model | value branch]
         # (every piece 16-byte aligned): what a training step has to exchange between data-parallel ranks -- the gradients of
-        # the nets it trains plus the loss slots -- is ONE contiguous range in either phase (reduce_range()).
+        # the nets it trains plus the loss slots -- is ONE contiguous range in either phase (reduce_range()), and so are the part
+        # that is complete early in the backward pass and the rest (reduce_ranges()).
         al = lambda k: (k + 3) // 4 * 4
-        order = ("world_model", "task_encoder", "motor_decoder", "value_branch")
+        order = ("motor_decoder", "task_encoder", "world_model", "value_branch")
         sizes = {name: eng.grad_elems(name) for name in NET_NAMES}
         offs, cur = {}, 0
         for name in order:
             offs[name] = cur
             cur += al(sizes[name])
-            if name == "world_model":
+            if name == "task_encoder":
                 loss_off = cur
                 cur += al(_abi.PVAE_LOSS_SLOTS)
         pool = self._grad_pool = self._pool_alloc(cur, p0.device)
@@ -509,12 +510,31 @@ class PhysicsVAE(TorchModelV2, nn.Module):
         return torch.zeros(n, dtype=torch.float32, device=device)
 
     def reduce_range(self, world_phase):
-        """The contiguous slice of the gradient pool a data-parallel step all-reduces: [world model | loss slots] in the world
-        phase, [loss slots | task encoder | motor decoder] in the VAE phase."""
+        """The contiguous slice of the gradient pool a data-parallel step all-reduces: [loss slots | world model] in the world
+        phase, [motor decoder | task encoder | loss slots] in the VAE phase."""
         o, sz = self._pool_off, self._pool_sizes
         if world_phase:
-            return self._grad_pool[o["world_model"]:o["loss"] + _abi.PVAE_LOSS_SLOTS]
-        return self._grad_pool[o["loss"]:o["motor_decoder"] + sz["motor_decoder"]]
+            return self._grad_pool[o["loss"]:o["world_model"] + sz["world_model"]]
+        return self._grad_pool[o["motor_decoder"]:o["loss"] + _abi.PVAE_LOSS_SLOTS]
+
+    def reduce_ranges(self, world_phase):
+        """reduce_range() split in two for the overlapped exchange (include/pvae_sm100.h, pvae_set_exchange): (early, late).
+        early: complete while backward GEMMs are still running -- world phase: the world model's layers 1 .. L-1 (everything behind
+        layer 0's [W0 | b0]); VAE phase: the motor decoder.  late: the rest plus the loss slots -- [loss | W0 | b0] / [task encoder |
+        loss].  early is None when the split is not 16-byte aligned or the net has a single layer."""
+        o, sz = self._pool_off, self._pool_sizes
+        if world_phase:
+            layers = self._world_model.fc_layers()
+            if len(layers) < 2:
+                return None, self.reduce_range(True)
+            l0 = layers[0].linear
+            cut = o["world_model"] + l0.weight.numel() + l0.bias.numel()
+            end = o["world_model"] + sz["world_model"]
+            if cut % 4 or cut >= end:
+                return None, self.reduce_range(True)
+            return self._grad_pool[cut:end], self._grad_pool[o["loss"]:cut]
+        return (self._grad_pool[o["motor_decoder"]:o["motor_decoder"] + sz["motor_decoder"]],
+                self._grad_pool[o["task_encoder"]:o["loss"] + _abi.PVAE_LOSS_SLOTS])
 
     def flat_params(self, name):
         return self._flat[name][0]

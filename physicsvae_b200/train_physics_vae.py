@@ -303,6 +303,24 @@ class TrainModel(torch_models.TrainModel):
     def _engine_changed(self, eng):
         if self.config.get("deterministic"):
             eng.set_deterministic(True)             # run-to-run bit-identical gradients (no split-K, ordered bias-gradient sums)
+        self._arm_exchange(eng)
+
+    def _arm_exchange(self, eng=None):
+        """Data parallel over a symmetric gradient pool: let the engine exchange the part of the gradients that is complete early
+        in the backward pass on a side stream, beside the remaining GEMMs; `_reduce` then exchanges only the rest."""
+        had = getattr(self, "_early", None) is not None
+        self._early = None
+        eng = eng or self.engine
+        if parallel.world_size() == 1 or not hasattr(self, "world_phase"):
+            if had:
+                pool = parallel.pool_of(self.model.reduce_range(True))
+                if pool is not None:
+                    pool.arm_overlap(eng, None)
+            return
+        early, late = self.model.reduce_ranges(self.world_phase)
+        pool = parallel.pool_of(late)
+        if pool is not None and pool.arm_overlap(eng, early):
+            self._early = early
 
     def sync_replicas(self):
         """Data-parallel ranks must hold the same parameters: every rank builds its model from its own RNG stream, so the
@@ -318,6 +336,8 @@ class TrainModel(torch_models.TrainModel):
         self.s_rec_coeff = 1.0 if world else self.config.get("world_model_s_rec_coeff")
         self.vae_cycle_coeff = 0.0 if world else self.config.get("vae_cycle_coeff")
         self.world_phase = bool(world)
+        if getattr(self, "model", None) is not None and getattr(self.model, "_engine", None) is not None:
+            self._arm_exchange()                     # the early / late split of the exchanged range follows the phase
 
     def load_dataset(self, file):
         num_data = args.num_data if args is not None else self.config.get("num_data")
@@ -378,6 +398,9 @@ class TrainModel(torch_models.TrainModel):
         """Forward + loss (+ backward when `train`) for the `n` rows at the device cursor; loss coefficients weighted by `w`
         (n_rank * R / n, see parallel.py).  The Philox offset is (device-side noise counter) + rank."""
         eng = self.engine
+        self._forked = False
+        if self._early is not None and parallel.world_size() == 1:
+            self._arm_exchange(eng)                  # (the ranks stopped sharing this trainer -- replica mode: nobody to exchange with)
         bufs = self._buffers[self._bound[1]][0]
         if isinstance(bufs, list) and len(bufs) > 1:
             # lookahead > 1: autoregressive rollout, gradients through time (pvae_rollout_step); the test pass runs the same call and
@@ -394,6 +417,7 @@ class TrainModel(torch_models.TrainModel):
                 raise ValueError("world phase needs s_rec_coeff > 0")
             if train:
                 eng.world_step(n, s_coeff=self.s_rec_coeff * w)
+                self._forked = self._early is not None       # (the step exchanged the early range itself)
             else:
                 eng.eval_loss(n, True, s_coeff=self.s_rec_coeff * w)
         else:
@@ -404,6 +428,7 @@ class TrainModel(torch_models.TrainModel):
                       a_coeff=self.a_rec_coeff * w, kl_coeff=kl * w, cyc_coeff=self.vae_cycle_coeff * w)
             if train:
                 eng.vae_step(n, **kw)
+                self._forked = self._early is not None
             else:
                 eng.eval_loss(n, False, **kw)
         if w != 1.0:
@@ -413,7 +438,13 @@ class TrainModel(torch_models.TrainModel):
         """The step's only collective: ONE averaging all-reduce over [gradients of the trained nets | loss slots] -- a single
         contiguous range of the model's gradient pool (PhysicsVAE.reduce_range)."""
         if parallel.world_size() > 1:
-            parallel.allreduce_avg_([self.model.reduce_range(self.world_phase) if train else self.engine.loss])
+            if not train:
+                rng = self.engine.loss
+            elif getattr(self, "_forked", False):
+                rng = self.model.reduce_ranges(self.world_phase)[1]      # the engine step exchanged the early part beside its GEMMs
+            else:
+                rng = self.model.reduce_range(self.world_phase)
+            parallel.allreduce_avg_([rng])
 
     def batch_loss(self, lo, hi, eps=None, train=True):
         """Forward + loss + backward for rows [lo, hi) of the resident buffer; gradients land in `.grad` (all-reduced when
@@ -429,9 +460,13 @@ class TrainModel(torch_models.TrainModel):
             eng.set_cursor(s)
             self._engine_step(n, w, eps=eps, train=train)
         else:
+            self._forked = False
             if train:
                 for name in self._nets():
                     self.model.flat_grads(name).zero_()
+                if self._early is not None:          # the other ranks' steps exchange the early range themselves: take part
+                    eng.run_exchange()
+                    self._forked = True
             eng.loss.zero_()
         self._reduce(train)
         return eng.loss[0].clone()
