@@ -543,6 +543,21 @@ def run_b200(args, cfg):
         dp_check["replicas_identical_after_timed_steps"] = replicas_identical
         dp_check["ok"] = dp_check["ok"] and replicas_identical
     gpu_launches_timed = int(main["launches_per_step"] * steps)
+    exchange_us = None
+    if world > 1:
+        # the gradient exchange on its own: the full [gradients | loss] range of the headline phase, 50 back-to-back calls
+        rng_ = tr.model.reduce_range(phase == "world")
+        for _ in range(5):
+            parallel.allreduce_avg_([rng_])
+        barrier(world)
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for _ in range(50):
+            parallel.allreduce_avg_([rng_])
+        x1.record()
+        barrier(world)
+        exchange_us = {"us_per_call": max_over_ranks(x0.elapsed_time(x1), dev, world) / 50 * 1e3, "bytes": int(rng_.numel() * 4),
+                       "what": "averaging exchange of the whole [gradients | loss] range of the %s phase, alone, back to back" % phase}
 
     # ---- end-to-end legs (world phase of the headline workload unless --phase vae) ------------------------------------------
     # (1) "e2e": every step uploads ITS inputs from pinned host memory and reads the loss back.  The mini-batch travels in the
@@ -677,7 +692,7 @@ def run_b200(args, cfg):
         line.update(extra)
         if cfgs:
             line["configs"] = cfgs
-        line["allreduce"] = dict(parallel.allreduce_kind(), overlapped_with_backward=bool(os.environ.get("PVAE_OVERLAP", "1") != "0" and world > 1
+        line["allreduce"] = dict(parallel.allreduce_kind(), exchange=exchange_us, overlapped_with_backward=bool(os.environ.get("PVAE_OVERLAP", "0") == "1" and world > 1
                                                                                           and parallel.allreduce_kind()["kind"].startswith("symm")))
         if dp_check is not None:
             line["dp_check"] = dp_check

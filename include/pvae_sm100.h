@@ -217,7 +217,8 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
 int pvae_symm_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, int rank, int world, int64_t offset_elems, int64_t count_elems,
                         int64_t flags_offset_elems, pvae_stream s);
 int64_t pvae_symm_flag_elems(void);
-/* Overlap: arm the training steps of `h` to exchange the range [offset, offset + count) themselves -- on a side stream, with `ctas`
+/* Overlap (experimental, the Python trainer arms it only with PVAE_OVERLAP=1: it pays at N = 2 and loses at N = 8):
+ * arm the training steps of `h` to exchange the range [offset, offset + count) themselves -- on a side stream, with `ctas`
  * CTAs, as soon as the gradients inside it are complete (world-model step: after the weight gradient of layer 1, i.e. everything but
  * layer 0; VAE step: after the decoder's backward pass, i.e. the decoder's gradients) -- while the remaining backward GEMMs run on the
  * other SMs; the step joins the side stream before it finishes (fork / join are stream events: one CUDA graph).  The caller

@@ -107,6 +107,24 @@ struct GemmDesc {
   GemmDesc() { memset(&epi, 0, sizeof(epi)); }
 };
 
+// L2-aware traversal: the big batch-indexed tensors of a step (134 MB each at batch 65536) do not fit the 126 MB L2, but
+// most of one does.  A GEMM that walks the batch in the direction OPPOSITE to the last kernel that touched its main
+// batch-indexed operand starts on the rows that kernel touched last, i.e. the ones still resident.  The table remembers, per
+// buffer, the direction of the last walk; the launch sequence of a step is static, so a captured graph freezes a
+// consistent zig-zag.  One table per engine (Device): pointers of a destroyed engine cannot alias a later one's.  (Order never changes results: tiles are independent, weight gradients accumulate with atomics.)
+struct WalkTable {
+  static constexpr int N = 64;
+  const void* ptr[N];
+  int dir[N];
+  int n = 0;
+  int last(const void* p) const { for (int i = 0; i < n; ++i) if (ptr[i] == p) return dir[i]; return -1; }
+  void set(const void* p, int d) {
+    if (!p) return;
+    for (int i = 0; i < n; ++i) if (ptr[i] == p) { dir[i] = d; return; }
+    if (n < N) { ptr[n] = p; dir[n] = d; ++n; }
+  }
+};
+
 struct Device {
   int id = 0;
   int sms = 148;
@@ -126,26 +144,8 @@ struct Device {
   int det_scratch_elems = 0;
   int32_t* cursor = nullptr;   // device int: first row of the current mini-batch
   bool attr_set = false;
+  mutable WalkTable walk;
 };
-
-// L2-aware traversal: the big batch-indexed tensors of a step (134 MB each at batch 65536) do not fit the 126 MB L2, but
-// most of one does.  A GEMM that walks the batch in the direction OPPOSITE to the last kernel that touched its main
-// batch-indexed operand starts on the rows that kernel touched last, i.e. the ones still resident.  The table remembers, per
-// buffer, the direction of the last walk; the launch sequence of a step is static, so a captured graph freezes a
-// consistent zig-zag.  (Order never changes results: tiles are independent, weight gradients accumulate with atomics.)
-struct WalkTable {
-  static constexpr int N = 64;
-  const void* ptr[N];
-  int dir[N];
-  int n = 0;
-  int last(const void* p) const { for (int i = 0; i < n; ++i) if (ptr[i] == p) return dir[i]; return -1; }
-  void set(const void* p, int d) {
-    if (!p) return;
-    for (int i = 0; i < n; ++i) if (ptr[i] == p) { dir[i] = d; return; }
-    if (n < N) { ptr[n] = p; dir[n] = d; ++n; }
-  }
-};
-static WalkTable g_walk;
 
 static int batch_direction(const Device& dev, const GemmDesc& d) {
   if (!dev.snake) return 0;
@@ -153,16 +153,16 @@ static int batch_direction(const Device& dev, const GemmDesc& d) {
   // the wider one decides
   const void* main_in = d.A[0].base;
   if (d.split && d.B.width >= d.A[0].width + (d.nseg > 1 ? d.A[1].width : 0)) main_in = d.B.base;   // (tie: the gradient is the fresher one)
-  const int prev = g_walk.last(main_in);
+  const int prev = dev.walk.last(main_in);
   const int dir = prev < 0 ? 0 : 1 - prev;
-  g_walk.set(d.A[0].base, dir);
-  if (d.nseg > 1) g_walk.set(d.A[1].base, dir);
-  if (d.split) g_walk.set(d.B.base, dir);
-  g_walk.set(d.epi.out, dir);
-  g_walk.set(d.epi.out2, dir);
-  if (d.epi.type != EPI_WGRAD) g_walk.set(d.epi.out_f32, dir);
-  g_walk.set(d.epi.aux, dir);
-  g_walk.set(d.epi.add, dir);
+  dev.walk.set(d.A[0].base, dir);
+  if (d.nseg > 1) dev.walk.set(d.A[1].base, dir);
+  if (d.split) dev.walk.set(d.B.base, dir);
+  dev.walk.set(d.epi.out, dir);
+  dev.walk.set(d.epi.out2, dir);
+  if (d.epi.type != EPI_WGRAD) dev.walk.set(d.epi.out_f32, dir);
+  dev.walk.set(d.epi.aux, dir);
+  dev.walk.set(d.epi.add, dir);
   return dir;
 }
 

@@ -286,6 +286,8 @@ class TrainModel(_TrainableBase):
 
     # ---- the SGD loop (torch_models.py:131-161) -----------------------------------------------------------------------
     def step(self):
+        import time as _time
+        t_start = _time.perf_counter()
         self.iter += 1
         self.model.train()
         self._bind("train")
@@ -297,6 +299,7 @@ class TrainModel(_TrainableBase):
         for lo in range(n_full * bs, n, bs):            # the short last batch (or everything, without graphs): eager launches
             self._loss_acc += self.train_batch(lo, min(lo + bs, n))
         mean_train_loss = float(self._loss_acc.item()) / len(self.train_loader)
+        train_seconds = _time.perf_counter() - t_start              # (the .item() above waited for the epoch's last kernel)
 
         mean_test_loss = 0.0
         if self.test_loader:
@@ -310,7 +313,9 @@ class TrainModel(_TrainableBase):
 
         if self.lr_scheduler:
             self.lr_scheduler.step()
-        return {"mean_train_loss": mean_train_loss, "mean_test_loss": mean_test_loss}
+        # the reference's two keys (torch_models.py:160-161) + throughput of the training pass
+        return {"mean_train_loss": mean_train_loss, "mean_test_loss": mean_test_loss,
+                "transitions_per_sec": n / max(train_seconds, 1e-9), "train_seconds": train_seconds}
 
     def train_batch(self, lo, hi):
         """zero_grad -> compute_loss -> backward -> [all-reduce] -> Adam, for rows [lo, hi) of the resident buffer."""

@@ -26,7 +26,7 @@ for m in $MODES; do
   case $m in
     symm) run symm PVAE_SYMM_AR=1 NCCL_DEBUG=WARN ;;
     nccl) run nccl PVAE_SYMM_AR=0 NCCL_DEBUG=WARN ;;
-    nooverlap) run nooverlap PVAE_SYMM_AR=1 PVAE_OVERLAP=0 NCCL_DEBUG=WARN ;;
+    overlap) run overlap PVAE_SYMM_AR=1 PVAE_OVERLAP=1 NCCL_DEBUG=WARN ;;
     multimem) run multimem PVAE_SYMM_AR=1 PVAE_SYMM_MULTIMEM=1 NCCL_DEBUG=WARN ;;
   esac
 done
