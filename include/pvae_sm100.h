@@ -89,6 +89,11 @@ int pvae_destroy(pvae_handle h);
  * nets that are never trained).  replaces: model.parameters() / .grad consumed by torch.optim.Adam (torch_models.py:119-122) */
 int pvae_bind_net(pvae_handle h, int net, const float* const* W_dev, const float* const* b_dev, float* grad_flat_dev);
 int64_t pvae_net_grad_elems(pvae_handle h, int net);
+/* Parameters of the activations: rllib's Swish (ray 1.11, what get_activation_fn("swish") returns, rllib_model_torch.py:33-35) computes
+ * x * sigmoid(beta x) with beta a trainable scalar per layer.  beta_dev[l] (fp32, PVAE_MAX_LAYERS entries) = beta of layer l's activation
+ * (entries of non-swish layers are ignored); dbeta_dev[l] receives d loss / d beta from the training steps (zeroed by them; may be
+ * NULL).  Not bound: beta = 1. */
+int pvae_bind_act_params(pvae_handle h, int net, const float* beta_dev, float* dbeta_dev);
 
 /* refresh the bf16 (hi/lo) shadow copies of the fp32 masters of every net whose bit is set in net_mask
  * (after load_state_dict or optimizer.step()).  */

@@ -32,8 +32,9 @@ def gen_layers(width, depth, out_size="output", act_hidden="relu", act_out="line
     return layers
 
 
-def activation(name, x):
-    """get_activation_fn, rllib_model_torch.py:30-46."""
+def activation(name, x, beta=None):
+    """get_activation_fn, rllib_model_torch.py:30-46.  swish = ray 1.11's rllib Swish: x * sigmoid(beta * x), beta a trainable scalar
+    initialised to 1.0 (ray/rllib/utils/torch_ops.py; restated in oracle/ref_stub)."""
     if name in ("linear", None):
         return x
     if name == "relu":
@@ -45,7 +46,7 @@ def activation(name, x):
     if name == "elu":
         return F.elu(x)
     if name in ("swish", "silu"):
-        return x * torch.sigmoid(x)
+        return x * torch.sigmoid(x if beta is None else beta * x)
     raise ValueError("Unknown activation ({})!".format(name))
 
 
@@ -72,6 +73,8 @@ def _init_fc(prefix, size_in, size_out, layers, params, acts):
         wk, bk = "%s._model.%d._model.0.weight" % (prefix, i), "%s._model.%d._model.0.bias" % (prefix, i)
         params[wk] = w.clone()
         params[bk] = torch.zeros(out)
+        if l["activation"] in ("swish", "silu"):            # rllib's Swish module sits at index 1 of the SlimFC's Sequential
+            params["%s._model.%d._model.1._beta" % (prefix, i)] = torch.tensor(1.0)
         names.append((wk, bk, l["activation"]))
         prev = out
     acts[prefix] = names
@@ -120,7 +123,7 @@ class OracleModel:
     def _fc(self, net, x):
         """FC.forward (rllib_model_torch.py:274-275): Linear + bias + activation per layer."""
         for wk, bk, act in self.layers[net]:
-            x = activation(act, F.linear(x, self.params[wk], self.params[bk]))
+            x = activation(act, F.linear(x, self.params[wk], self.params[bk]), self.params.get(wk.replace("._model.0.weight", "._model.1._beta")))
         return x
 
     def forward_encoder(self, obs, eps=None):

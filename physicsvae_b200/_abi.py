@@ -29,7 +29,7 @@ SYMBOLS = [
     "pvae_sync_weights", "pvae_adam_step", "pvae_workspace_bytes", "pvae_bind_workspace", "pvae_transitions_bytes", "pvae_ingest", "pvae_ingest_episodes",
     "pvae_bind_transitions", "pvae_set_cursor", "pvae_advance_cursor", "pvae_world_step", "pvae_vae_step",
     "pvae_forward", "pvae_gemm_bf16", "pvae_launch_count", "pvae_debug_trace", "pvae_eval_loss", "pvae_noise_counter", "pvae_fc_forward",
-    "pvae_symm_allreduce", "pvae_symm_flag_elems", "pvae_rollout_workspace_bytes", "pvae_bind_rollout_workspace", "pvae_rollout_step", "pvae_set_deterministic", "pvae_set_exchange", "pvae_run_exchange",
+    "pvae_symm_allreduce", "pvae_symm_flag_elems", "pvae_rollout_workspace_bytes", "pvae_bind_rollout_workspace", "pvae_rollout_step", "pvae_set_deterministic", "pvae_set_exchange", "pvae_run_exchange", "pvae_bind_act_params",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
     lib.pvae_create.argtypes = [C.POINTER(vp), C.POINTER(ModelDesc), i32]
     lib.pvae_destroy.argtypes = [vp]
     lib.pvae_bind_net.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), vp]
+    lib.pvae_bind_act_params.argtypes = [vp, i32, vp, vp]
     lib.pvae_net_grad_elems.restype = i64
     lib.pvae_net_grad_elems.argtypes = [vp, i32]
     lib.pvae_sync_weights.argtypes = [vp, u32, vp]

@@ -326,6 +326,8 @@ struct Net {
   uint32_t* mask[PVAE_MAX_LAYERS];   // ReLU sign bits of act[l], [mask_ld[l] words of 32 columns][max_batch]
   int act_ld[PVAE_MAX_LAYERS];
   int mask_ld[PVAE_MAX_LAYERS];
+  const float* beta = nullptr;      // [n_layers] fp32: beta of layer l's swish activation (pvae_bind_act_params), null = 1 everywhere
+  float* dbeta = nullptr;           // [n_layers] fp32 gradient accumulators, or null
   bool bound = false;
   bool generic = false;        // input widths given explicitly (stand-alone FC): usable through pvae_fc_forward only
 };
@@ -492,6 +494,7 @@ static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, con
       d.epi = last;
       d.epi.act = net.acts[l]; d.epi.bias = net.b[l];
     }
+    if (net.acts[l] == ACT_SWISH && net.beta) d.epi.act_param = net.beta + l;
     CKR(launch_gemm(h->dev, d, st));
   }
   return PVAE_OK;
@@ -573,6 +576,10 @@ static int net_backward(pvae_engine* h, Net& net, const NetIO& in, int batch, bo
       d.epi.mask = net.mask[l - 1]; d.epi.mask_ld = h->max_batch;
       set_out(d.epi, h, net.g[l - 1], net.act_ld[l - 1]);
       d.epi.colsum = train ? net.grad + net.gb[l - 1] : nullptr;
+      if (net.acts[l - 1] == ACT_SWISH && net.beta) {
+        d.epi.act_param = net.beta + (l - 1);
+        d.epi.act_grad = (train && net.dbeta) ? net.dbeta + (l - 1) : nullptr;
+      }
       CKR(launch_gemm(h->dev, d, st));
     } else if (in_epi) {
       GemmDesc d;
@@ -628,6 +635,7 @@ static int small_chain(pvae_engine* h, Net& net, int batch, const float* in0, in
   int width = 0;
   for (int l = 0; l < net.n_layers; ++l) {
     sn.L[l].W = net.Wsh[l]; sn.L[l].ps = net.wsh_ps[l]; sn.L[l].bias = net.b[l];
+    sn.L[l].act_param = (net.acts[l] == ACT_SWISH && net.beta) ? net.beta + l : nullptr;
     sn.L[l].out = net.out_dims[l]; sn.L[l].kpad = net.kpad[l]; sn.L[l].act = net.acts[l];
     width = net.kpad[l] > width ? net.kpad[l] : width;
     width = net.out_dims[l] > width ? net.out_dims[l] : width;
@@ -841,6 +849,13 @@ int pvae_bind_net(pvae_handle h, int net_id, const float* const* W_dev, const fl
   return PVAE_OK;
 }
 
+int pvae_bind_act_params(pvae_handle h, int net_id, const float* beta_dev, float* dbeta_dev) {
+  if (!h || net_id < 0 || net_id >= PVAE_NUM_NETS) return fail(PVAE_ERR_INVALID, "bad handle / net id");
+  h->nets[net_id].beta = beta_dev;
+  h->nets[net_id].dbeta = beta_dev ? dbeta_dev : nullptr;
+  return PVAE_OK;
+}
+
 int64_t pvae_net_grad_elems(pvae_handle h, int net_id) {
   if (!h || net_id < 0 || net_id >= PVAE_NUM_NETS) return -1;
   return h->nets[net_id].grad_elems;
@@ -1045,6 +1060,7 @@ static int world_impl(pvae_handle h, int batch, float s_coeff, float* loss_dev, 
   if (backward) {
     if (!wm.grad) return fail(PVAE_ERR_STATE, "world model has no gradient buffer bound");
     CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
+    if (wm.dbeta) CK(cudaMemsetAsync(wm.dbeta, 0, PVAE_MAX_LAYERS * sizeof(float), st));
   }
   if (h->acc_dirty) CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));   // only after a step that failed half-way: finalize clears them
   h->acc_dirty = true;
@@ -1099,6 +1115,8 @@ static int vae_impl(pvae_handle h, int batch, const float* eps_dev, uint64_t see
     if (!te.grad || !md.grad) return fail(PVAE_ERR_STATE, "encoder / decoder have no gradient buffers bound");
     CK(cudaMemsetAsync(te.grad, 0, te.grad_elems * sizeof(float), st));
     CK(cudaMemsetAsync(md.grad, 0, md.grad_elems * sizeof(float), st));
+    if (te.dbeta) CK(cudaMemsetAsync(te.dbeta, 0, PVAE_MAX_LAYERS * sizeof(float), st));
+    if (md.dbeta) CK(cudaMemsetAsync(md.dbeta, 0, PVAE_MAX_LAYERS * sizeof(float), st));
   }
   const bool draws = prior && noise && !eps_dev;     // the step consumes the Philox stream
   if (h->acc_dirty) CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));   // only after a step that failed half-way: finalize clears them
@@ -1238,10 +1256,15 @@ static int rollout_impl(pvae_handle h, int phase, int batch, int L, const void* 
   const int z = h->z, Lte = te.n_layers, Lmd = md.n_layers, Lwm = wm.n_layers;
   const float invL = 1.f / (float)L;
   if (world) { a_coeff = 0.f; kl_coeff = 0.f; cyc_coeff = 0.f; } else { s_coeff = 0.f; }
-  if (train_wm) CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
+  if (train_wm) {
+    CK(cudaMemsetAsync(wm.grad, 0, wm.grad_elems * sizeof(float), st));
+    if (wm.dbeta) CK(cudaMemsetAsync(wm.dbeta, 0, PVAE_MAX_LAYERS * sizeof(float), st));
+  }
   if (train_vae) {
     CK(cudaMemsetAsync(te.grad, 0, te.grad_elems * sizeof(float), st));
     CK(cudaMemsetAsync(md.grad, 0, md.grad_elems * sizeof(float), st));
+    if (te.dbeta) CK(cudaMemsetAsync(te.dbeta, 0, PVAE_MAX_LAYERS * sizeof(float), st));
+    if (md.dbeta) CK(cudaMemsetAsync(md.dbeta, 0, PVAE_MAX_LAYERS * sizeof(float), st));
   }
   if (h->acc_dirty) CK(cudaMemsetAsync(h->acc, 0, 4 * sizeof(double), st));
   h->acc_dirty = true;

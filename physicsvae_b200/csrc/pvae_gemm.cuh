@@ -76,6 +76,8 @@ struct EpiParams {
   uint32_t* mask;                  // ReLU sign bits [32-column word][mask_ld rows] (1 bit per output): written by EPI_STORE, read by EPI_DGRAD
   int64_t mask_ld;                 // rows per 32-column word plane (the workspace batch capacity)
   double* loss;                    // EPI_MSE: sum of squared errors accumulated here
+  const float* act_param;          // swish: beta of x * sigmoid(beta x) (device scalar, rllib's Swish parameter); null = 1
+  float* act_grad;                 // EPI_DGRAD + swish: d loss / d beta accumulated here (null: not wanted)
 };
 
 struct GemmParams {
@@ -284,22 +286,27 @@ template <int CG> __device__ __forceinline__ uint32_t umma_idesc(int n, int a_ma
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
 // ------------------------------------------------------------------------------------------------
-template <int act> __device__ __forceinline__ float act_fwd(float v) {
+template <int act> __device__ __forceinline__ float act_fwd(float v, float beta = 1.f) {
   switch (act) {
     case ACT_RELU:    return fmaxf(v, 0.f);
     case ACT_TANH:    return tanhf(v);
     case ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
     case ACT_ELU:     return v > 0.f ? v : expm1f(v);
-    case ACT_SWISH:   return v / (1.f + __expf(-v));
+    case ACT_SWISH:   return v / (1.f + __expf(-beta * v));
     default:          return v;
   }
+}
+// d/d beta of x * sigmoid(beta x) = x^2 s (1 - s), s = sigmoid(beta x)  (x: the stored pre-activation)
+__device__ __forceinline__ float swish_dbeta(float x, float beta) {
+  const float sg = 1.f / (1.f + __expf(-beta * x));
+  return x * x * sg * (1.f - sg);
 }
 // derivative of the activation expressed through what the forward pass stored: its OUTPUT y -- except for swish, whose
 // derivative is not a function of the output: the forward pass keeps the PRE-activation x of swish layers (in the layer's
 // gradient buffer, which the backward pass overwrites in place), and y here is that x:  d/dx x.s(x) = s(x) (1 + x (1 - s(x)))
-template <int act> __device__ __forceinline__ float act_bwd_from_out(float y) {
+template <int act> __device__ __forceinline__ float act_bwd_from_out(float y, float beta = 1.f) {
   switch (act) {
-    case ACT_SWISH:   { const float sg = 1.f / (1.f + __expf(-y)); return sg * (1.f + y * (1.f - sg)); }
+    case ACT_SWISH:   { const float sg = 1.f / (1.f + __expf(-beta * y)); return sg * (1.f + beta * y * (1.f - sg)); }
     case ACT_RELU:    return y > 0.f ? 1.f : 0.f;
     case ACT_TANH:    return 1.f - y * y;
     case ACT_SIGMOID: return y * (1.f - y);
@@ -470,7 +477,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float (&v)[32], const float* bias_s, int row, bool row_ok,
-                                               int col0, int nv, int row0, int lane, double& loss_local) {
+                                               int col0, int nv, int row0, int lane, double& loss_local, float beta, float& dbeta_local) {
   if (EPI == EPI_WGRAD) {
     if (row_ok) {
       float* dst = e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn;
@@ -498,7 +505,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float (&v)[32
     if (ACT == ACT_SWISH && e.out2 && row_ok)      // swish: keep the pre-activation for the backward pass
       store_row32(e.out2 + (int64_t)row * e.out2_ld + col0, e.out2_ps, e.out2_planes, nv, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i], beta);
     if (row_ok) {
       if (e.out_f32) store_f32_row32(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn, e.f32_sn, nv, v);
       if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
@@ -539,8 +546,12 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float (&v)[32
       if (ACT != ACT_LINEAR) {
         float y[32];
         load_row32(e.aux + (int64_t)row * e.aux_ld + col0, e.aux_ps, e.aux_planes, nv, y);
+        if (ACT == ACT_SWISH && e.act_grad) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= act_bwd_from_out<ACT>(y[i]);
+          for (int i = 0; i < 32; ++i) dbeta_local += v[i] * swish_dbeta(y[i], beta);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= act_bwd_from_out<ACT>(y[i], beta);
       }
       if (e.out_f32) store_f32_row32(e.out_f32 + (int64_t)row * e.f32_sm + (int64_t)col0 * e.f32_sn, e.f32_sn, nv, v);
       if (e.out) store_row32(e.out + (int64_t)row * e.out_ld + col0, e.out_ps, e.out_planes, nv, v);
@@ -1021,6 +1032,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     const float* bias = (EPI == EPI_STORE || EPI == EPI_MSE) ? e.bias : nullptr;
     int acc = 0; uint32_t acc_phase = 0;
     double loss_local = 0.0;
+    const float beta = (ACT == ACT_SWISH && e.act_param) ? __ldg(e.act_param) : 1.f;
+    float dbeta_local = 0.f;
     uint32_t aux_phase = 0;
     const bool cs_mma = p.cs_mma > 0;              // see the column-sum code below
     constexpr int CS_TILES = 4;                   // N tiles whose bias-gradient column sums are kept in registers
@@ -1100,7 +1113,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          epilogue_chunk<EPI, ACT>(e, v, bias_s, row, row_ok, col0, nv, row0, lane, loss_local);
+          epilogue_chunk<EPI, ACT>(e, v, bias_s, row, row_ok, col0, nv, row0, lane, loss_local, beta, dbeta_local);
         }
       } else {
         // Each warp stages its 32 x 32 bf16 chunk in a private 2 KiB slab and stores it with one TMA instruction -- no
@@ -1155,7 +1168,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
           if (EPI == EPI_STORE) {
             if (ACT != ACT_RELU || e.out_f32 != nullptr || nv < 32) {   // (warp-uniform) general path
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i], beta);
               if (nv < 32) {                      // ragged last chunk: keep the padding columns of the mask / slab zero
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = (i < nv) ? v[i] : 0.f;
@@ -1221,8 +1234,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
                 for (int g = 0; g < 4; ++g) {
                   float y[8];
                   aux_piece(g, y);
+                  if (ACT == ACT_SWISH && e.act_grad) {      // (rows / columns outside the tensor hold zero pre-activations: no contribution)
 #pragma unroll
-                  for (int t = 0; t < 8; ++t) v[g * 8 + t] *= act_bwd_from_out<ACT>(y[t]);
+                    for (int t = 0; t < 8; ++t) dbeta_local += ((row_ok && g * 8 + t < nv) ? v[g * 8 + t] : 0.f) * swish_dbeta(y[t], beta);
+                  }
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) v[g * 8 + t] *= act_bwd_from_out<ACT>(y[t], beta);
                 }
               }
               if (nv < 32 || (!USE_MASK && !row_ok)) {   // keep what the bias-gradient column sums must not see at zero
@@ -1334,6 +1351,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, off);
       if (lane == 0 && loss_local != 0.0) atomicAdd(e.loss, loss_local);
+    }
+    if (EPI == EPI_DGRAD && ACT == ACT_SWISH && e.act_grad) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) dbeta_local += __shfl_xor_sync(0xffffffffu, dbeta_local, off);
+      if (lane == 0 && dbeta_local != 0.f) atomicAdd(e.act_grad, dbeta_local);
     }
   }
 

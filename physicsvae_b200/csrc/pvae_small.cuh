@@ -25,6 +25,7 @@ struct SmallLayer {
   const __nv_bfloat16* W;      // shadow operand [plane][out][kpad]
   int64_t ps;                  // plane stride (elements)
   const float* bias;
+  const float* act_param;      // swish: beta (device scalar) or null = 1
   int32_t out, kpad, act, pad;
 };
 struct SmallNet {
@@ -35,13 +36,13 @@ struct SmallNet {
   int32_t trace;               // PVAE_SMALL_TRACE=1: CTA 0 prints its per-layer clock breakdown (debugging aid)
 };
 
-__device__ __forceinline__ float small_act(int act, float v) {
+__device__ __forceinline__ float small_act(int act, float v, float beta = 1.f) {
   switch (act) {
     case 1: return fmaxf(v, 0.f);
     case 2: return tanhf(v);
     case 3: return 1.f / (1.f + __expf(-v));
     case 4: return v > 0.f ? v : expm1f(v);
-    case 5: return v / (1.f + __expf(-v));
+    case 5: return v / (1.f + __expf(-beta * v));
     default: return v;
   }
 }
@@ -123,6 +124,7 @@ small_fc_kernel(const __grid_constant__ SmallNet net, const float* __restrict__ 
         for (int b = 0; b < BT; ++b) acc[j][b] = 0.f;
       const int n_mine = n0 + (lane < NPW ? lane : 0) * NW;                 // the neuron this lane finishes
       const float bias = (L.bias && lane < NPW && n_mine < n_hi) ? __ldg(L.bias + n_mine) : 0.f;
+      const float beta = (L.act == 5 && L.act_param) ? __ldg(L.act_param) : 1.f;
       for (int k = lane * 8; k < L.kpad; k += 256) {        // kpad is a multiple of 64: whole 16-byte pieces
         uint4 q[NPW], q2[NPW];
 #pragma unroll
@@ -176,7 +178,7 @@ small_fc_kernel(const __grid_constant__ SmallNet net, const float* __restrict__ 
       if (lane < NPW && n_mine < n_hi) {
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
-          float v = small_act(L.act, mine[b] + bias);
+          float v = small_act(L.act, mine[b] + bias, beta);
           if (last) {
             if (b < B) out[(int64_t)b * out_ld + n_mine] = v;
           } else {

@@ -100,9 +100,20 @@ class Engine:
         _abi.check(self.lib.pvae_bind_net(self._h, NET_NAMES.index(name), W, b, _ptr(grad_flat)))
         self._keep[name] = (list(weights), list(biases), grad_flat)
 
+    def bind_act_params(self, name, beta, dbeta=None):
+        """beta: fp32 [PVAE_MAX_LAYERS] CUDA tensor, entry l = beta of layer l's swish activation; dbeta: its gradient accumulator
+        (include/pvae_sm100.h, pvae_bind_act_params)."""
+        for t in (beta, dbeta):
+            if t is not None and (t.device != self.device or t.dtype != torch.float32 or t.numel() != _abi.PVAE_MAX_LAYERS or not t.is_contiguous()):
+                raise ValueError("activation parameters must be contiguous fp32 [%d] tensors on %s" % (_abi.PVAE_MAX_LAYERS, self.device))
+        _abi.check(self.lib.pvae_bind_act_params(self._h, NET_NAMES.index(name), _ptr(beta), _ptr(dbeta)))
+        self._keep[name + "/act"] = (beta, dbeta)
+
     def sync_weights(self, names=None):
         mask = 0
         for name in (names or [n for n in NET_NAMES if n in self._keep]):
+            if name.endswith("/act"):
+                continue
             mask |= 1 << NET_NAMES.index(name)
         with torch.cuda.device(self.device):
             _abi.check(self.lib.pvae_sync_weights(self._h, mask, _stream()))

@@ -57,14 +57,14 @@ except Exception:  # noqa
 
 
 class Swish(nn.Module):
-    """ray.rllib.utils.torch_ops.Swish (ray 1.11): x * sigmoid(beta * x) with `_beta` a parameter initialised to 1.0 -- kept so
-    that state dicts of swish nets interchange with the reference (`..._model.{i}._model.1._beta`).  The engine evaluates
-    swish with beta = 1 and does not train beta (PhysicsVAE.sync_weights refuses any other value): a documented deviation,
-    the training CLI never selects swish (train_physics_vae.py:266 hard-wires relu)."""
+    """ray.rllib.utils.torch_ops.Swish (ray 1.11, what get_activation_fn("swish") returns, rllib_model_torch.py:33-35):
+    x * sigmoid(beta * x) with `_beta` a trainable parameter initialised to 1.0 (state-dict key `..._model.{i}._model.1._beta`).
+    Inside a PhysicsVAE the engine reads beta from the device and deposits its gradient like any other parameter's
+    (pvae_bind_act_params); a stand-alone FC evaluates swish with beta = 1."""
 
     def __init__(self):
         super().__init__()
-        self._beta = nn.Parameter(torch.tensor(1.0), requires_grad=False)
+        self._beta = nn.Parameter(torch.tensor(1.0))
 
     def forward(self, x):
         return x * torch.sigmoid(self._beta * x)
@@ -450,20 +450,39 @@ class PhysicsVAE(TorchModelV2, nn.Module):
         # (every piece 16-byte aligned): what a training step has to exchange between data-parallel ranks -- the gradients of
         # the nets it trains plus the loss slots -- is ONE contiguous range in either phase (reduce_range()), and so are the part
         # that is complete early in the backward pass and the rest (reduce_ranges()).
+        # The "scalar block" between encoder and world model holds the loss slots and, per net, the gradients of the activations'
+        # parameters (swish beta, one slot per layer): it is part of the exchanged range in both phases.
         al = lambda k: (k + 3) // 4 * 4
         order = ("motor_decoder", "task_encoder", "world_model", "value_branch")
         sizes = {name: eng.grad_elems(name) for name in NET_NAMES}
+        SCALARS = _abi.PVAE_LOSS_SLOTS + 3 * _abi.PVAE_MAX_LAYERS
         offs, cur = {}, 0
         for name in order:
             offs[name] = cur
             cur += al(sizes[name])
             if name == "task_encoder":
                 loss_off = cur
-                cur += al(_abi.PVAE_LOSS_SLOTS)
+                cur += al(SCALARS)
         pool = self._grad_pool = self._pool_alloc(cur, p0.device)
         eng.loss = pool[loss_off:loss_off + _abi.PVAE_LOSS_SLOTS]
-        self._pool_off = dict(offs, loss=loss_off, end=cur)
+        self._pool_off = dict(offs, loss=loss_off, end=cur, scalars=SCALARS)
         self._pool_sizes = sizes
+        # swish layers: beta values of a net live in one small tensor (entry l = layer l), their gradients in the scalar block
+        self._betas = {}
+        for i, name in enumerate(("task_encoder", "motor_decoder", "world_model")):
+            acts = [m._model[1] if len(m._model) > 1 else None for m in self.net(name).fc_layers()]
+            if not any(isinstance(a, Swish) for a in acts):
+                continue
+            beta = torch.ones(_abi.PVAE_MAX_LAYERS, dtype=torch.float32, device=p0.device)
+            g0 = loss_off + _abi.PVAE_LOSS_SLOTS + i * _abi.PVAE_MAX_LAYERS
+            dbeta = pool[g0:g0 + _abi.PVAE_MAX_LAYERS]
+            for l, a in enumerate(acts):
+                if isinstance(a, Swish):
+                    beta[l] = a._beta.data.to(p0.device)
+                    a._beta.data = beta[l]
+                    a._beta._pvae_grad_view = dbeta[l]
+            eng.bind_act_params(name, beta, dbeta)
+            self._betas[name] = (beta, dbeta)
         for name in NET_NAMES:
             layers = self.net(name).fc_layers()
             n = sizes[name]
@@ -515,7 +534,7 @@ class PhysicsVAE(TorchModelV2, nn.Module):
         o, sz = self._pool_off, self._pool_sizes
         if world_phase:
             return self._grad_pool[o["loss"]:o["world_model"] + sz["world_model"]]
-        return self._grad_pool[o["motor_decoder"]:o["loss"] + _abi.PVAE_LOSS_SLOTS]
+        return self._grad_pool[o["motor_decoder"]:o["loss"] + o["scalars"]]
 
     def reduce_ranges(self, world_phase):
         """reduce_range() split in two for the overlapped exchange (include/pvae_sm100.h, pvae_set_exchange): (early, late).
@@ -534,7 +553,7 @@ class PhysicsVAE(TorchModelV2, nn.Module):
                 return None, self.reduce_range(True)
             return self._grad_pool[cut:end], self._grad_pool[o["loss"]:cut]
         return (self._grad_pool[o["motor_decoder"]:o["motor_decoder"] + sz["motor_decoder"]],
-                self._grad_pool[o["task_encoder"]:o["loss"] + _abi.PVAE_LOSS_SLOTS])
+                self._grad_pool[o["task_encoder"]:o["loss"] + o["scalars"]])
 
     def flat_params(self, name):
         return self._flat[name][0]
@@ -549,9 +568,6 @@ class PhysicsVAE(TorchModelV2, nn.Module):
 
     def sync_weights(self, names=None):
         eng = self.engine()
-        betas = [m._beta for m in self.modules() if isinstance(m, Swish)]
-        if betas and not bool((torch.stack([b.detach().reshape(()) for b in betas]) == 1.0).all()):
-            raise NotImplementedError("swish layers run with beta = 1 on the sm_100a engine (rllib's trainable beta is not implemented)")
         eng.sync_weights(names)
         if names is None:
             self._weights_dirty = False
@@ -719,13 +735,13 @@ class PhysicsVAE(TorchModelV2, nn.Module):
     def set_learnable_task_encoder(self, learnable):
         if self._task_encoder:
             for name, param in self._task_encoder.named_parameters():
-                param.requires_grad = learnable and not name.endswith("_beta")
+                param.requires_grad = learnable
         self._attach_grads()
 
     def set_learnable_motor_decoder(self, learnable, free_log_std=True):
         if self._motor_decoder:
             for name, param in self._motor_decoder.named_parameters():
-                param.requires_grad = learnable and not name.endswith("_beta")
+                param.requires_grad = learnable
                 if "log_std" in name:
                     param.requires_grad = free_log_std
         self._attach_grads()
@@ -736,7 +752,7 @@ class PhysicsVAE(TorchModelV2, nn.Module):
     def set_learnable_world_model(self, learnable):
         if self._world_model:
             for name, param in self._world_model.named_parameters():
-                param.requires_grad = learnable and not name.endswith("_beta")
+                param.requires_grad = learnable
         self._attach_grads()
 
 

@@ -486,8 +486,7 @@ class TrainModel(torch_models.TrainModel):
                                                  bool(getattr(self, "dp_local_shards", False)))
 
     def _graph_prepare(self, batch_size):
-        for name in self._nets():
-            self.optimizer._net_state(name)              # Adam moments exist before the capture (no allocation inside it)
+        self.optimizer.prepare(self._nets())             # Adam moments exist before the capture (no persistent allocation inside it)
         if not self.world_phase:
             # the device-side noise counter must be ON while the step is captured: the library decides at launch time whether the
             # reparameterisation kernel reads it (and the finalisation kernel bumps it)

@@ -67,7 +67,7 @@ def fast_transitions(cfg, n, seed=0):
     return np.ascontiguousarray(X), Y
 
 
-def make_trainer(cfg, X, Y, batch_size, precision="bf16x3", world_epochs=10 ** 9, state_dict=None, X_test=None, Y_test=None, **extra):
+def make_trainer(cfg, X, Y, batch_size, precision="bf16x3", world_epochs=10 ** 9, state_dict=None, X_test=None, Y_test=None, act="relu", **extra):
     """The product's train_physics_vae.TrainModel on given transition arrays (no pickle): DatasetBase(X, Y) straight in."""
     from physicsvae_b200 import train_physics_vae as tp
     from physicsvae_b200 import torch_models as tm
@@ -82,11 +82,11 @@ def make_trainer(cfg, X, Y, batch_size, precision="bf16x3", world_epochs=10 ** 9
     custom = dict(tp.MODEL_CONFIG)
     custom.update(observation_space=box(2 * cfg["dsb"]), observation_space_body=box(cfg["dsb"]), observation_space_task=box(cfg["dsb"]),
                   action_space=box(cfg["da"]), engine_precision=precision, engine_max_batch=batch_size,
-                  value_fn_layers=orc.gen_layers(cfg["te"][0], cfg["te"][1]))          # (oracle_model builds the value branch like this)
+                  value_fn_layers=orc.gen_layers(cfg["te"][0], cfg["te"][1], act_hidden=act))          # (oracle_model builds the value branch like this)
     config = {"max_iter_world_model": world_epochs, "model": {"custom_model": "physics_vae", "custom_model_config": custom},
               "lr": 5e-4, "lr_schedule": "step", "lr_schedule_params": {"step_size": 50, "gamma": 0.7}, "weight_decay": 0.0,
               "dataset_train": "train", "dataset_test": "test" if X_test is not None else None, "loss": "MSE", "loss_test": "MSE",
-              "batch_size": batch_size, "latent_dim": cfg["z"], "latent_prior_type": "normal_zero_mean_one_std", "act_fn": "relu",
+              "batch_size": batch_size, "latent_dim": cfg["z"], "latent_prior_type": "normal_zero_mean_one_std", "act_fn": act,
               "MD_width": cfg["md"][0], "MD_depth": cfg["md"][1], "TE_width": cfg["te"][0], "TE_depth": cfg["te"][1],
               "lookahead": 1, "world_model_width": cfg["wm"][0], "world_model_depth": cfg["wm"][1], "vae_kl_coeff": 1.0,
               "motor_decoder_a_rec_coeff": 1.0, "world_model_s_rec_coeff": 0.0, "vae_cycle_coeff": 1e-3,
