@@ -132,9 +132,12 @@ int pvae_ingest(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t dst_row,
  * [n_states][da] float32; first_state_dev: [n_rows] int64, the state row of s_t of each transition (s_{t+1} is the next row:
  * transitions never cross an episode boundary because the builder never emits the last state of an episode as s_t).
  * replaces: the per-transition np.hstack loop of load_dataset_for_PhysicsVAE (train_physics_vae.py:133-156) + DatasetBase
- * collation, and halves the upload (1.76 KB instead of 3.3 KB per transition at 197 / 45). */
+ * collation, and halves the upload (1.76 KB instead of 3.3 KB per transition at 197 / 45).
+ * states_is_f64: 1 = float64 states, 0 = float32 states (actions float32 in both); 2 = states AND actions are bf16 (a loader that keeps
+ * the dataset in the engine's operand precision -- PVAE_PREC_BF16 only; the same values the device-side conversion of the fp32 data
+ * produces, at half the upload again). */
 int pvae_ingest_episodes(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t dst_row, const void* states_dev,
-                         int states_is_f64, int64_t n_states, const float* actions_dev, const int64_t* first_state_dev,
+                         int states_is_f64, int64_t n_states, const void* actions_dev, const int64_t* first_state_dev,
                          int64_t n_rows, pvae_stream s);
 /* select the buffer the step functions read from; mini-batch b = rows [cursor, cursor + batch) */
 int pvae_bind_transitions(pvae_handle h, const void* buf_dev, int64_t buf_rows);

@@ -51,8 +51,10 @@ __global__ void ingest_kernel(const SrcT* __restrict__ src, int64_t src_ld, int 
 // ---- dataset build on the device (load_dataset_for_PhysicsVAE, train_physics_vae.py:133-156): every state of every episode is
 // uploaded ONCE ([n_states][dsb]); transition r is (s = states[first[r]], a = actions[first[r]], s' = states[first[r] + 1]).
 // One thread per (row, 2 destination columns) of the resident x rows (s | 0.. | a | 0.. | s' | 0..) / y rows (a | 0..).
-template <typename SrcT>
-__global__ void ingest_episodes_kernel(const SrcT* __restrict__ states, const float* __restrict__ actions,
+template <typename T> __device__ __forceinline__ float to_f32(T v) { return (float)v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename SrcT, typename ActT = float>
+__global__ void ingest_episodes_kernel(const SrcT* __restrict__ states, const ActT* __restrict__ actions,
                                        const int64_t* __restrict__ first, int dsb, int da, int a_col, int s2_col,
                                        __nv_bfloat16* __restrict__ dst, int64_t dst_ld, int64_t dst_ps, int planes, int64_t n_rows) {
   const int64_t pairs_per_row = dst_ld >> 1;
@@ -67,11 +69,11 @@ __global__ void ingest_episodes_kernel(const SrcT* __restrict__ states, const fl
       const int c = c0 + k;
       float x = 0.f;
       if (s2_col >= 0) {                       // x row
-        if (c < dsb) x = (float)states[st * dsb + c];
-        else if (c >= a_col && c < a_col + da) x = actions[st * da + (c - a_col)];
-        else if (c >= s2_col && c < s2_col + dsb) x = (float)states[(st + 1) * dsb + (c - s2_col)];
+        if (c < dsb) x = to_f32(states[st * dsb + c]);
+        else if (c >= a_col && c < a_col + da) x = to_f32(actions[st * da + (c - a_col)]);
+        else if (c >= s2_col && c < s2_col + dsb) x = to_f32(states[(st + 1) * dsb + (c - s2_col)]);
       } else if (c < da) {                     // y row
-        x = actions[st * da + c];
+        x = to_f32(actions[st * da + c]);
       }
       v[k] = x;
     }

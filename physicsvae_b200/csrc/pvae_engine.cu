@@ -985,15 +985,26 @@ int pvae_ingest(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t dst_row,
 }
 
 int pvae_ingest_episodes(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t dst_row, const void* states_dev, int states_is_f64,
-                         int64_t n_states, const float* actions_dev, const int64_t* first_state_dev, int64_t n_rows, pvae_stream s) {
+                         int64_t n_states, const void* actions_void, const int64_t* first_state_dev, int64_t n_rows, pvae_stream s) {
+  const float* actions_dev = reinterpret_cast<const float*>(actions_void);
   if (!h || !buf_dev || !states_dev || !actions_dev || !first_state_dev) return fail(PVAE_ERR_INVALID, "null argument");
   if (n_rows <= 0 || dst_row < 0 || dst_row + n_rows > buf_rows) return fail(PVAE_ERR_INVALID, "row range [%lld, %lld) outside the buffer of %lld rows", (long long)dst_row, (long long)(dst_row + n_rows), (long long)buf_rows);
   if (n_states < 2) return fail(PVAE_ERR_INVALID, "an episode needs at least two states");
+  if (states_is_f64 == 2 && h->planes > 1) return fail(PVAE_ERR_INVALID, "bf16 episode arrays carry one precision plane: use them with PVAE_PREC_BF16 only");
   if ((reinterpret_cast<uintptr_t>(buf_dev) & 15) != 0) return fail(PVAE_ERR_INVALID, "transition buffer must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)s;
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(buf_dev);
   __nv_bfloat16* yb = xb + (int64_t)h->planes * buf_rows * h->tx_ld;
   const int64_t xt = n_rows * (h->tx_ld / 2), yt = n_rows * (h->ty_ld / 2);
+  if (states_is_f64 == 2) {
+    // states AND actions already in bf16 (a loader that keeps the dataset in the engine's operand precision: half the upload of fp32)
+    const __nv_bfloat16* sb = reinterpret_cast<const __nv_bfloat16*>(states_dev);
+    const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(actions_void);
+    ingest_episodes_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(sb, ab, first_state_dev,
+        h->dsb, h->da, h->dsb8, h->dsbp, xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
+    ingest_episodes_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(yt, 256, h->dev.sms), 256, 0, st>>>(sb, ab, first_state_dev,
+        h->dsb, h->da, 0, -1, yb + dst_row * h->ty_ld, h->ty_ld, buf_rows * h->ty_ld, h->planes, n_rows);
+  } else {
   if (states_is_f64)
     ingest_episodes_kernel<double><<<grid_for(xt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const double*>(states_dev), actions_dev, first_state_dev,
         h->dsb, h->da, h->dsb8, h->dsbp, xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
@@ -1002,6 +1013,7 @@ int pvae_ingest_episodes(pvae_handle h, void* buf_dev, int64_t buf_rows, int64_t
         h->dsb, h->da, h->dsb8, h->dsbp, xb + dst_row * h->tx_ld, h->tx_ld, buf_rows * h->tx_ld, h->planes, n_rows);
   ingest_episodes_kernel<float><<<grid_for(yt, 256, h->dev.sms), 256, 0, st>>>(reinterpret_cast<const float*>(states_dev), actions_dev, first_state_dev,
       h->dsb, h->da, 0, -1, yb + dst_row * h->ty_ld, h->ty_ld, buf_rows * h->ty_ld, h->planes, n_rows);
+  }
   g_launches.fetch_add(2, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return PVAE_OK;

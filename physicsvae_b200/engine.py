@@ -164,18 +164,26 @@ class Engine:
             raise _abi.PvaeError("alloc_transitions() first")
         if states.dim() != 2 or states.shape[1] != self.dsb or actions.shape != (states.shape[0], self.da):
             raise ValueError("episode arrays must be [S, %d] and [S, %d]" % (self.dsb, self.da))
-        if states.dtype not in (torch.float64, torch.float32):
-            raise ValueError("states must be float64 or float32")
-        states = states.to(self.device).contiguous()
-        actions = actions.to(self.device, torch.float32).contiguous()
+        if states.dtype == torch.bfloat16:
+            # a loader that keeps the dataset in the engine's operand precision (bf16 mode only): states and actions both bf16
+            if self.planes != 1:
+                raise ValueError("bf16 episode arrays need precision='bf16' (the fp32-accurate mode keeps hi + lo planes)")
+            code = 2
+            states = states.to(self.device).contiguous()
+            actions = actions.to(self.device, torch.bfloat16).contiguous()
+        elif states.dtype in (torch.float64, torch.float32):
+            code = 1 if states.dtype == torch.float64 else 0
+            states = states.to(self.device).contiguous()
+            actions = actions.to(self.device, torch.float32).contiguous()
+        else:
+            raise ValueError("states must be float64, float32 or bfloat16")
         first_state = first_state.to(self.device, torch.int64).contiguous()
         # (the range check reads the index back to the host: per-step callers that built the index themselves skip it)
         if check and first_state.numel() and (int(first_state.min()) < 0 or int(first_state.max()) + 1 >= states.shape[0]):
             raise ValueError("first_state index out of range")
         with torch.cuda.device(self.device):
-            _abi.check(self.lib.pvae_ingest_episodes(self._h, _ptr(self.transitions), self.n_rows, int(dst_row), _ptr(states),
-                                                     1 if states.dtype == torch.float64 else 0, states.shape[0], _ptr(actions),
-                                                     _ptr(first_state), first_state.numel(), _stream()))
+            _abi.check(self.lib.pvae_ingest_episodes(self._h, _ptr(self.transitions), self.n_rows, int(dst_row), _ptr(states), code,
+                                                     states.shape[0], _ptr(actions), _ptr(first_state), first_state.numel(), _stream()))
 
     def set_cursor(self, row):
         with torch.cuda.device(self.device):

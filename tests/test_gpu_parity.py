@@ -345,6 +345,20 @@ def test_device_side_dataset_build_equals_array_ingest(precision, tmp_path):
     assert torch.equal(a.view(torch.uint8).flatten(), buf.view(torch.uint8).flatten())
     with pytest.raises(ValueError):
         eng.ingest_episodes(torch.from_numpy(states).cuda(), torch.from_numpy(actions).cuda(), torch.tensor([len(states) - 1]).cuda())
+    # a loader that keeps the dataset in bf16 (the engine's operand precision): same resident bytes as converting fp32 on the device
+    s32, a32 = torch.from_numpy(states).float(), torch.from_numpy(actions).float()
+    if precision == "bf16":
+        buf.zero_()
+        eng.ingest_episodes(s32.cuda(), a32.cuda(), torch.from_numpy(first).cuda())
+        torch.cuda.synchronize()
+        b32 = buf.clone()
+        buf.zero_()
+        eng.ingest_episodes(s32.bfloat16().cuda(), a32.bfloat16().cuda(), torch.from_numpy(first).cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(b32.view(torch.uint8).flatten(), buf.view(torch.uint8).flatten())
+    else:
+        with pytest.raises(ValueError):
+            eng.ingest_episodes(s32.bfloat16().cuda(), a32.bfloat16().cuda(), torch.from_numpy(first).cuda())
     ds = tp.load_dataset_for_PhysicsVAE([f])
     assert ds.episode_source is not None and len(ds.episode_source[2]) == len(ds) == n
 
