@@ -594,10 +594,7 @@ def run_b200(args, cfg):
             prefetch(i + 1)                  # buffer (i + 1) % 2 was last read by step i - 1, which loss.item() has retired
         torch.cuda.current_stream().wait_event(ready[i % 2])
         s_, a_, f_ = bufs[i % 2]
-        loss = tr_e.compute_loss_episodes(s_, a_, f_)
-        loss.backward()
-        tr_e.optimizer.step()
-        return loss.item()
+        return tr_e.train_on_episodes(s_, a_, f_).item()       # dataset build + forward + loss + backward + [exchange] + Adam: one graph launch
     e2e_steps = max(3, min(steps, 20))
     prefetch(0)
     for i in range(3):
@@ -613,7 +610,8 @@ def run_b200(args, cfg):
     e2e = {"value": B * world * e2e_steps / (ems * 1e-3), "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
            "upload_dtype": str(sh.dtype).replace("torch.", ""),
-           "api": "double-buffered pinned-host loader (unique states + index, %s) -> TrainModel.compute_loss_episodes + backward + optimizer.step + loss.item()" % str(sh.dtype).replace("torch.", "")}
+           "api": "double-buffered pinned-host loader (unique states + index, %s) -> TrainModel.train_on_episodes (one captured graph per staging buffer: "
+                  "device-side dataset build + compute_loss + backward + Adam) + loss.item()" % str(sh.dtype).replace("torch.", "")}
     # (2) "e2e_resident": what the reference's Trainable.step() does -- whole epochs over the dataset -- with the dataset uploaded
     #     once at setup: TrainModel.step() = graph replays + one loss read-back per epoch (+ the LR scheduler)
     epochs = max(2, min(steps // 4, 10))

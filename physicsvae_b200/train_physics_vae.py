@@ -476,6 +476,59 @@ class TrainModel(torch_models.TrainModel):
         gradient buffer is touched, nothing but the loss slots is exchanged between ranks."""
         return self.batch_loss(lo, hi, train=False)
 
+    def train_on_episodes(self, states, actions, first_state):
+        """One whole SGD step (zero_grad -> compute_loss -> backward -> [exchange] -> Adam, torch_models.py:137-143) on a mini-batch
+        handed over in the compact form of compute_loss_episodes, as DEVICE tensors (the caller's loader copied them from pinned host
+        memory).  The step -- device-side dataset build included -- is ONE captured CUDA graph per staging buffer set, so the host
+        side of a step is a graph launch; returns the loss as a 0-dim device tensor (read it with .item(), like the reference)."""
+        B = int(first_state.shape[0])
+        if B < 2:
+            raise ValueError("a mini-batch needs at least 2 transitions (the reference squeezes the batch axis)")
+        if not self._graph_ok(B) or self.lookahead != 1:
+            loss = self.compute_loss_episodes(states, actions, first_state)
+            self.optimizer.step()
+            return loss.detach()
+        self._engine_rows = max(self._engine_rows, B)
+        eng = self.engine
+        buf = self._buffers.get("adhoc")
+        if buf is None or isinstance(buf[0], list) or buf[1] != B:
+            buf = (torch.zeros(eng.transitions_bytes(B), dtype=torch.uint8, device=self.device), B)
+            self._buffers["adhoc"] = buf
+        self._bind("adhoc")
+        key = ("episodes", states.data_ptr(), actions.data_ptr(), first_state.data_ptr(), str(states.dtype), id(buf[0])) + self._graph_key(B)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            self._graph_prepare(B)
+            if self.model._weights_dirty:
+                self.model.sync_weights()
+            s0, n, w = self._shard(0, B)
+            if n <= 0:
+                raise _abi.PvaeError("a captured step needs at least one row per rank")
+
+            def body():
+                eng.ingest_episodes(states, actions, first_state, dst_row=0, check=False)
+                eng.set_cursor(s0)
+                self._engine_step(n, w)
+                self._reduce()
+                self.optimizer.step()
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            self._graphs[key] = g
+            if not self.world_phase:
+                eng.noise_counter(True, (self._noise_step + 1) * parallel.world_size(), parallel.world_size())
+        g.replay()
+        if not self.world_phase:
+            self._noise_step += 1
+        return eng.loss[0]
+
     # ---- the captured full-batch step (torch_models.TrainModel._graph_step) ------------------------------------------------
     def _graph_supported(self):
         return self.lookahead == 1          # (a rollout re-carves the workspace per step on the host: eager launches)
