@@ -301,3 +301,30 @@ def test_bench_reference_arm_and_flop_model():
     assert b.flops_per_transition(197, 45, 32, [256] * 2, [512] * 3, [1024] * 2) == (8493056, 10269696)
     assert b.flops_per_transition(512, 128, 32, [1024] * 3, [1024] * 3, [1024] * 3) == (18350080, 44892160)
     assert b.flops_per_transition(197, 45, 32, [256] * 2, [512] * 3, [1024] * 2) == orc.flops_per_transition(197, 45, 32, [256] * 2, [512] * 3, [1024] * 2)
+
+
+def test_round2_host_logic_cli_flags_output_paths_swish_keys():
+    """Host-side pieces added in round 2 that need no GPU: the extra CLI flags keep the reference's defaults, a sweep's --output
+    names one file per trial, rllib's Swish contributes a `_beta` key per swish layer (state-dict interchange), and FC / PhysicsVAE
+    still refuse to compute on the CPU."""
+    from physicsvae_b200 import train_physics_vae as tp
+    from physicsvae_b200 import rllib_model_torch as pm
+    from physicsvae_b200 import parallel, _abi
+    a = tp.arg_parser().parse_args(["--data_train", "x.pkl"])
+    assert a.deterministic is False and a.sweep_mode == "dp" and a.precision == "bf16x3" and a.batch_size == 256 and a.lr == 0.0005
+    assert tp.arg_parser().parse_args(["--data_train", "x.pkl", "--deterministic"]).deterministic is True
+    assert tp.output_path("out/model.pt", 3, 1) == "out/model.pt"
+    assert tp.output_path("out/model.pt", 3, 4) == "out/model.trial_00003.pt"
+    assert parallel.world_size() == 1 and parallel.graph_capturable() and parallel.symmetric_pool_factory() is None
+    assert parallel.allreduce_kind()["kind"] == "nccl"
+    layers = tp.gen_layers(8, 2, act_hidden="swish")
+    fc = pm.FC(size_in=5, size_out=3, layers=layers)
+    keys = list(fc.state_dict().keys())
+    assert keys == ["_model.0._model.0.weight", "_model.0._model.0.bias", "_model.0._model.1._beta", "_model.1._model.0.weight",
+                    "_model.1._model.0.bias", "_model.1._model.1._beta", "_model.2._model.0.weight", "_model.2._model.0.bias"]
+    assert float(fc.state_dict()["_model.0._model.1._beta"]) == 1.0 and fc._model[0]._model[1]._beta.requires_grad
+    assert fc.layer_spec() == [(8, "swish"), (8, "swish"), (3, "linear")]
+    with pytest.raises(_abi.PvaeError):
+        fc(torch.zeros(2, 5))                      # CPU tensors: no eager fallback
+    with pytest.raises(ValueError):
+        pm.get_activation_fn("gelu")
