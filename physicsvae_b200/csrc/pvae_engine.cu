@@ -136,6 +136,7 @@ struct Device {
   int pdl = 1;            // PVAE_PDL=0: plain stream-ordered GEMM launches
   int snake = 1;          // PVAE_SNAKE=0: every GEMM walks the batch front to back (see batch_direction)
   int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
+  int prefetch = 0;       // PVAE_PREFETCH: L2 prefetch distance of the streamed operands in units (0 = off, -1 = by K depth); measured slower (profiles/r02_bench.md), off
   int fast_epi = 1;       // PVAE_FAST_EPI=0: never use the lean ReLU store / dgrad epilogue (A/B experiments)
   int small_fwd = 1;      // PVAE_SMALL_FWD=0: batches <= 16 of the inference API also take the tensor-core path
   int reserved_sms = 0;   // SMs the GEMM grids leave free while the gradient exchange of a data-parallel step runs beside them (pvae_set_exchange)
@@ -200,6 +201,8 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   else bn = rup(cdiv(d.N, n_tiles), n_tiles > 1 ? 64 : 16);
   if (bn > MAX_BN) bn = MAX_BN;
   p.cs_mma = dev.cs_mma;
+  p.pf_dist = dev.prefetch;
+  p.pf_b = d.epi.type == EPI_WGRAD;
   p.reverse = batch_direction(dev, d);
   n_tiles = cdiv(d.N, bn);
   p.n_tiles = n_tiles;
@@ -238,6 +241,8 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
     }
   }
   p.splits = splits;
+  // L2 prefetch distance: short units (thin K) are over before a DRAM round trip completes -- look two units ahead
+  if (p.pf_dist < 0) p.pf_dist = cdiv(iters, splits) <= 6 ? 2 : 1;
   p.row_cursor = dev.cursor;
   p.epi = d.epi;
   p.epi.m_valid = d.M;
@@ -715,6 +720,8 @@ static int init_device(Device& dev, int device) {
   if (env) dev.cs_mma = atoi(env) != 0;
   env = getenv("PVAE_FAST_EPI");
   if (env) dev.fast_epi = atoi(env) != 0;
+  env = getenv("PVAE_PREFETCH");
+  if (env) { int v = atoi(env); if (v >= -1 && v <= 8) dev.prefetch = v; }
   env = getenv("PVAE_SMALL_FWD");
   if (env) dev.small_fwd = atoi(env) != 0;
   env = getenv("PVAE_CLUSTER");

@@ -101,6 +101,8 @@ struct GemmParams {
   int32_t dbg;                     // PVAE_DBG bit mask: skip parts of the TMA epilogue (timing experiments only, results are wrong)
   int32_t reverse;                 // walk the batch dimension from its far end (see UnitWalk)
   int32_t cs_mma;                  // bias-gradient column sums: 1 = mma.sync (ones . slab), 0 = lanes add columns, -1 = by K depth
+  int32_t pf_dist;                 // L2 prefetch of the streamed operand(s): units ahead of the one being loaded (0 = off)
+  int32_t pf_b;                    // prefetch B as well (weight gradients stream both operands; forward / dgrad weights live in L2)
   int32_t cg;                      // 1, or 2: CTA pairs on adjacent M tiles run one 256-row tcgen05.mma.cta_group::2 (kernel template CG)
   const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
   CUtensorMap tmOut;               // TMA-store epilogue: the primary bf16 output, box 64 cols x 32 rows (one warp's slab)
@@ -175,6 +177,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+// L2 prefetch of one box: no shared memory, no barrier -- the later cp.async.bulk.tensor of the same box then pays L2 latency
+// instead of DRAM latency, which the 5-6 pipeline stages (160-192 KiB in flight per CTA) cannot hide on their own.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // One lane of a converged warp (warp-uniform control flow around it keeps TMA / MMA operands in uniform registers).
 __device__ __forceinline__ bool elect_one() {
@@ -733,12 +741,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
     const uint32_t full0 = (CG == 2) ? mapa_u32(full_bar(0), 0u) : full_bar(0);
     int stage = 0; uint32_t phase = 0;
     UnitWalk w; w.init(unit0, unit_stride, p.n_tiles, m_pairs, iters_total, p.splits, p.reverse);
+    // Operand boxes of the unit `wp` is at, as L2 prefetches (same coordinate arithmetic as the copy loop below).
+    auto prefetch_unit = [&](const UnitWalk& wp) {
+      const int m_tile = wp.m_pair() * csize + crank;
+      const int it_end = wp.it_end();
+      int it = wp.it_begin();
+      const int b_n = p.b_n0 + wp.nt * bn + crank * bn_loc;
+      while (it < it_end) {
+        KRun run; run.init(it, it_end, p.kb[0], p.kb[1], p.passes);
+        it += run.n;
+        const int seg = run.seg;
+        const int a_plane = (run.pass == 2) ? 1 : 0;
+        const int b_plane = (run.pass == 1) ? 1 : 0;
+        const int aseg = (p.m_seg_tiles && m_tile >= p.m_seg_tiles) ? 1 : seg;
+        const int m_loc = (p.m_seg_tiles && m_tile >= p.m_seg_tiles) ? m_tile - p.m_seg_tiles : m_tile;
+        const CUtensorMap* tmA = &p.tmA[aseg];
+        const int a_row = p.a_r0[aseg] + (p.a_dyn[aseg] ? row0 : 0);
+        int ac0 = a_mn ? p.a_c0[aseg] + m_loc * BM : p.a_c0[aseg] + run.r0 * BK;
+        int ac1 = a_mn ? a_row + run.r0 * BK : a_row + m_loc * BM;
+        int bc0 = b_mn ? b_n : p.b_k0[seg] + run.r0 * BK;
+        int bc1 = b_mn ? p.b_k0[seg] + run.r0 * BK + (p.b_dyn ? row0 : 0) : b_n;
+        for (int j = 0; j < run.n; ++j) {
+          if (elect_one()) {
+            tma_prefetch_3d(tmA, ac0, ac1, a_plane);
+            if (a_mn) tma_prefetch_3d(tmA, ac0 + 64, ac1, a_plane);
+            if (p.pf_b) {
+              tma_prefetch_3d(&p.tmB, bc0, bc1, b_plane);
+              for (int x = 1; x < b_boxes; ++x) tma_prefetch_3d(&p.tmB, bc0 + 64 * x, bc1, b_plane);
+            }
+          }
+          __syncwarp();
+          if (a_mn) ac1 += BK; else ac0 += BK;
+          if (b_mn) bc1 += BK; else bc0 += BK;
+        }
+      }
+    };
+    UnitWalk wpf = w;                                      // runs pf_dist units ahead of w
+    int upf = unit0;
+    if (p.pf_dist > 0) {
+      for (int d = 0; d < p.pf_dist; ++d) {
+        if (d > 0 && upf < total_units) prefetch_unit(wpf);   // units 1 .. pf_dist-1: nobody prefetches them later
+        upf += unit_stride; wpf.next();
+      }
+    }
     for (int u = unit0; u < total_units; u += unit_stride, w.next()) {
       const int n_tile = w.nt;
       const int m_tile = w.m_pair() * csize + crank;
       const int it_end = w.it_end();
       int it = w.it_begin();
       const int b_n = p.b_n0 + n_tile * bn + crank * bn_loc;
+      if (p.pf_dist > 0) {
+        if (upf < total_units) prefetch_unit(wpf);
+        upf += unit_stride; wpf.next();
+      }
       while (it < it_end) {
         KRun run; run.init(it, it_end, p.kb[0], p.kb[1], p.passes);
         it += run.n;
