@@ -337,17 +337,24 @@ def time_steps(tr, steps, warmup, world, dev, sampler=None):
     return ms, (sampler.stop(t0, t1) if sampler else None)
 
 
-def probe_kernel_ms(tr, kev, groups, per_group):
+def probe_kernel_ms(tr, kev, groups, per_group, first=None):
     """Duration of the engine's launch sequence INSIDE the product's step graph: two external CUDA events recorded as nodes of
-    the graph around pvae_{world,vae}_step.  Each sample is the last replay of a group of `per_group` back-to-back replays."""
-    samples = []
+    the graph around pvae_{world,vae}_step.  Each sample is the last replay of a group of `per_group` back-to-back replays;
+    `first` is the sample the timed region itself left behind (its last replay).  Returns the median (a group that starts on
+    an idle, clock-gated GPU reads a few percent long) and the spread."""
+    samples = [first] if first else []
     for _ in range(groups):
         tr.train_steps(per_group)
         torch.cuda.synchronize()
         v = kev[0].elapsed_time(kev[1])
         if v > 0:
             samples.append(v)
-    return sum(samples) / len(samples) if samples else None
+    if not samples:
+        return None, None
+    srt = sorted(samples)
+    med = srt[len(srt) // 2] if len(srt) % 2 else 0.5 * (srt[len(srt) // 2 - 1] + srt[len(srt) // 2])
+    return med, {"n": len(srt), "min_ms": srt[0], "median_ms": med, "max_ms": srt[-1], "last_replay_of_timed_region_ms": first,
+                 "replays_per_sample": per_group}
 
 
 def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local, dims=None):
@@ -373,13 +380,15 @@ def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, loca
         kev = None
     tr._graph_probe = kev
     ms, clocks = time_steps(tr, steps, warmup, world, dev, ClockSampler(local) if rank == 0 else None)
-    kernel_ms = probe_kernel_ms(tr, kev, max(5, min(steps, 20)), 5) if kev else None
+    # the events now hold the LAST replay of the timed region (barrier() synchronised): the first kernel sample
+    first = kev[0].elapsed_time(kev[1]) if kev else None
+    kernel_ms, kernel_samples = probe_kernel_ms(tr, kev, 10, max(5, min(steps, 20)), first if first and first > 0 else None) if kev else (None, None)
     # not GEMMs: loss finalisation, fused Adam (one per trained net), cursor advance; VAE phase also reparameterisation fwd / bwd;
     # N > 1 with the symmetric gradient pool: the library's peer-memory all-reduce kernel
     from physicsvae_b200 import parallel as _par
     gemm_launches = launches_per_step - {"world": 3, "vae": 6}[phase] - (1 if world > 1 and _par.allreduce_kind()["kind"].startswith("symm") else 0)
     return {"phase": phase, "B": B, "value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "clocks": clocks,
-            "kernel_ms": kernel_ms, "kev": kev, "flops_step": flops_step, "launches_per_step": int(launches_per_step),
+            "kernel_ms": kernel_ms, "kernel_samples": kernel_samples, "kev": kev, "flops_step": flops_step, "launches_per_step": int(launches_per_step),
             "gemm_launches": int(gemm_launches), "sustained": None, "config": workload(args, cfg, phase, B, dims), "dims": dims or args.config}
 
 
@@ -402,7 +411,8 @@ def measure_sustained(res, tr, world, rank, dev, local, seconds):
     barrier(world)
     t1 = time.time()
     sms = max_over_ranks(e0.elapsed_time(e1), dev, world)
-    k_sus = probe_kernel_ms(tr, kev, 8, 50) if kev else None
+    first = kev[0].elapsed_time(kev[1]) if kev else None
+    k_sus = probe_kernel_ms(tr, kev, 8, 50, first if first and first > 0 else None)[0] if kev else None
     res["sustained"] = {"steps": n_sus, "ms_per_step": sms / n_sus, "value": B * world * n_sus / (sms * 1e-3), "kernel_ms_per_step": k_sus,
                         "clocks": sampler.stop(t0, t1) if sampler else None}
 
@@ -434,7 +444,7 @@ def finish_phase(args, res, tr):
                 "peak_sustained": pk["bf16_tflops_sustained"], "peak_source": pk_src + " (MEASURED_PEAKS.json: cuBLAS bf16 burst / sustained)",
                 "traffic": traffic, "kernel": "pvae_gemm_kernel", "launches_per_step": res["gemm_launches"],
                 "avg_launch_ms": kernel_ms / gl, "algorithmic_flops_per_launch": flops_step / gl,
-                "kernel_ms_per_step": kernel_ms, "algorithmic_flops_per_step": flops_step,
+                "kernel_ms_per_step": kernel_ms, "kernel_ms_samples": res.get("kernel_samples"), "algorithmic_flops_per_step": flops_step,
                 "timing": "external CUDA events recorded as nodes of the product's step graph around the engine's launch sequence",
                 "whole_step_tflops": flops_step / (res["ms_per_step"] * 1e-3) / 1e12}
     out = {k: res[k] for k in ("value", "ms_per_step", "steps", "clocks", "sustained", "launches_per_step", "config")}
@@ -507,7 +517,10 @@ def run_b200(args, cfg):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
+        # one loader process per GPU: keep it (and the pinned staging memory it is about to allocate) on the GPU's NUMA node
+        numa = parallel.bind_to_gpu_numa_node(local) if os.environ.get("PVAE_NUMA_BIND", "1") != "0" else {"bound": False, "why": "PVAE_NUMA_BIND=0"}
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
     B, phase = args.batch, args.phase
@@ -700,6 +713,8 @@ def run_b200(args, cfg):
                                                                                           and parallel.allreduce_kind()["kind"].startswith("symm")))
         if dp_check is not None:
             line["dp_check"] = dp_check
+        if numa is not None:
+            line["numa"] = numa          # (rank 0's record: where its loader process and pinned staging memory live)
         if not args.no_cpu_baseline:
             v, cms, cores, rows, nsteps, kind = cpu_arm(cfg, phase, args.cpu_sample or 4096, 3, 1, min_seconds=10.0)
             line["cpu_baseline"] = {"value": v, "unit": "transitions/s", "cores": cores, "kind": kind, "ms_per_step": cms,

@@ -197,6 +197,41 @@ def allreduce_avg_(tensors, group=None):
             t.div_(w)
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index, sysfs="/sys", bdf=None):
+    """Run this process on the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers it allocates afterwards
+    (first touch) are local to the GPU's PCIe root: with one loader process per GPU, uploads that cross the socket interconnect
+    share its bandwidth between all ranks.  Best effort -- returns a record of what was done (or why nothing was)."""
+    try:
+        if bdf is None:
+            pr = torch.cuda.get_device_properties(device_index)
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"bound": False, "why": "no NUMA node reported for %s" % bdf}
+        with open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)) as f:
+            local = _cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        use = allowed & local
+        if not use:
+            return {"bound": False, "node": node, "why": "none of the %d CPUs this process may use is on node %d" % (len(allowed), node)}
+        if use != allowed:
+            os.sched_setaffinity(0, use)
+        return {"bound": True, "node": node, "cpus": len(use), "of": len(allowed), "pci": bdf}
+    except Exception as e:                                           # (no sysfs in the container, no such attribute, ...)
+        return {"bound": False, "why": "%s: %s" % (type(e).__name__, e)}
+
+
 def barrier():
     """All ranks that share a trainer wait for each other (no-op for a single rank and in replica mode)."""
     if world_size() > 1:

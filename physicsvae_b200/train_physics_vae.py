@@ -696,6 +696,8 @@ def init_distributed(sweep_mode="dp"):
         backend = os.environ.get("PVAE_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
+            if os.environ.get("PVAE_NUMA_BIND", "1") != "0":
+                parallel.bind_to_gpu_numa_node(local)     # loader process + its pinned staging memory next to the GPU's PCIe root
         if backend == "nccl":
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:

@@ -328,3 +328,30 @@ def test_round2_host_logic_cli_flags_output_paths_swish_keys():
         fc(torch.zeros(2, 5))                      # CPU tensors: no eager fallback
     with pytest.raises(ValueError):
         pm.get_activation_fn("gelu")
+
+
+def test_bind_to_gpu_numa_node_reads_sysfs(tmp_path):
+    """parallel.bind_to_gpu_numa_node: PCI address -> NUMA node -> CPU list, intersected with the CPUs the process may use."""
+    import os
+    from physicsvae_b200 import parallel
+    bdf = "0000:1b:00.0"
+    d = tmp_path / "bus" / "pci" / "devices" / bdf
+    d.mkdir(parents=True)
+    allowed = sorted(os.sched_getaffinity(0))
+    try:
+        (d / "numa_node").write_text("1\n")
+        n = tmp_path / "devices" / "system" / "node" / "node1"
+        n.mkdir(parents=True)
+        keep = allowed[: max(1, len(allowed) // 2)]
+        (n / "cpulist").write_text("%s,%d-%d\n" % (",".join(map(str, keep)), 100000, 100003))
+        r = parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path), bdf=bdf)
+        assert r["bound"] and r["node"] == 1 and r["cpus"] == len(keep) and r["of"] == len(allowed)
+        assert sorted(os.sched_getaffinity(0)) == keep
+        (d / "numa_node").write_text("-1\n")
+        assert not parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path), bdf=bdf)["bound"]
+        (d / "numa_node").write_text("1\n")
+        (n / "cpulist").write_text("100000-100003\n")
+        assert not parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path), bdf=bdf)["bound"]       # no usable CPU there: untouched
+        assert not parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path / "nope"), bdf=bdf)["bound"]
+    finally:
+        os.sched_setaffinity(0, allowed)
