@@ -276,7 +276,7 @@ static int launch_gemm(const Device& dev, const GemmDesc& d, cudaStream_t st) {
   const bool fast = dev.fast_epi && tma && cluster == 2 && e.act == ACT_RELU && (e.type == EPI_STORE || e.type == EPI_DGRAD) &&
                     d.M % (BM * cluster) == 0 && d.N % 32 == 0 && bn % 32 == 0 && !d.mseg && d.m_gap == 0 && e.add == nullptr &&
                     e.out_f32 == nullptr && e.mask != nullptr && (e.type == EPI_DGRAD || e.bias != nullptr) && dev.cs_mma == 0 &&
-                    splits == 1 && (!DEBUG_HOOKS || p.dbg == 0);
+                    splits == 1 && (!DEBUG_HOOKS || (p.dbg & ~32) == 0);     // (role-timeline stamps exist in the lean block too)
   GemmKernelFn fn = select_kernel(p.epi.type, p.epi.act, tma, cluster, fast);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

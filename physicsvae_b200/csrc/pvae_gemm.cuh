@@ -942,8 +942,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       const int row = m_tile * BM + q * 32 + lane;
       float nxt_bias[2] = {0.f, 0.f}; uint32_t nxt_mask[2] = {0u, 0u};
       if (u + unit_stride < total_units) { UnitWalk wn = w; wn.next(); fetch(wn, nxt_bias, nxt_mask); }
+      const int tk = (DEBUG_HOOKS && (p.dbg & 32)) ? (u - unit0) / unit_stride : 0;
+      if (DEBUG_HOOKS && ew == 0 && lane == 0) trace_stamp(p.dbg, tk, 4);
       mbar_wait<W_TFULL>(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (DEBUG_HOOKS && ew == 0 && lane == 0) trace_stamp(p.dbg, tk, 5);
       const uint32_t tmem_unit = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * MAX_BN + cgrp * 32);
       const int col_unit = n_tile * bn + cgrp * 32;
       auto chunk = [&](auto jc) {
@@ -1046,6 +1049,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      if (DEBUG_HOOKS && ew == 0 && lane == 0) trace_stamp(p.dbg, tk, 6);
       pre_bias[0] = nxt_bias[0]; pre_bias[1] = nxt_bias[1];
       pre_mask[0] = nxt_mask[0]; pre_mask[1] = nxt_mask[1];
     }
