@@ -217,8 +217,9 @@ int pvae_forward(pvae_handle h, uint32_t parts, int batch, const float* obs_dev,
  * Averaging all-reduce, in place, of the fp32 range [offset, offset + count) of a SYMMETRIC allocation: the same buffer layout
  * allocated on every rank of one node and mapped into every peer (torch.distributed._symmetric_memory / CUDA IPC / VMM), its base
  * address on rank p being peer_ptrs_host[p] (a host array of `world` device addresses as seen from THIS rank).  One kernel: device-side
- * rank barrier through flags inside the allocation, rank r reduces slice r over NVLink (peer loads, or multimem.ld_reduce when
- * multicast_ptr != 0) and writes the averaged slice into every rank's copy (peer stores / multimem.st), barrier.  All ranks must call
+ * rank barrier through flags inside the allocation, rank r reduces slice r over NVLink (cp.async.bulk copies of the peers' slices
+ * into shared memory, five 32 KiB stages in flight per CTA; PVAE_SYMM_BULK=0: per-thread peer loads; multicast_ptr != 0:
+ * multimem.ld_reduce, the switch adds) and writes the averaged slice into every rank's copy (bulk / peer stores / multimem.st), barrier.  All ranks must call
  * it the same number of times; every replica ends up with bit-identical values.  The flag block -- pvae_symm_flag_elems() fp32-sized
  * words at flags_offset inside the same allocation, zeroed on every rank before the first call -- carries the sequence numbers, so the
  * call is CUDA-graph replayable.  world <= 8. */

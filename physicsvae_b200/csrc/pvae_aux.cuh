@@ -463,6 +463,96 @@ __global__ void __launch_bounds__(AR_THREADS) symm_allreduce_kernel(const SymmAr
   if (threadIdx.x == 0) *ctr = seq + 2;
 }
 
+// The same exchange with the data moved by the bulk-copy engine (cp.async.bulk) instead of per-thread loads: one thread of a
+// CTA keeps ARB_STAGES x 32 KiB of peer reads in flight (a stage = the same chunk of the slice from every rank, landing in
+// shared memory, completion on an mbarrier), the 256 threads add the `world` copies in fixed rank order, and the averaged chunk
+// leaves as one bulk store per rank.  Bytes in flight per SM no longer depend on registers: 160 KiB instead of the 64 KiB that
+// 512 threads x 8 outstanding 16-byte loads hold -- what an exchange squeezed onto a few SMs beside the backward GEMMs needs.
+// Barriers, flag block, slice ownership and summation order are those of symm_allreduce_kernel (results bit-identical to it).
+constexpr int ARB_THREADS = 256, ARB_STAGES = 5, ARB_STAGE_BYTES = 32768, ARB_OUT_SLOTS = 3, ARB_OUT_BYTES = 16384;
+constexpr int ARB_SMEM_BYTES = ARB_STAGES * ARB_STAGE_BYTES + ARB_OUT_SLOTS * ARB_OUT_BYTES + 64;
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(dst)), "r"(src_smem), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(ARB_THREADS) symm_allreduce_bulk_kernel(const SymmArgs a) {
+  extern __shared__ __align__(128) uint8_t arb_smem[];
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(a.peer[a.rank] + a.flags_off);
+  uint32_t* ctr = my_flags + AR_CTAS * AR_MAX_RANKS + blockIdx.x;
+  const uint32_t seq = *ctr;
+  const uint32_t smem0 = smem_u32(arb_smem);
+  const uint32_t out0 = smem0 + ARB_STAGES * ARB_STAGE_BYTES;
+  const uint32_t bar0 = out0 + ARB_OUT_SLOTS * ARB_OUT_BYTES;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ARB_STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
+    fence_barrier_init();
+  }
+  symm_barrier(a, my_flags, seq + 1);            // (its __syncthreads also publish the barrier initialisation)
+  asm volatile("fence.proxy.async;" ::: "memory");   // peer data observed through the flags (generic proxy) -> bulk reads (async proxy)
+  const int64_t n4 = a.count >> 2;
+  const int64_t per = (n4 + a.world - 1) / a.world;
+  const int64_t lo = (int64_t)a.rank * per, hi = lo + per < n4 ? lo + per : n4;
+  // a chunk = chunk4 float4 of the slice, from every rank: world * chunk4 * 16 B <= one stage; the sum of a chunk <= one out slot
+  int chunk4 = (ARB_STAGE_BYTES / 16) / a.world;
+  if (chunk4 > ARB_OUT_BYTES / 16) chunk4 = ARB_OUT_BYTES / 16;
+  chunk4 &= ~63;
+  const int64_t n_chunks = hi > lo ? (hi - lo + chunk4 - 1) / chunk4 : 0;
+  const int64_t my_chunks = n_chunks > (int64_t)blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](int64_t k) {                  // thread 0: the k-th chunk of this CTA into stage k % ARB_STAGES
+    const int64_t c = (int64_t)blockIdx.x + k * gridDim.x;
+    const int64_t first = lo + c * chunk4;
+    const uint32_t n = (uint32_t)((hi - first < chunk4 ? hi - first : chunk4) * 16);
+    const int st = (int)(k % ARB_STAGES);
+    const uint32_t bar = bar0 + 8u * st;
+    mbar_expect_tx(bar, n * (uint32_t)a.world);
+    for (int p = 0; p < a.world; ++p)
+      bulk_load(smem0 + st * ARB_STAGE_BYTES + p * (chunk4 * 16), a.peer[p] + a.off + (first << 2), n, bar);
+  };
+  if (threadIdx.x == 0)
+    for (int64_t k = 0; k < my_chunks && k < ARB_STAGES; ++k) issue(k);
+  for (int64_t k = 0; k < my_chunks; ++k) {
+    const int64_t c = (int64_t)blockIdx.x + k * gridDim.x;
+    const int64_t first = lo + c * chunk4;
+    const int n4c = (int)(hi - first < chunk4 ? hi - first : chunk4);
+    const int st = (int)(k % ARB_STAGES);
+    const int os = (int)(k % ARB_OUT_SLOTS);
+    mbar_wait<W_FULL>(bar0 + 8u * st, (uint32_t)((k / ARB_STAGES) & 1));
+    const float4* in = reinterpret_cast<const float4*>(arb_smem + st * ARB_STAGE_BYTES);
+    float4* out = reinterpret_cast<float4*>(arb_smem + ARB_STAGES * ARB_STAGE_BYTES + os * ARB_OUT_BYTES);
+    for (int i = threadIdx.x; i < n4c; i += ARB_THREADS) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < a.world; ++p) {          // fixed order 0 .. world-1, as in symm_allreduce_kernel
+        const float4 v = in[p * chunk4 + i];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      t.x *= a.scale; t.y *= a.scale; t.z *= a.scale; t.w *= a.scale;
+      out[i] = t;
+    }
+    fence_proxy_async();                           // this thread's shared-memory writes -> visible to the bulk stores
+    __syncthreads();                               // the out slot is complete, the input stage has been read by everyone
+    if (threadIdx.x == 0) {
+      for (int p = 0; p < a.world; ++p)
+        bulk_store(a.peer[p] + a.off + (first << 2), out0 + os * ARB_OUT_BYTES, (uint32_t)n4c * 16u);
+      tma_store_commit();
+      // three out slots, one __syncthreads per chunk: the slot that chunk k + 2 fills was last read by the stores of chunk k - 1,
+      // which this wait (only the newest group may be pending) retires before thread 0 reaches the __syncthreads of chunk k + 1
+      tma_store_wait_read<1>();
+      if (k + ARB_STAGES < my_chunks) issue(k + ARB_STAGES);
+    }
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the stores have been performed, not just read out of shared memory
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  __threadfence_system();
+  symm_barrier(a, my_flags, seq + 2);
+  if (threadIdx.x == 0) *ctr = seq + 2;
+}
+
 // ---- loss bookkeeping ---------------------------------------------------------------------------------------------
 // acc: [0] sum sq a, [1] sum kl, [2] sum sq s (world), [3] sum sq cyc
 // (the accumulators are cleared here, for the next step: one memset node less per step)

@@ -505,6 +505,26 @@ static int net_forward(pvae_engine* h, Net& net, const NetIO& in, int batch, con
   return PVAE_OK;
 }
 
+// The exchange kernel of a launch: the bulk-copy variant (default; measured 54 -> 38 us per 6 MB call on 8 GPUs, 118 -> 86 us per 24 MB,
+// profiles/r02_scaling.md) or per-thread peer loads (PVAE_SYMM_BULK=0, and whenever the switch reduces: multimem).
+static bool symm_bulk() {
+  static const int bulk = [] { const char* e = getenv("PVAE_SYMM_BULK"); return e ? atoi(e) : 1; }();
+  return bulk != 0;
+}
+static int launch_symm(const SymmArgs& a, int ctas, cudaStream_t st) {
+  const bool bulk = symm_bulk();
+  if (bulk && !a.mc) {
+    static const cudaError_t attr = cudaFuncSetAttribute(symm_allreduce_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ARB_SMEM_BYTES);
+    CK(attr);
+    symm_allreduce_bulk_kernel<<<ctas, ARB_THREADS, ARB_SMEM_BYTES, st>>>(a);
+  } else {
+    symm_allreduce_kernel<<<ctas, AR_THREADS, 0, st>>>(a);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return PVAE_OK;
+}
+
 // ---- overlapped gradient exchange (data parallel): fork = the gradients of the early range are complete once everything launched so
 // far on `st` has run -> exchange them on the side stream with a few CTAs while the remaining GEMMs run on the other SMs; join before
 // the step ends.  Both are stream-ordered events: capturable (fork / join inside one graph).
@@ -512,9 +532,7 @@ static int exchange_fork(pvae_engine* h, cudaStream_t st) {
   if (!h->xchg.on || h->xchg.forked) return PVAE_OK;
   CK(cudaEventRecord(h->xchg.ev_fork, st));
   CK(cudaStreamWaitEvent(h->xchg.side, h->xchg.ev_fork, 0));
-  symm_allreduce_kernel<<<h->xchg.ctas, AR_THREADS, 0, h->xchg.side>>>(h->xchg.args);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  CK(cudaGetLastError());
+  CKR(launch_symm(h->xchg.args, h->xchg.ctas, h->xchg.side));
   CK(cudaEventRecord(h->xchg.ev_join, h->xchg.side));
   h->xchg.forked = true;
   h->dev.reserved_sms = h->xchg.ctas;              // the GEMMs launched from here on leave that many SMs to the exchange kernel
@@ -1468,10 +1486,7 @@ int pvae_set_exchange(pvae_handle h, const uint64_t* peer_ptrs_host, uint64_t mu
 int pvae_run_exchange(pvae_handle h, pvae_stream s) {
   if (!h) return fail(PVAE_ERR_INVALID, "null handle");
   if (!h->xchg.on) return PVAE_OK;
-  symm_allreduce_kernel<<<h->xchg.ctas, AR_THREADS, 0, (cudaStream_t)s>>>(h->xchg.args);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  CK(cudaGetLastError());
-  return PVAE_OK;
+  return launch_symm(h->xchg.args, h->xchg.ctas, (cudaStream_t)s);
 }
 
 int pvae_set_deterministic(pvae_handle h, int enable) {
@@ -1668,10 +1683,9 @@ int pvae_symm_allreduce(const uint64_t* peer_ptrs_host, uint64_t multicast_ptr, 
   a.mc = reinterpret_cast<float*>(multicast_ptr);
   a.rank = rank; a.world = world; a.off = offset_elems; a.count = count_elems; a.flags_off = flags_offset_elems;
   a.scale = 1.f / (float)world;
-  symm_allreduce_kernel<<<AR_CTAS, AR_THREADS, 0, (cudaStream_t)s>>>(a);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  CK(cudaGetLastError());
-  return PVAE_OK;
+  static const int env_ctas = [] { const char* e = getenv("PVAE_SYMM_CTAS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= AR_CTAS ? v : 0; }();
+  const int ctas = env_ctas ? env_ctas : (symm_bulk() && !a.mc ? AR_CTAS / 2 : AR_CTAS);      // (bulk copies: 32 CTAs move as much as 64)
+  return launch_symm(a, ctas, (cudaStream_t)s);
 }
 
 int64_t pvae_symm_flag_elems(void) { return (int64_t)AR_CTAS * AR_MAX_RANKS + AR_CTAS; }

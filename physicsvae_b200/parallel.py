@@ -5,8 +5,8 @@ range of the model's gradient pool) equals the gradient of the global mean loss 
 
 The all-reduce itself: when the ranks share one NVLink / NVSwitch node the gradient pool is a SYMMETRIC allocation
 (torch.distributed._symmetric_memory: the same buffer mapped into every peer) and the exchange is the library's own single
-kernel over peer memory (pvae_symm_allreduce, include/pvae_sm100.h: device-side rank barrier, rank r reduces slice r with peer
-loads -- or multimem.ld_reduce through the switch -- and stores it into every replica).  torch.distributed's NCCL all-reduce
+kernel over peer memory (pvae_symm_allreduce, include/pvae_sm100.h: device-side rank barrier, rank r reduces slice r -- pulled from
+the peers by the bulk-copy engine, by plain peer loads, or by multimem.ld_reduce through the switch -- and stores it into every replica).  torch.distributed's NCCL all-reduce
 (gloo in the CPU tests) is the fallback and the parity path (PVAE_SYMM_AR=0); torch.distributed is plumbing -- rendezvous,
 broadcast of the initial parameters, barriers."""
 import ctypes as C
@@ -157,7 +157,9 @@ def symmetric_pool_factory():
                 print("[physicsvae_b200] symmetric gradient pool unavailable (%s); using NCCL all-reduce" % repr(e)[:160], file=sys.stderr)
             return torch.zeros(n, dtype=torch.float32, device=device)
         _symm_pools[:] = [p for p in _symm_pools if p.buf is not None][-3:] + [pool]      # keep the last few alive (engines get re-created)
-        _symm_note.update(kind="symm-multimem" if pool.mc else "symm-p2p", why="multicast available" if pool.has_multicast else "no multicast binding")
+        bulk = os.environ.get("PVAE_SYMM_BULK", "1") != "0"       # (read by the library: bulk-copy engine moves the slices, the default)
+        _symm_note.update(kind="symm-multimem" if pool.mc else ("symm-p2p-bulk" if bulk else "symm-p2p"),
+                          why="multicast available" if pool.has_multicast else "no multicast binding")
         return pool.view
     return factory
 
@@ -168,7 +170,7 @@ def pool_of(t):
 
 
 def allreduce_kind():
-    """What the gradient exchange of this job runs on: "symm-p2p" / "symm-multimem" (the library's own kernel over peer memory),
+    """What the gradient exchange of this job runs on: "symm-p2p-bulk" / "symm-p2p" / "symm-multimem" (the library's own kernels over peer memory),
     "nccl" / "gloo" (torch.distributed), and why."""
     return dict(_symm_note)
 
