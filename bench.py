@@ -339,22 +339,22 @@ def time_steps(tr, steps, warmup, world, dev, sampler=None):
 
 def probe_kernel_ms(tr, kev, groups, per_group, first=None):
     """Duration of the engine's launch sequence INSIDE the product's step graph: two external CUDA events recorded as nodes of
-    the graph around pvae_{world,vae}_step.  Each sample is the last replay of a group of `per_group` back-to-back replays;
-    `first` is the sample the timed region itself left behind (its last replay).  Returns the median (a group that starts on
-    an idle, clock-gated GPU reads a few percent long) and the spread."""
-    samples = [first] if first else []
+    the graph around pvae_{world,vae}_step.  `first` is the sample the timed region itself left behind (its last replay): that is
+    the number reported -- it belongs to the regime `value` was measured in.  Further samples (each the last replay of a group of
+    `per_group` back-to-back replays after a synchronize) show the spread; their median is the fallback when `first` is missing."""
+    samples = []
     for _ in range(groups):
         tr.train_steps(per_group)
         torch.cuda.synchronize()
         v = kev[0].elapsed_time(kev[1])
         if v > 0:
             samples.append(v)
-    if not samples:
+    if not samples and not first:
         return None, None
     srt = sorted(samples)
-    med = srt[len(srt) // 2] if len(srt) % 2 else 0.5 * (srt[len(srt) // 2 - 1] + srt[len(srt) // 2])
-    return med, {"n": len(srt), "min_ms": srt[0], "median_ms": med, "max_ms": srt[-1], "last_replay_of_timed_region_ms": first,
-                 "replays_per_sample": per_group}
+    med = (srt[len(srt) // 2] if len(srt) % 2 else 0.5 * (srt[len(srt) // 2 - 1] + srt[len(srt) // 2])) if srt else None
+    return (first or med), {"last_replay_of_timed_region_ms": first, "later_groups": {"n": len(srt), "min_ms": srt[0] if srt else None, "median_ms": med,
+                                                                                       "max_ms": srt[-1] if srt else None, "replays_per_sample": per_group}}
 
 
 def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local, dims=None):

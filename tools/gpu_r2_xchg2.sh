@@ -18,10 +18,16 @@ except Exception as e:
     import subprocess; print(subprocess.run(["tail", "-n", "15", "gpurun_out/x2_n${N}_${label}_$TAG.log"], capture_output=True, text=True).stdout)
 PY
 }
-for cfg in "world" "wide --config wide --batch 16384" "vae --phase vae"; do
+IFS=';' read -ra CFGS <<< "${CFGS:-world;wide --config wide --batch 16384;vae --phase vae}"
+for cfg in "${CFGS[@]}"; do
   set -- $cfg; name=$1; shift
-  run ${name}_regs "$@" -- PVAE_SYMM_BULK=0
-  run ${name}_bulk "$@" -- PVAE_SYMM_BULK=1
-  run ${name}_bulk_ovl "$@" -- PVAE_SYMM_BULK=1 PVAE_OVERLAP=1
-  run ${name}_bulk_ovl4 "$@" -- PVAE_SYMM_BULK=1 PVAE_OVERLAP=1 PVAE_OVERLAP_SMS=4
+  for m in ${MODES:-regs bulk bulk_ovl bulk_ovl4}; do
+    case $m in
+      regs) run ${name}_regs "$@" -- PVAE_SYMM_BULK=0 ;;
+      bulk) run ${name}_bulk "$@" -- PVAE_SYMM_BULK=1 ;;
+      bulk_ovl) run ${name}_bulk_ovl "$@" -- PVAE_SYMM_BULK=1 PVAE_OVERLAP=1 ;;
+      bulk_ovl4) run ${name}_bulk_ovl4 "$@" -- PVAE_SYMM_BULK=1 PVAE_OVERLAP=1 PVAE_OVERLAP_SMS=4 ;;
+      nccl) run ${name}_nccl "$@" -- PVAE_SYMM_AR=0 ;;
+    esac
+  done
 done
