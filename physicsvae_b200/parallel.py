@@ -114,9 +114,9 @@ class SymmetricPool(object):
         early None switches it off.  Returns True when armed."""
         from . import _abi
         ctas = int(os.environ.get("PVAE_OVERLAP_SMS", "8"))
-        # Opt-in (PVAE_OVERLAP=1).  Measured: at N = 2 the overlap hides ~8 us per step (0.581 vs 0.589 ms world, 0.925 vs 0.933 VAE); at
-        # N = 8 it LOSES (0.612 vs 0.600 ms world, 0.634 vs 0.411 on the wide config's 24 MB of gradients): eight CTAs of
-        # latency-bound peer loads move ~170 GB/s, the exchange outlasts the GEMMs it hides behind and those run on 140 SMs meanwhile.
+        # Opt-in (PVAE_OVERLAP=1).  Measured with the bulk-copy exchange kernel (profiles/r02_scaling.md): nothing at N = 2 (0.5933 vs
+        # 0.5915 ms world), -1.3 % on the world step at N = 8 (0.5895 vs 0.5973), a LOSS on the wide config's 24 MB of gradients
+        # (0.388 vs 0.379 ms at N = 8): the GEMMs give up 8 SMs for longer than the exchange saves.
         if early is None or os.environ.get("PVAE_OVERLAP", "0") != "1" or not self.contains(early):
             _abi.check(self.lib.pvae_set_exchange(engine._h, None, 0, 0, 0, 0, 0, 0, 0))
             return False
