@@ -136,7 +136,7 @@ struct Device {
   int pdl = 1;            // PVAE_PDL=0: plain stream-ordered GEMM launches
   int snake = 1;          // PVAE_SNAKE=0: every GEMM walks the batch front to back (see batch_direction)
   int cs_mma = 0;         // PVAE_CS_MMA=1: bias-gradient column sums on mma.sync instead of lane adds (slower, kept for experiments)
-  int prefetch = 0;       // PVAE_PREFETCH: L2 prefetch distance of the streamed operands in units (0 = off, -1 = by K depth); measured slower (profiles/r02_bench.md), off
+  int prefetch = 0;       // PVAE_PREFETCH (debug-hooks build only): L2 prefetch distance of the streamed operands in units (-1 = by K depth); measured slower (profiles/r02_bench.md)
   int fast_epi = 1;       // PVAE_FAST_EPI=0: never use the lean ReLU store / dgrad epilogue (A/B experiments)
   int small_fwd = 1;      // PVAE_SMALL_FWD=0: batches <= 16 of the inference API also take the tensor-core path
   int reserved_sms = 0;   // SMs the GEMM grids leave free while the gradient exchange of a data-parallel step runs beside them (pvae_set_exchange)

@@ -101,7 +101,7 @@ struct GemmParams {
   int32_t dbg;                     // PVAE_DBG bit mask: skip parts of the TMA epilogue (timing experiments only, results are wrong)
   int32_t reverse;                 // walk the batch dimension from its far end (see UnitWalk)
   int32_t cs_mma;                  // bias-gradient column sums: 1 = mma.sync (ones . slab), 0 = lanes add columns, -1 = by K depth
-  int32_t pf_dist;                 // L2 prefetch of the streamed operand(s): units ahead of the one being loaded (0 = off)
+  int32_t pf_dist;                 // (debug build only) L2 prefetch of the streamed operand(s): units ahead of the one being loaded (0 = off)
   int32_t pf_b;                    // prefetch B as well (weight gradients stream both operands; forward / dgrad weights live in L2)
   int32_t cg;                      // 1, or 2: CTA pairs on adjacent M tiles run one 256-row tcgen05.mma.cta_group::2 (kernel template CG)
   const int32_t* row_cursor;       // device int (first row of the current mini-batch in the resident buffers) or null
@@ -776,9 +776,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
         }
       }
     };
+    // (experiment, compiled only into the -DPVAE_DEBUG_HOOKS build: measured 10-15 % slower, profiles/r02_bench.md)
     UnitWalk wpf = w;                                      // runs pf_dist units ahead of w
     int upf = unit0;
-    if (p.pf_dist > 0) {
+    if (DEBUG_HOOKS && p.pf_dist > 0) {
       for (int d = 0; d < p.pf_dist; ++d) {
         if (d > 0 && upf < total_units) prefetch_unit(wpf);   // units 1 .. pf_dist-1: nobody prefetches them later
         upf += unit_stride; wpf.next();
@@ -790,7 +791,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pvae_gemm_kernel(const __grid_
       const int it_end = w.it_end();
       int it = w.it_begin();
       const int b_n = p.b_n0 + n_tile * bn + crank * bn_loc;
-      if (p.pf_dist > 0) {
+      if (DEBUG_HOOKS && p.pf_dist > 0) {
         if (upf < total_units) prefetch_unit(wpf);
         upf += unit_stride; wpf.next();
       }

@@ -7,7 +7,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "physicsvae_b200", "lib", "libpvae_sm100.so")
-KEY = ["UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "UTMALDG", "UTMASTG", "UTMACMDFLUSH", "UBLKCP", "SYNCS", "ELECT", "UCGABAR", "HMMA", "LDSM",
+KEY = ["UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF", "UTMACMDFLUSH", "UBLKCP", "SYNCS", "ELECT", "UCGABAR", "HMMA", "LDSM",
        "FADD2", "REDG", "RED", "ATOMG", "ATOM", "F2FP", "PRMT", "MEMBAR", "ACQBULK", "LDGDEPBAR", "HGMMA"]
 
 
@@ -46,7 +46,8 @@ def main():
     what = {"UTCHMMA": "`tcgen05.mma.kind::f16` (5th-gen tensor core, accumulator in TMEM)", "UTCBAR": "`tcgen05.commit` -> mbarrier (`.2CTA.MULTICAST`: both CTAs of a pair)",
             "UTCATOMSWS": "`tcgen05.alloc` / `dealloc` (TMEM columns)", "LDTM": "`tcgen05.ld` (TMEM -> registers, epilogue)",
             "UTMALDG": "TMA tile load `cp.async.bulk.tensor.3d` (`.2CTA`: pair-addressed barrier)", "UTMASTG": "TMA tile store (epilogue slabs)",
-            "UTMACMDFLUSH": "`cp.async.bulk.commit_group`", "SYNCS": "mbarrier init / arrive / expect_tx / try_wait", "ELECT": "`elect.sync` (one issuing lane)",
+            "UTMACMDFLUSH": "`cp.async.bulk.commit_group`", "UBLKCP": "`cp.async.bulk` (untiled bulk copy; `.S.G`: global -> shared, the gradient exchange pulling peer slices; `.G.S`: shared -> global)",
+            "UTMAPF": "`cp.async.bulk.prefetch.tensor` (the optional L2 operand prefetch, off by default)", "SYNCS": "mbarrier init / arrive / expect_tx / try_wait", "ELECT": "`elect.sync` (one issuing lane)",
             "UCGABAR": "cluster barrier (CTA pair)", "HMMA": "`mma.sync` (legacy tensor path: only the optional PVAE_CS_MMA=1 column-sum experiment)",
             "LDSM": "`ldmatrix` (same experiment)", "FADD2": "`add.f32x2` (packed fp32 adds: bias, column sums)", "F2FP": "`cvt.rn(.relu).bf16x2.f32`",
             "PRMT": "`prmt` (ReLU mask expansion, byte sign replication)", "REDG": "`red.global.add.f32` (split-K weight gradients, bias gradients)",
