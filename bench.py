@@ -337,24 +337,31 @@ def time_steps(tr, steps, warmup, world, dev, sampler=None):
     return ms, (sampler.stop(t0, t1) if sampler else None)
 
 
-def probe_kernel_ms(tr, kev, groups, per_group, first=None):
+def probe_kernel_ms(tr, kev, groups, per_group, step_ms, first=None):
     """Duration of the engine's launch sequence INSIDE the product's step graph: two external CUDA events recorded as nodes of
-    the graph around pvae_{world,vae}_step.  `first` is the sample the timed region itself left behind (its last replay): that is
-    the number reported -- it belongs to the regime `value` was measured in.  Further samples (each the last replay of a group of
-    `per_group` back-to-back replays after a synchronize) show the spread; their median is the fallback when `first` is missing."""
-    samples = []
+    the graph around pvae_{world,vae}_step.  The events only ever hold the LAST replay, and the step time is not stationary (the
+    board ramps towards its power cap during a long timed region), so one replay cannot stand for the region's average.  What
+    is stable is the SHARE of the step the launch sequence takes: each sample = in-graph duration of the last replay of a group
+    of `per_group` back-to-back replays / the CUDA-event average step of the same group.  Reported: median share x `step_ms` (the
+    timed region's average step).  `first` = the raw in-graph duration of the timed region's own last replay, kept for reference."""
+    shares, raw = [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(groups):
+        e0.record()
         tr.train_steps(per_group)
+        e1.record()
         torch.cuda.synchronize()
         v = kev[0].elapsed_time(kev[1])
-        if v > 0:
-            samples.append(v)
-    if not samples and not first:
-        return None, None
-    srt = sorted(samples)
-    med = (srt[len(srt) // 2] if len(srt) % 2 else 0.5 * (srt[len(srt) // 2 - 1] + srt[len(srt) // 2])) if srt else None
-    return (first or med), {"last_replay_of_timed_region_ms": first, "later_groups": {"n": len(srt), "min_ms": srt[0] if srt else None, "median_ms": med,
-                                                                                       "max_ms": srt[-1] if srt else None, "replays_per_sample": per_group}}
+        g = e0.elapsed_time(e1) / per_group
+        if v > 0 and g > 0:
+            shares.append(v / g)
+            raw.append(v)
+    if not shares:
+        return first, {"last_replay_of_timed_region_ms": first}
+    srt = sorted(shares)
+    share = srt[len(srt) // 2] if len(srt) % 2 else 0.5 * (srt[len(srt) // 2 - 1] + srt[len(srt) // 2])
+    return share * step_ms, {"share_of_step": {"n": len(srt), "min": srt[0], "median": share, "max": srt[-1], "replays_per_group": per_group},
+                             "raw_last_replay_ms": {"timed_region": first, "groups_min": min(raw), "groups_max": max(raw)}}
 
 
 def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, local, dims=None):
@@ -382,7 +389,7 @@ def measure_phase(args, cfg, tr, phase, B, world, rank, dev, steps, warmup, loca
     ms, clocks = time_steps(tr, steps, warmup, world, dev, ClockSampler(local) if rank == 0 else None)
     # the events now hold the LAST replay of the timed region (barrier() synchronised): the first kernel sample
     first = kev[0].elapsed_time(kev[1]) if kev else None
-    kernel_ms, kernel_samples = probe_kernel_ms(tr, kev, 10, max(5, min(steps, 20)), first if first and first > 0 else None) if kev else (None, None)
+    kernel_ms, kernel_samples = probe_kernel_ms(tr, kev, 10, max(5, min(steps, 20)), ms / steps, first if first and first > 0 else None) if kev else (None, None)
     # not GEMMs: loss finalisation, fused Adam (one per trained net), cursor advance; VAE phase also reparameterisation fwd / bwd;
     # N > 1 with the symmetric gradient pool: the library's peer-memory all-reduce kernel
     from physicsvae_b200 import parallel as _par
@@ -412,7 +419,7 @@ def measure_sustained(res, tr, world, rank, dev, local, seconds):
     t1 = time.time()
     sms = max_over_ranks(e0.elapsed_time(e1), dev, world)
     first = kev[0].elapsed_time(kev[1]) if kev else None
-    k_sus = probe_kernel_ms(tr, kev, 8, 50, first if first and first > 0 else None)[0] if kev else None
+    k_sus = probe_kernel_ms(tr, kev, 8, 50, sms / n_sus, first if first and first > 0 else None)[0] if kev else None
     res["sustained"] = {"steps": n_sus, "ms_per_step": sms / n_sus, "value": B * world * n_sus / (sms * 1e-3), "kernel_ms_per_step": k_sus,
                         "clocks": sampler.stop(t0, t1) if sampler else None}
 
@@ -445,7 +452,8 @@ def finish_phase(args, res, tr):
                 "traffic": traffic, "kernel": "pvae_gemm_kernel", "launches_per_step": res["gemm_launches"],
                 "avg_launch_ms": kernel_ms / gl, "algorithmic_flops_per_launch": flops_step / gl,
                 "kernel_ms_per_step": kernel_ms, "kernel_ms_samples": res.get("kernel_samples"), "algorithmic_flops_per_step": flops_step,
-                "timing": "external CUDA events recorded as nodes of the product's step graph around the engine's launch sequence",
+                "timing": "share of the step between two external CUDA events recorded as nodes of the product's step graph around the engine's "
+                          "launch sequence (median over groups of replays) x the timed region's average step",
                 "whole_step_tflops": flops_step / (res["ms_per_step"] * 1e-3) / 1e12}
     out = {k: res[k] for k in ("value", "ms_per_step", "steps", "clocks", "sustained", "launches_per_step", "config")}
     out["roofline"] = roof
