@@ -49,7 +49,6 @@ def parse():
     ap.add_argument("--config", default="default", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=65536, help="mini-batch rows PER GPU")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
-    ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows per step of the CPU arm (0: the workload's batch, shrunk only if the run would take too long)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all cores; 1 with --cpu-sample 256 = configs[0])")
